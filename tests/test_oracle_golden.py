@@ -1,0 +1,62 @@
+"""Pin the oracle to outputs of the REAL reference classes (fixtures made by tests/golden/make_golden.py)."""
+import pytest
+import torch
+
+from oracle import clipseg as OC
+from tests.golden_cases import CASES, TINY, learner_state, load_case, load_weights
+
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference(name):
+    w = load_weights()
+    d, learner, head = load_case(name)
+    learner = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in learner.items()}
+    head = {k: v.clone().requires_grad_(True) for k, v in head.items()}
+    st = learner_state(name, learner)
+    logits = OC.net_forward(w, TINY, st, head, d["input_ids"], d["attention_mask"], d["image"])
+    assert logits.shape == d["logits"].shape
+    err = (logits - d["logits"]).abs().max().item()
+    assert err <= TOL, f"logits max-abs {err}"
+    (logits * d["grad_weight"]).sum().backward()
+    # reference state_dict lists shared (unified) projector tensors once per depth; parameters() dedups.
+    for k, v in d.items():
+        if k.startswith("learner_grad/"):
+            pk = k[len("learner_grad/"):]
+            has = bool(d[f"learner_hasgrad/{pk}"])
+            g = learner[pk].grad
+            if not has:
+                assert g is None or g.abs().max() == 0, f"{pk}: reference gives no grad"
+                continue
+            # unified projection: the reference accumulates all depths into the one shared tensor
+            if CASES[name].get("proj_style") == "lora" and "projection_layers." in pk:
+                tail = pk.split(".", 2)[2]
+                g = sum(learner[k2].grad for k2 in learner if k2.startswith("projection_layers.") and
+                        k2.split(".", 2)[2] == tail and learner[k2].grad is not None)
+            scale = max(1.0, v.abs().max().item())
+            gerr = (g - v).abs().max().item() / scale
+            assert gerr <= 5e-5, f"{pk}: grad rel err {gerr}"
+        if k.startswith("head_grad/"):
+            pk = k[len("head_grad/"):]
+            has = bool(d[f"head_hasgrad/{pk}"])
+            g = head[pk].grad
+            if not has:
+                assert g is None or g.abs().max() == 0, f"{pk}: reference gives no grad"
+            else:
+                scale = max(1.0, v.abs().max().item())
+                assert (g - v).abs().max().item() / scale <= 5e-5, pk
+
+
+def test_known_quirks():
+    """Reference control-flow quirks the oracle (and the product) must keep."""
+    d, _, _ = load_case("vpt_d12_n3")
+    # VPT depth 12 with the 10-layer early exit: ctx[0] is concatenated, ctx[1..10] overwrite after layers
+    # 1..10 (the write after layer 10 still reaches the decoder through the last tap) -> only ctx[11] is dead.
+    g = d["learner_grad/context_vectors"]
+    assert g[11:].abs().max() == 0 and all(g[i].abs().max() > 0 for i in range(11))
+    # VPT ignores residual_ratio; CoOp ignores the whole additive layer
+    assert not bool(d["head_hasgrad/residual_ratio"])
+    d, _, _ = load_case("coop_d1_n4")
+    assert not bool(d["head_hasgrad/additive_decoder_layer.1.weight"])
+    assert not bool(d["head_hasgrad/residual_ratio"])
