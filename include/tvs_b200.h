@@ -1,0 +1,190 @@
+/* tvs_b200.h - C ABI of the B200-native TuneVLSeg prompt-tuning hot path (libtvs_b200.so).
+ *
+ * The reference (naamiinepal/tunevlseg) has NO native / FFI layer: its hot path is Python calling ATen
+ * library kernels through transformers / monai / torchmetrics.  This header is
+ * therefore the boundary a maintainer would bind from the reference's Python wrappers (ctypes stub in
+ * INTEGRATION.md); every entry cites the reference call site(s) (relative to /root/reference, or to
+ * site-packages/transformers/models/clipseg/modeling_clipseg.py = "hf:") whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     never allocates, and returns 0 on success or a negative code (message: tvs_last_error());
+ *   - row-major everywhere; "ld*" are leading dimensions in ELEMENTS;
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t), f32 = float, i64 = int64_t, u8 = uint8_t;
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry fails.
+ */
+#ifndef TVS_B200_H
+#define TVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVS_ABI_VERSION 1
+
+int tvs_version(void);
+const char* tvs_last_error(void);
+/* number of kernels launched by this library in the calling process since load (bench.py: gpu_launches) */
+int64_t tvs_launch_count(void);
+/* 0 when the current device is sm_100 and the library can run on it */
+int tvs_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM  C[M,N] = epilogue( A[M,K] * W[N,K]^T )  on tcgen05 / TMEM, operands by TMA, fp32 accumulate.
+ * Replaces every nn.Linear on the path (hf::297-300 q/k/v/out_proj, hf::345-353 fc1/fc2, decoder
+ * reduces / film hf::551-552,582-584, text/visual projection) and, with a transposed weight copy,
+ * their dgrad (frozen backbone: there is no wgrad).
+ *
+ * epilogue, in this order (each step optional):
+ *     v  = acc (+ bias[n])
+ *     pre_bf16[m,n] = v                      save the pre-activation for the backward pass
+ *     v  = act(v)                            act: TVS_ACT_*
+ *     v += residual_f32[m,n]
+ *     out_f32[m,n] = v ; out_bf16[m,n] = v
+ * TVS_ACT_DQGELU / TVS_ACT_DRELU multiply v by act'(aux_bf16[m,n]) (aux = saved pre-activation, or the
+ * post-ReLU activation for DRELU) - the dgrad-through-activation epilogue.
+ * Requirements: K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, A and W 16-byte aligned.
+ * ------------------------------------------------------------------------------------------------ */
+enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4 };
+
+typedef struct tvs_gemm_args {
+    const void* A;  int64_t lda;           /* bf16 [M,K] */
+    const void* W;  int64_t ldw;           /* bf16 [N,K] */
+    int32_t M, N, K;
+    const float* bias;                     /* f32 [N] or NULL */
+    const float* residual; int64_t ldr;    /* f32 [M,N] or NULL (may alias out_f32) */
+    float* out_f32;  int64_t ldo32;        /* f32 [M,N] or NULL */
+    void*  out_bf16; int64_t ldo16;        /* bf16 [M,N] or NULL */
+    void*  pre_bf16; int64_t ldpre;        /* bf16 [M,N] or NULL */
+    const void* aux_bf16; int64_t ldaux;   /* bf16 [M,N], required by TVS_ACT_D* */
+    int32_t act;
+    int32_t tile_n;                        /* 0 = auto, else 64 / 128 / 256 */
+} tvs_gemm_args;
+
+int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension D (eps inside the sqrt), one warp per row.
+ * Replaces nn.LayerNorm at hf::362-365 (layer_norm1/2), hf::782 (pre_layrnorm), hf::636
+ * (final_layer_norm), hf::784 (post_layernorm), decoder post-norms hf::395-398.
+ * fwd: y = (x - mean) * rstd * gamma + beta ; saves mean/rstd (f32 [M]) when non-NULL.
+ * bwd: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma   (no dgamma/dbeta: frozen)
+ *      dx_out_f32 = dx (+ dx_add_f32) ; dx_out_bf16 = same, rounded.  dy is bf16 (dy_bf16) or f32 (dy_f32).
+ * D % 4 == 0, D <= 1024.
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int32_t D,
+                      float* y_f32, void* y_bf16, float* mean, float* rstd, void* stream);
+int tvs_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
+                      const float* mean, const float* rstd, const float* dx_add_f32, int64_t M, int32_t D,
+                      float* dx_out_f32, void* dx_out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention, flash style (scores never leave the SM), fp32 softmax.
+ * Replaces eager_attention_forward hf::256-276 as called from CLIPSegAttention hf::302-338.
+ * qkv: bf16 [B*S, 3*H*hd]  (columns: Q | K | V, each head-major; the d^-0.5 scale is pre-folded into Wq)
+ * out: bf16 [B*S, H*hd] ; lse: f32 [B,H,S] (natural-log-sum-exp of the row, saved for the backward)
+ * causal != 0: key j > query i is masked (text tower, base_multimodal_clipseg.py:205-209);
+ * key_mask: u8 [B,S] 1 = attend, 0 = padding, or NULL (base_multimodal_clipseg.py:212-222).
+ * hd is 64 (towers) or 16 (decoder).  bwd writes dqkv (same layout as qkv); delta is f32 [B,H,S] scratch.
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t hd, int32_t causal,
+                 const uint8_t* key_mask, void* out, float* lse, void* stream);
+int tvs_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
+                 int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vision embedding pieces (hf::196-212 CLIPSegVisionEmbeddings.forward; base_multimodal_clipseg.py:449-465)
+ * im2col: image f32 [B,3,H,W] -> bf16 [B*g*g, 3*P*P] (column order c,py,px = Conv2d weight flattening)
+ * assemble: h[b,0] = cls + pos[0]; h[b,1+p] = patches[b*g*g+p] + pos[1+p]; h[b,1+g*g+j] = ctx[(b),j]
+ *           (ctx_batch_stride = 0 for a shared prompt, n*D for per-sample prompts); n may be 0.
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_im2col_patches(const float* image, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, void* out_bf16,
+                       void* stream);
+int tvs_vision_assemble(const float* patches, const float* cls, const float* pos, const float* ctx,
+                        int64_t ctx_batch_stride, int32_t B, int32_t G2, int32_t n, int32_t D, float* h,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Deep-prompt row replacement and its backward (base_visual_learner.py:18-23: h[:, -n:] = ctx;
+ * coop_context_learner.py:124-134: h[:, 1:n+1] = ctx).  x: f32 [B,S,D]; rows row0..row0+n-1.
+ * grad: dctx[(b),j,:] (+)= sum_b dx[b,row0+j,:]  then dx rows are zeroed (the overwritten values have no
+ * upstream).  ctx_batch_stride = 0 -> reduced over the batch, else per-sample.
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_prompt_overwrite(float* x, void* x_bf16, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t n,
+                         const float* ctx, int64_t ctx_batch_stride, void* stream);
+int tvs_prompt_grad(float* dx, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t n, float* dctx,
+                    int64_t ctx_batch_stride, int32_t zero_rows, void* stream);
+
+/* f32 -> bf16 copy (n elements, n % 4 == 0) */
+int tvs_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* y (+)= x for f32 buffers (gradient merge at the decoder taps) */
+int tvs_add_f32(float* y, const float* x, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FiLM conditioning (base_clipseg.py:111-115): y[b,s,:] = mul[b,:] * x[b,s,:] + add[b,:]  (f32)
+ * bwd: dx = mul * dy ; dmul[b,:] = sum_s dy * x ; dadd[b,:] = sum_s dy
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_film_fwd(const float* x, const float* mul, const float* add, int32_t B, int32_t S, int32_t D, float* y,
+                 void* y_bf16, void* stream);
+int tvs_film_bwd(const float* dy, const float* x, const float* mul, int32_t B, int32_t S, int32_t D, float* dx,
+                 float* dmul, float* dadd, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder head (base_clipseg.py:132-157, vpt_clipseg.py:287-304; hf::573-575 ConvTranspose2d(64,1,P,P)):
+ *   tconv: f32 [B*g*g, P*P]  = feat @ Wt^T (from tvs_gemm_bf16; no bias)     -> pixel shuffle + bias_t
+ *   addmap: f32 [B*g*g, KK]  = feat @ Wa^T  (KK = k*k taps of the additive Conv2d, contracted over the
+ *           channels at LOW resolution; bilinear upsampling and the k x k replicate-padded stencil commute
+ *           with that contraction, so the (B,64,H,W) upsampled tensor is never materialised)
+ *   logits[b,Y,X] = wa * (tconv + bias_t) + wb * (sum_k up(addmap_k)[clamp(Y+ky-k/2), clamp(X+kx-k/2)] + bias_a)
+ *   blend: 0 none (wa=1, wb=0), 1 ratio (wa = 1-r, wb = r), 2 add (wa = wb = 1).  r read from *ratio.
+ * bwd: dtconv (bf16 [B*g*g, P*P]) = wa * dlogits ; daddmap (f32 [B*g*g, KK]) ; dbias_a, dratio (f32 scalars,
+ *      accumulated with atomics into zero-initialised outputs).
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_head_fwd(const float* tconv, int64_t ld_tconv, const float* addmap, int64_t ld_addmap, const float* bias_t,
+                 const float* bias_a, const float* ratio, int32_t blend, int32_t B, int32_t G, int32_t P,
+                 int32_t ksize, float* logits, float* add_out /* f32 [B,H,W] additive branch incl. bias, or NULL */,
+                 void* stream);
+int tvs_head_bwd(const float* dlogits, const float* tconv, int64_t ld_tconv, const float* add_out,
+                 const float* bias_t, const float* ratio, int32_t blend, int32_t B, int32_t G, int32_t P,
+                 int32_t ksize, void* dtconv_bf16, int64_t ld_dtconv, float* daddmap, int64_t ld_daddmap,
+                 float* dbias_a, float* dratio, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused Dice+BCE loss and Dice / IoU counters in ONE pass over logits and mask.
+ * Replaces monai.losses.DiceCELoss(sigmoid=True, lambda_dice, lambda_ce) (configs/model/maple_clipseg.yaml:29-33),
+ * torch.sigmoid + mask.long() (src/models/image_text_mask_module.py:103-107) and the update step of
+ * torchmetrics Dice(threshold, average="samples") / JaccardIndex(task="binary") (:118-119, :284-298).
+ *   logits, mask: f32 [B, N]   (N = H*W; mask in [0,1], target = (int64)mask)
+ *   parts:  f64 [B,4]  = { sum p*y, sum p, sum y, sum bce }      (p = sigmoid(logit))
+ *   counts: i64 [B,3]  = { tp, fp, fn } with p >= threshold       (Dice, bit-exact)
+ *   confmat:i64 [4]    = { tn, fp, fn, tp } with p >  threshold, ACCUMULATED into the buffer (IoU state)
+ *   loss:   f32 [1]    = lambda_dice * mean_b(1 - (2I+1e-5)/(P+G+1e-5)) + lambda_ce * mean bce
+ *   scratch: >= tvs_dicebce_scratch_bytes(B, N) bytes
+ * bwd: dlogits[b,i] = gscale[0] * dloss/dlogit  (gscale: f32 [1] device scalar = upstream grad)
+ * ------------------------------------------------------------------------------------------------ */
+int64_t tvs_dicebce_scratch_bytes(int32_t B, int64_t N);
+int tvs_dicebce_metrics_fwd(const float* logits, const float* mask, int32_t B, int64_t N, float threshold,
+                            float lambda_dice, float lambda_ce, double* parts, int64_t* counts, int64_t* confmat,
+                            float* loss, void* scratch, void* stream);
+int tvs_dicebce_bwd(const float* logits, const float* mask, const double* parts, const float* gscale, int32_t B,
+                    int64_t N, float lambda_dice, float lambda_ce, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AdamW over one flat f32 buffer (torch.optim.AdamW semantics; configs/model/maple_clipseg.yaml:36-39).
+ * grad is multiplied by grad_scale first (1/world after the NCCL sum).  step is 1-based.
+ * step_dev / lr_dev: optional DEVICE scalars that override step / lr, so that a captured CUDA graph can be
+ * replayed with an advancing step (tvs_counter_inc bumps the device counter from inside the graph).
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   const int32_t* step_dev, const float* lr_dev, void* stream);
+int tvs_counter_inc(int32_t* counter_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVS_B200_H */

@@ -1,0 +1,61 @@
+// Shared device/host helpers for the tunevlseg_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace tvs {
+
+// ---- error plumbing: every C-ABI entry returns 0 on success, <0 on error; message via tvs_last_error() ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define TVS_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::tvs::set_error(__VA_ARGS__);     \
+            return -1;                         \
+        }                                      \
+    } while (0)
+
+#define TVS_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::tvs::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));            \
+            return -2;                                                                   \
+        }                                                                                \
+    } while (0)
+
+int sm_count();
+
+// ---- small device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+    __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+    return __bfloat1622float2(t);
+}
+__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// quick_gelu(x) = x * sigmoid(1.702 x)   (transformers ACT2FN["quick_gelu"])
+__device__ __forceinline__ float quick_gelu(float x) { return x * sigmoidf_fast(1.702f * x); }
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+    float s = sigmoidf_fast(1.702f * x);
+    return s * (1.0f + 1.702f * x * (1.0f - s));
+}
+
+}  // namespace tvs

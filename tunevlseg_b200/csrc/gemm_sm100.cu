@@ -1,0 +1,461 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * W[N,K]^T), bf16 in, fp32 accumulate.
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0 (one lane)  TMA producer: A tile 128x64 and W tile BNx64 per k-block into a STAGES-deep smem ring
+//                      (128-byte swizzle), completion on `full[stage]` mbarriers;
+//   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (128 x BN x 16, cta_group::1) per k-block, accumulator in
+//                      TMEM (two buffers of BN columns so the epilogue of tile i overlaps the MMAs of tile i+1),
+//                      tcgen05.commit releases the smem slot (`empty[stage]`) and publishes `tmem_full[buf]`;
+//   warp 2             TMEM allocate / free;
+//   warps 4-7          epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / activation /
+//                      activation-gradient / residual, stores fp32 and/or bf16 rows.
+// Tail handling: TMA zero-fills rows >= M, >= N and columns >= K; the epilogue predicates its stores.
+//
+// Replaces the nn.Linear calls of HF CLIPSeg (modeling_clipseg.py:297-300, :345-353) and their dgrad.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tvs_b200.h"
+
+namespace tvs {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmEpilogue {
+    const float* bias;
+    const float* residual;
+    long long ldr;
+    float* out_f32;
+    long long ldo32;
+    __nv_bfloat16* out_bf16;
+    long long ldo16;
+    __nv_bfloat16* pre_bf16;
+    long long ldpre;
+    const __nv_bfloat16* aux_bf16;
+    long long ldaux;
+    int act;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 1024B (8 rows x 128B),
+//   [46,48) version = 1 (sm_100), [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue math for one 32-column chunk of one row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0,
+                                               int N) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    const bool full = (col0 + 32 <= N);
+    if (full) {
+        if (ep.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 b = __ldg(b4 + i);
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+        }
+        if (ep.pre_bf16) {
+            uint4* p = reinterpret_cast<uint4*>(ep.pre_bf16 + row * ep.ldpre + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                p[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        }
+        if (ep.act == TVS_ACT_QGELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+        } else if (ep.act == TVS_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        } else if (ep.act == TVS_ACT_DQGELU || ep.act == TVS_ACT_DRELU) {
+            const uint4* a = reinterpret_cast<const uint4*>(ep.aux_bf16 + row * ep.ldaux + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 q = __ldg(a + i);
+                uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 u = unpack_bf16x2(w[j]);
+                    if (ep.act == TVS_ACT_DQGELU) {
+                        v[8 * i + 2 * j] *= quick_gelu_grad(u.x);
+                        v[8 * i + 2 * j + 1] *= quick_gelu_grad(u.y);
+                    } else {
+                        v[8 * i + 2 * j] = u.x > 0.0f ? v[8 * i + 2 * j] : 0.0f;
+                        v[8 * i + 2 * j + 1] = u.y > 0.0f ? v[8 * i + 2 * j + 1] : 0.0f;
+                    }
+                }
+            }
+        }
+        if (ep.residual) {
+            const float4* r4 = reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 r = r4[i];
+                v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+            }
+        }
+        if (ep.out_f32) {
+            float4* o = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ldo32 + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        if (ep.out_bf16) {
+            uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + row * ep.ldo16 + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+        }
+    } else {
+        // ragged N tail (e.g. the 25-tap additive map): scalar, fully predicated
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            int c = col0 + i;
+            if (c < N) {
+                float x = v[i];
+                if (ep.bias) x += __ldg(ep.bias + c);
+                if (ep.pre_bf16) ep.pre_bf16[row * ep.ldpre + c] = __float2bfloat16(x);
+                if (ep.act == TVS_ACT_QGELU) x = quick_gelu(x);
+                else if (ep.act == TVS_ACT_RELU) x = fmaxf(x, 0.0f);
+                else if (ep.act == TVS_ACT_DQGELU) x *= quick_gelu_grad(__bfloat162float(ep.aux_bf16[row * ep.ldaux + c]));
+                else if (ep.act == TVS_ACT_DRELU) x = __bfloat162float(ep.aux_bf16[row * ep.ldaux + c]) > 0.0f ? x : 0.0f;
+                if (ep.residual) x += ep.residual[row * ep.ldr + c];
+                if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = x;
+                if (ep.out_bf16) ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
+                         int N, int K, GemmEpilogue ep) {
+    using L = GemmSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * L::A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m = (M + BM - 1) / BM;
+    const int num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (K + BK - 1) / BK;
+    constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full[0], 1);
+        mbar_init(&tmem_full[1], 1);
+        mbar_init(&tmem_empty[0], 4);
+        mbar_init(&tmem_empty[1], 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, &full_bar[stage]);
+                    tma_load_2d(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN, &full_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * L::A_BYTES));
+                    const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * L::B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;  // TMEM lane quarter this warp may touch = warp % 4
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const long long row = static_cast<long long>(m_blk) * BM + ew * 32 + lane;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c * 32, r);
+                const int col0 = n_blk * BN + c * 32;
+                if (row < M && col0 < N) epilogue_chunk(ep, r, row, col0, N);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle.
+static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    TVS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TVS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
+    return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
+    using L = GemmSmem<BN, STAGES>;
+    CUtensorMap ta, tw;
+    if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.lda, BM)) return rc;
+    if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN)) return rc;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tw, a.M, a.N, a.K, ep);
+    return check_launch("gemm_bf16_tcgen05_kernel");
+}
+
+static int pick_tile_n(int M, int N) {
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    const int sms = sm_count();
+    const int num_m = (M + BM - 1) / BM;
+    auto eff = [&](int bn) {
+        long long tiles = static_cast<long long>(num_m) * ((N + bn - 1) / bn);
+        long long waves = (tiles + sms - 1) / sms;
+        double wave_eff = static_cast<double>(tiles) / static_cast<double>(waves * sms);
+        double pad_eff = static_cast<double>(N) / static_cast<double>(((N + bn - 1) / bn) * bn);
+        // 128x128 tiles read 128 B/clk of smem per MMA (the limit); 128x256 needs 96 B/clk
+        return wave_eff * pad_eff * (bn == 256 ? 1.0 : 0.92);
+    };
+    return eff(256) >= eff(128) ? 256 : 128;
+}
+
+}  // namespace tvs
+
+extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream) {
+    using namespace tvs;
+    TVS_REQUIRE(args != nullptr, "tvs_gemm_bf16: null args");
+    const tvs_gemm_args& a = *args;
+    TVS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "tvs_gemm_bf16: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+    TVS_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0, "tvs_gemm_bf16: K, lda, ldw must be multiples of 8 (K=%d lda=%lld ldw=%lld)",
+                a.K, (long long)a.lda, (long long)a.ldw);
+    TVS_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+                "tvs_gemm_bf16: A and W must be 16-byte aligned");
+    TVS_REQUIRE(a.out_f32 || a.out_bf16 || a.pre_bf16, "tvs_gemm_bf16: no output");
+    TVS_REQUIRE(!(a.act == TVS_ACT_DQGELU || a.act == TVS_ACT_DRELU) || a.aux_bf16, "tvs_gemm_bf16: aux_bf16 required for derivative epilogues");
+    if (a.N % 32 == 0 || a.N > 32) {
+        // vector paths are used for every full 32-column chunk: check their alignment once
+        TVS_REQUIRE(!a.out_f32 || (a.ldo32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0), "tvs_gemm_bf16: out_f32 alignment");
+        TVS_REQUIRE(!a.out_bf16 || (a.ldo16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0), "tvs_gemm_bf16: out_bf16 alignment");
+        TVS_REQUIRE(!a.pre_bf16 || (a.ldpre % 8 == 0 && (reinterpret_cast<uintptr_t>(a.pre_bf16) & 15) == 0), "tvs_gemm_bf16: pre_bf16 alignment");
+        TVS_REQUIRE(!a.aux_bf16 || (a.ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a.aux_bf16) & 15) == 0), "tvs_gemm_bf16: aux_bf16 alignment");
+        TVS_REQUIRE(!a.residual || (a.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0), "tvs_gemm_bf16: residual alignment");
+        TVS_REQUIRE(!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "tvs_gemm_bf16: bias alignment");
+    }
+    GemmEpilogue ep;
+    ep.bias = a.bias;
+    ep.residual = a.residual;
+    ep.ldr = a.ldr;
+    ep.out_f32 = a.out_f32;
+    ep.ldo32 = a.ldo32;
+    ep.out_bf16 = static_cast<__nv_bfloat16*>(a.out_bf16);
+    ep.ldo16 = a.ldo16;
+    ep.pre_bf16 = static_cast<__nv_bfloat16*>(a.pre_bf16);
+    ep.ldpre = a.ldpre;
+    ep.aux_bf16 = static_cast<const __nv_bfloat16*>(a.aux_bf16);
+    ep.ldaux = a.ldaux;
+    ep.act = a.act;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N);
+    switch (bn) {
+        case 64: return launch_gemm<64, 8>(a, ep, s);
+        case 128: return launch_gemm<128, 6>(a, ep, s);
+        case 256: return launch_gemm<256, 4>(a, ep, s);
+        default: set_error("tvs_gemm_bf16: tile_n must be 0, 64, 128 or 256 (got %d)", bn); return -1;
+    }
+}

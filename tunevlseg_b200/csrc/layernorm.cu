@@ -1,0 +1,142 @@
+// LayerNorm forward / backward (dgrad only), one warp per row, float4 loads, warp-shuffle reductions.
+// Replaces nn.LayerNorm on the path: transformers modeling_clipseg.py:362-365 (layer_norm1/2), :782 (pre_layrnorm),
+// :636 (final_layer_norm), :784 (post_layernorm), :395-398 (decoder post-norms).  HBM-bound: reads the fp32 row once.
+#include "common.cuh"
+#include "tvs_b200.h"
+
+namespace tvs {
+
+constexpr int LN_MAXC = 8;  // float4 chunks per lane -> D <= 1024
+constexpr int LN_WARPS = 4;
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M,
+                     int D, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const int nch = D >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[LN_MAXC];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nch) {
+            v[i] = xr[c];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nch) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nch) {
+            const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + b.x;
+            o.y = (v[i].y - mean) * rstd * g.y + b.y;
+            o.z = (v[i].z - mean) * rstd * g.z + b.z;
+            o.w = (v[i].w - mean) * rstd * g.w + b.w;
+            if (y32) reinterpret_cast<float4*>(y32 + row * D)[c] = o;
+            if (y16) reinterpret_cast<uint2*>(y16 + row * D)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add,
+                     long long M, int D, float* dx32, __nv_bfloat16* __restrict__ dx16) {
+    const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const int nch = D >> 2;
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    float4 gg[LN_MAXC], xh[LN_MAXC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nch) {
+            float4 d;
+            if (dy16) {
+                const uint2 raw = reinterpret_cast<const uint2*>(dy16 + row * D)[c];
+                const float2 lo = unpack_bf16x2(raw.x), hi = unpack_bf16x2(raw.y);
+                d = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                d = reinterpret_cast<const float4*>(dy32 + row * D)[c];
+            }
+            const float4 g = __ldg(g4 + c);
+            const float4 xv = xr[c];
+            gg[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+            xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+            s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+            s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+        }
+    }
+    const float c1 = warp_sum(s1) / static_cast<float>(D);
+    const float c2 = warp_sum(s2) / static_cast<float>(D);
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nch) {
+            float4 o;
+            o.x = rs * (gg[i].x - c1 - xh[i].x * c2);
+            o.y = rs * (gg[i].y - c1 - xh[i].y * c2);
+            o.z = rs * (gg[i].z - c1 - xh[i].z * c2);
+            o.w = rs * (gg[i].w - c1 - xh[i].w * c2);
+            if (dx_add) {
+                const float4 a = reinterpret_cast<const float4*>(dx_add + row * D)[c];
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            if (dx32) reinterpret_cast<float4*>(dx32 + row * D)[c] = o;
+            if (dx16) reinterpret_cast<uint2*>(dx16 + row * D)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+    }
+}
+
+}  // namespace tvs
+
+extern "C" __attribute__((visibility("default"))) int tvs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int32_t D, float* y_f32,
+                                 void* y_bf16, float* mean, float* rstd, void* stream) {
+    using namespace tvs;
+    TVS_REQUIRE(x && gamma && beta && (y_f32 || y_bf16), "tvs_layernorm_fwd: null pointer");
+    TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_fwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
+    const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
+    layernorm_fwd_kernel<<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
+                                                                                        static_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
+    return check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int tvs_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma, const float* mean,
+                                 const float* rstd, const float* dx_add_f32, int64_t M, int32_t D, float* dx_out_f32, void* dx_out_bf16,
+                                 void* stream) {
+    using namespace tvs;
+    TVS_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "tvs_layernorm_bwd: exactly one of dy_bf16 / dy_f32");
+    TVS_REQUIRE(x && gamma && mean && rstd && (dx_out_f32 || dx_out_bf16), "tvs_layernorm_bwd: null pointer");
+    TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_bwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
+    const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
+    layernorm_bwd_kernel<<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, M, D, dx_out_f32,
+        static_cast<__nv_bfloat16*>(dx_out_bf16));
+    return check_launch("layernorm_bwd_kernel");
+}
