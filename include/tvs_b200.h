@@ -116,8 +116,21 @@ int tvs_vision_assemble(const float* patches, const float* cls, const float* pos
  * ------------------------------------------------------------------------------------------------ */
 int tvs_prompt_overwrite(float* x, void* x_bf16, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t n,
                          const float* ctx, int64_t ctx_batch_stride, void* stream);
-int tvs_prompt_grad(float* dx, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t n, float* dctx,
-                    int64_t ctx_batch_stride, int32_t zero_rows, void* stream);
+int tvs_prompt_grad(float* dx, void* dx_bf16 /* optional bf16 mirror of dx whose rows are zeroed too */, int32_t B,
+                    int32_t S, int32_t D, int32_t row0, int32_t n, float* dctx, int64_t ctx_batch_stride,
+                    int32_t zero_rows, void* stream);
+
+/* Row slicing around the decoder (base_clipseg.py:132-142: output[:, 1:-n] drops the CLS and prompt rows):
+ * slice:   y[b, r, :] = x[b, row0 + r, :], r < nrows   (f32 and/or bf16 copy)
+ * unslice: dx[b, s, :] = dy[b, s - row0, :] inside the window, 0 elsewhere (the backward of slice) */
+int tvs_slice_rows(const float* x, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t nrows, float* y_f32,
+                   void* y_bf16, void* stream);
+int tvs_unslice_rows(const float* dy, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t nrows, float* dx,
+                     void* stream);
+/* dw[n,k] += sum_m dy[m,n] * x[m,k] for a small trainable weight (N*K <= 4096): wgrad of the additive
+ * Conv2d(64,1,k) of base_clipseg.py:63-70 contracted at low resolution.  dw must be zero-initialised. */
+int tvs_wgrad_small(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, int64_t M, int32_t N, int32_t K,
+                    float* dw, void* stream);
 
 /* f32 -> bf16 copy (n elements, n % 4 == 0) */
 int tvs_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
@@ -170,6 +183,10 @@ int64_t tvs_dicebce_scratch_bytes(int32_t B, int64_t N);
 int tvs_dicebce_metrics_fwd(const float* logits, const float* mask, int32_t B, int64_t N, float threshold,
                             float lambda_dice, float lambda_ce, double* parts, int64_t* counts, int64_t* confmat,
                             float* loss, void* scratch, void* stream);
+/* counters only, from probabilities the caller already holds (metric(preds, target) API of
+ * src/models/image_text_mask_module.py:118-119); scratch as above */
+int tvs_metrics_from_probs(const float* preds, const float* mask, int32_t B, int64_t N, float threshold,
+                           int64_t* counts, int64_t* confmat, void* scratch, void* stream);
 int tvs_dicebce_bwd(const float* logits, const float* mask, const double* parts, const float* gscale, int32_t B,
                     int64_t N, float lambda_dice, float lambda_ce, float* dlogits, void* stream);
 

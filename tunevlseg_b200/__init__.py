@@ -1,0 +1,30 @@
+"""tunevlseg_b200 - a B200-native (sm_100a) implementation of TuneVLSeg's prompt-tuning train/eval step.
+
+Package layout (only what the hot path needs):
+    csrc/      hand-written CUDA kernels + the C ABI (include/tvs_b200.h) -> lib/libtvs_b200.so
+    abi.py     ctypes binding (raw device pointers + stream); no fallback
+    engine.py  weight packing, per-layer schedules, the four autograd nodes
+    models/    host-side mirror of the reference's ``src.models`` interface (same class names / signatures)
+    losses.py, metrics.py, optim.py   fused DiceCE loss, Dice/IoU metric objects, flat AdamW + NCCL all-reduce
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+
+__version__ = "0.1.0"
+
+
+def install_as_src() -> None:
+    """Expose this package under the reference's module paths, so its Hydra configs resolve unchanged:
+    ``_target_: src.models.core_models.coop.MapleCLIPSeg`` -> ``tunevlseg_b200.models.core_models.coop.MapleCLIPSeg``;
+    ``monai.losses.DiceCELoss`` -> the fused loss when monai is absent."""
+    names = ["models", "models.image_text_mask_module", "models.components", "models.components.hf_clipseg_wrapper",
+             "models.core_models", "models.core_models.coop", "models.core_models.coop.context_learner"]
+    if "src" not in sys.modules:
+        import types
+        sys.modules["src"] = types.ModuleType("src")
+    for n in names:
+        mod = importlib.import_module(f"{__name__}.{n}")
+        sys.modules[f"src.{n}"] = mod
+    setattr(sys.modules["src"], "models", sys.modules["src.models"])

@@ -1,0 +1,377 @@
+"""ctypes binding of libtvs_b200.so (the C ABI in include/tvs_b200.h) for torch tensors.
+
+PyTorch is plumbing here: it owns device memory and the stream; every compute call below hands raw device
+pointers and ``torch.cuda.current_stream().cuda_stream`` to the hand-written sm_100a kernels.  There is NO
+fallback: if the shared library is missing, cannot be loaded, or the device is not sm_100, a ``TvsError`` is
+raised - the product never routes through torch ops or the CPU oracle for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtvs_b200.so")
+
+ACT_NONE, ACT_QGELU, ACT_RELU, ACT_DQGELU, ACT_DRELU = range(5)
+BLEND_NONE, BLEND_RATIO, BLEND_ADD = range(3)
+
+
+class TvsError(RuntimeError):
+    pass
+
+
+class GemmArgs(Structure):
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_int64),
+        ("W", c_void_p), ("ldw", c_int64),
+        ("M", c_int32), ("N", c_int32), ("K", c_int32),
+        ("bias", c_void_p),
+        ("residual", c_void_p), ("ldr", c_int64),
+        ("out_f32", c_void_p), ("ldo32", c_int64),
+        ("out_bf16", c_void_p), ("ldo16", c_int64),
+        ("pre_bf16", c_void_p), ("ldpre", c_int64),
+        ("aux_bf16", c_void_p), ("ldaux", c_int64),
+        ("act", c_int32), ("tile_n", c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises TvsError when it is absent - build it with
+    ``python -m tunevlseg_b200.build`` (``__graft_entry__.build()`` does)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise TvsError(f"{_LIB_PATH} not found: run `python -m tunevlseg_b200.build` (no CPU / torch fallback exists)")
+    try:
+        lib = ctypes.CDLL(_LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise TvsError(f"cannot load {_LIB_PATH}: {e}") from e
+    lib.tvs_last_error.restype = c_char_p
+    lib.tvs_launch_count.restype = c_int64
+    lib.tvs_dicebce_scratch_bytes.restype = c_int64
+    lib.tvs_dicebce_scratch_bytes.argtypes = [c_int32, c_int64]
+    lib.tvs_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+    P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
+    sig = {
+        "tvs_layernorm_fwd": [P, P, P, F, I64, I32, P, P, P, P, P],
+        "tvs_layernorm_bwd": [P, P, P, P, P, P, P, I64, I32, P, P, P],
+        "tvs_attn_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P],
+        "tvs_attn_bwd": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, P],
+        "tvs_im2col_patches": [P, I32, I32, I32, I32, I32, P, P],
+        "tvs_vision_assemble": [P, P, P, P, I64, I32, I32, I32, I32, P, P],
+        "tvs_prompt_overwrite": [P, P, I32, I32, I32, I32, I32, P, I64, P],
+        "tvs_prompt_grad": [P, P, I32, I32, I32, I32, I32, P, I64, I32, P],
+        "tvs_slice_rows": [P, I32, I32, I32, I32, I32, P, P, P],
+        "tvs_unslice_rows": [P, I32, I32, I32, I32, I32, P, P],
+        "tvs_wgrad_small": [P, I64, P, I64, I64, I32, I32, P, P],
+        "tvs_cast_bf16": [P, P, I64, P],
+        "tvs_add_f32": [P, P, I64, P],
+        "tvs_film_fwd": [P, P, P, I32, I32, I32, P, P, P],
+        "tvs_film_bwd": [P, P, P, I32, I32, I32, P, P, P, P],
+        "tvs_head_fwd": [P, I64, P, I64, P, P, P, I32, I32, I32, I32, I32, P, P, P],
+        "tvs_head_bwd": [P, P, I64, P, P, P, I32, I32, I32, I32, I32, P, I64, P, I64, P, P, P],
+        "tvs_dicebce_metrics_fwd": [P, P, I32, I64, F, F, F, P, P, P, P, P, P],
+        "tvs_dicebce_bwd": [P, P, P, P, I32, I64, F, F, P, P],
+        "tvs_metrics_from_probs": [P, P, I32, I64, F, P, P, P, P],
+        "tvs_adamw_flat": [P, P, P, P, I64, F, F, F, F, F, I32, F, P, P, P],
+        "tvs_counter_inc": [P, P],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int32
+    _lib = lib
+    return lib
+
+
+_device_ok = False
+
+
+def require_device() -> None:
+    """Fail loudly unless the current CUDA device is an sm_100 part the library can drive."""
+    global _device_ok
+    if _device_ok:
+        return
+    lib = load()
+    if not torch.cuda.is_available():
+        raise TvsError("tunevlseg_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    torch.cuda.current_device()  # make sure a context exists
+    if lib.tvs_device_check() != 0:
+        raise TvsError(lib.tvs_last_error().decode())
+    _device_ok = True
+
+
+def launch_count() -> int:
+    return int(load().tvs_launch_count())
+
+
+def _ck(rc: int, what: str) -> None:
+    if rc != 0:
+        raise TvsError(f"{what}: {load().tvs_last_error().decode()} (rc={rc})")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor | None, dtype, name: str, dim2: bool = False) -> None:
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise TvsError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise TvsError(f"{name} must be {dtype}, got {t.dtype}")
+    if dim2:
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise TvsError(f"{name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    elif not t.is_contiguous():
+        raise TvsError(f"{name} must be contiguous")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=ACT_NONE,
+         tile_n=0):
+    """C[M,N] = epilogue(A[M,K] @ W[N,K]^T); see tvs_gemm_bf16 in include/tvs_b200.h.  2-D views with a row stride
+    are accepted (ld = stride(0))."""
+    require_device()
+    _chk(A, torch.bfloat16, "A", True); _chk(W, torch.bfloat16, "W", True)
+    _chk(bias, torch.float32, "bias"); _chk(residual, torch.float32, "residual", True)
+    _chk(out_f32, torch.float32, "out_f32", True); _chk(out_bf16, torch.bfloat16, "out_bf16", True)
+    _chk(pre_bf16, torch.bfloat16, "pre_bf16", True); _chk(aux_bf16, torch.bfloat16, "aux_bf16", True)
+    M, K = A.shape
+    N, K2 = W.shape
+    if K != K2:
+        raise TvsError(f"gemm: A is {tuple(A.shape)} but W is {tuple(W.shape)}")
+    for name, t in (("residual", residual), ("out_f32", out_f32), ("out_bf16", out_bf16), ("pre_bf16", pre_bf16),
+                    ("aux_bf16", aux_bf16)):
+        if t is not None and tuple(t.shape) != (M, N):
+            raise TvsError(f"gemm: {name} must be {(M, N)}, got {tuple(t.shape)}")
+    if bias is not None and bias.numel() != N:
+        raise TvsError("gemm: bias length")
+    g = GemmArgs()
+    g.A, g.lda, g.W, g.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
+    g.M, g.N, g.K = M, N, K
+    g.bias = _p(bias)
+    g.residual, g.ldr = _p(residual), (residual.stride(0) if residual is not None else 0)
+    g.out_f32, g.ldo32 = _p(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
+    g.out_bf16, g.ldo16 = _p(out_bf16), (out_bf16.stride(0) if out_bf16 is not None else 0)
+    g.pre_bf16, g.ldpre = _p(pre_bf16), (pre_bf16.stride(0) if pre_bf16 is not None else 0)
+    g.aux_bf16, g.ldaux = _p(aux_bf16), (aux_bf16.stride(0) if aux_bf16 is not None else 0)
+    g.act, g.tile_n = act, tile_n
+    _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None):
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
+    _chk(y_f32, torch.float32, "y_f32"); _chk(y_bf16, torch.bfloat16, "y_bf16")
+    D = x.shape[-1]
+    M = x.numel() // D
+    _ck(load().tvs_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, D, _p(y_f32), _p(y_bf16),
+                                 _p(mean), _p(rstd), _stream()), "tvs_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_add=None, dx_f32=None, dx_bf16=None):
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(dx_add, torch.float32, "dx_add"); _chk(dx_f32, torch.float32, "dx_f32")
+    _chk(dx_bf16, torch.bfloat16, "dx_bf16")
+    if not dy.is_contiguous():
+        raise TvsError("dy must be contiguous")
+    D = x.shape[-1]
+    M = x.numel() // D
+    d16 = dy.data_ptr() if dy.dtype == torch.bfloat16 else None
+    d32 = dy.data_ptr() if dy.dtype == torch.float32 else None
+    if d16 is None and d32 is None:
+        raise TvsError("dy must be bf16 or f32")
+    _ck(load().tvs_layernorm_bwd(d16, d32, x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(dx_add),
+                                 M, D, _p(dx_f32), _p(dx_bf16), _stream()), "tvs_layernorm_bwd")
+
+
+def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse):
+    require_device()
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(lse, torch.float32, "lse")
+    _chk(key_mask, torch.uint8, "key_mask")
+    _ck(load().tvs_attn_fwd(qkv.data_ptr(), B, S, H, hd, int(causal), _p(key_mask), out.data_ptr(), lse.data_ptr(),
+                            _stream()), "tvs_attn_fwd")
+
+
+def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv):
+    require_device()
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(dout, torch.bfloat16, "dout")
+    _chk(dqkv, torch.bfloat16, "dqkv"); _chk(lse, torch.float32, "lse"); _chk(delta, torch.float32, "delta")
+    _ck(load().tvs_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, S, H, hd, int(causal),
+                            _p(key_mask), delta.data_ptr(), dqkv.data_ptr(), _stream()), "tvs_attn_bwd")
+
+
+def im2col_patches(image, P, out_bf16):
+    require_device()
+    _chk(image, torch.float32, "image"); _chk(out_bf16, torch.bfloat16, "out")
+    B, C, H, W = image.shape
+    _ck(load().tvs_im2col_patches(image.data_ptr(), B, C, H, W, P, out_bf16.data_ptr(), _stream()), "tvs_im2col_patches")
+
+
+def vision_assemble(patches, cls, pos, ctx, B, G2, n, D, h):
+    require_device()
+    _chk(patches, torch.float32, "patches"); _chk(cls, torch.float32, "cls"); _chk(pos, torch.float32, "pos")
+    _chk(ctx, torch.float32, "ctx"); _chk(h, torch.float32, "h")
+    bs = 0 if (ctx is None or ctx.dim() == 2) else n * D
+    _ck(load().tvs_vision_assemble(patches.data_ptr(), cls.data_ptr(), pos.data_ptr(), _p(ctx), bs, B, G2, n, D,
+                                   h.data_ptr(), _stream()), "tvs_vision_assemble")
+
+
+def prompt_overwrite(x, row0, n, ctx, x_bf16=None):
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(ctx, torch.float32, "ctx"); _chk(x_bf16, torch.bfloat16, "x_bf16")
+    B, S, D = x.shape
+    bs = 0 if ctx.dim() == 2 else n * D
+    _ck(load().tvs_prompt_overwrite(x.data_ptr(), _p(x_bf16), B, S, D, row0, n, ctx.data_ptr(), bs, _stream()),
+        "tvs_prompt_overwrite")
+
+
+def prompt_grad(dx, row0, n, dctx, zero_rows=True, dx_bf16=None):
+    """dctx (+)= sum_b dx[:, row0:row0+n]; dctx is (n, D) [batch-reduced] or (B, n, D) [per sample]."""
+    require_device()
+    _chk(dx, torch.float32, "dx"); _chk(dctx, torch.float32, "dctx"); _chk(dx_bf16, torch.bfloat16, "dx_bf16")
+    B, S, D = dx.shape
+    bs = 0 if dctx.dim() == 2 else n * D
+    _ck(load().tvs_prompt_grad(dx.data_ptr(), _p(dx_bf16), B, S, D, row0, n, dctx.data_ptr(), bs, int(zero_rows),
+                               _stream()), "tvs_prompt_grad")
+
+
+def slice_rows(x, row0, nrows, y_f32=None, y_bf16=None):
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(y_f32, torch.float32, "y_f32"); _chk(y_bf16, torch.bfloat16, "y_bf16")
+    B, S, D = x.shape
+    _ck(load().tvs_slice_rows(x.data_ptr(), B, S, D, row0, nrows, _p(y_f32), _p(y_bf16), _stream()), "tvs_slice_rows")
+
+
+def unslice_rows(dy, S, row0, dx):
+    require_device()
+    _chk(dy, torch.float32, "dy"); _chk(dx, torch.float32, "dx")
+    B, nrows, D = dy.shape
+    _ck(load().tvs_unslice_rows(dy.data_ptr(), B, S, D, row0, nrows, dx.data_ptr(), _stream()), "tvs_unslice_rows")
+
+
+def wgrad_small(dy, x, dw):
+    """dw[n,k] += sum_m dy[m,n] x[m,k]; dy (M,N) and x (M,K) are f32 2-D views."""
+    require_device()
+    _chk(dy, torch.float32, "dy", True); _chk(x, torch.float32, "x", True); _chk(dw, torch.float32, "dw")
+    M, N = dy.shape
+    K = x.shape[1]
+    _ck(load().tvs_wgrad_small(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, N, K, dw.data_ptr(), _stream()),
+        "tvs_wgrad_small")
+
+
+def cast_bf16(x, y):
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(y, torch.bfloat16, "y")
+    _ck(load().tvs_cast_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "tvs_cast_bf16")
+
+
+def add_f32(y, x):
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(y, torch.float32, "y")
+    _ck(load().tvs_add_f32(y.data_ptr(), x.data_ptr(), x.numel(), _stream()), "tvs_add_f32")
+
+
+def film_fwd(x, mul, add, y=None, y_bf16=None):
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(mul, torch.float32, "mul"); _chk(add, torch.float32, "add")
+    B, S, D = x.shape
+    _ck(load().tvs_film_fwd(x.data_ptr(), mul.data_ptr(), add.data_ptr(), B, S, D, _p(y), _p(y_bf16), _stream()),
+        "tvs_film_fwd")
+
+
+def film_bwd(dy, x, mul, dx, dmul, dadd):
+    require_device()
+    for n_, t in (("dy", dy), ("x", x), ("mul", mul), ("dx", dx), ("dmul", dmul), ("dadd", dadd)):
+        _chk(t, torch.float32, n_)
+    B, S, D = x.shape
+    _ck(load().tvs_film_bwd(dy.data_ptr(), x.data_ptr(), mul.data_ptr(), B, S, D, dx.data_ptr(), dmul.data_ptr(),
+                            dadd.data_ptr(), _stream()), "tvs_film_bwd")
+
+
+def head_fwd(tconv, addmap, bias_t, bias_a, ratio, blend, B, G, P, ksize, logits, add_out=None):
+    require_device()
+    _chk(tconv, torch.float32, "tconv", True); _chk(addmap, torch.float32, "addmap", True)
+    _chk(logits, torch.float32, "logits"); _chk(add_out, torch.float32, "add_out")
+    _ck(load().tvs_head_fwd(tconv.data_ptr(), tconv.stride(0), _p(addmap), addmap.stride(0) if addmap is not None else 0,
+                            _p(bias_t), _p(bias_a), _p(ratio), blend, B, G, P, ksize, logits.data_ptr(), _p(add_out),
+                            _stream()), "tvs_head_fwd")
+
+
+def head_bwd(dlogits, tconv, add_out, bias_t, ratio, blend, B, G, P, ksize, dtconv_bf16, daddmap, dbias_a, dratio):
+    require_device()
+    _chk(dlogits, torch.float32, "dlogits"); _chk(dtconv_bf16, torch.bfloat16, "dtconv", True)
+    _chk(daddmap, torch.float32, "daddmap", True)
+    _ck(load().tvs_head_bwd(dlogits.data_ptr(), _p(tconv), tconv.stride(0) if tconv is not None else 0, _p(add_out),
+                            _p(bias_t), _p(ratio), blend, B, G, P, ksize, dtconv_bf16.data_ptr(), dtconv_bf16.stride(0),
+                            _p(daddmap), daddmap.stride(0) if daddmap is not None else 0, _p(dbias_a), _p(dratio),
+                            _stream()), "tvs_head_bwd")
+
+
+def dicebce_scratch_bytes(B: int, N: int) -> int:
+    return int(load().tvs_dicebce_scratch_bytes(B, N))
+
+
+def dicebce_metrics_fwd(logits, mask, threshold, lambda_dice, lambda_ce, parts, counts, confmat, loss, scratch):
+    require_device()
+    _chk(logits, torch.float32, "logits"); _chk(mask, torch.float32, "mask")
+    _chk(parts, torch.float64, "parts"); _chk(counts, torch.int64, "counts"); _chk(confmat, torch.int64, "confmat")
+    _chk(loss, torch.float32, "loss")
+    B = logits.shape[0]
+    N = logits.numel() // B
+    _ck(load().tvs_dicebce_metrics_fwd(logits.data_ptr(), mask.data_ptr(), B, N, threshold, lambda_dice, lambda_ce,
+                                       _p(parts), _p(counts), _p(confmat), _p(loss), scratch.data_ptr(), _stream()),
+        "tvs_dicebce_metrics_fwd")
+
+
+def metrics_from_probs(preds, mask, threshold, counts, confmat, scratch):
+    require_device()
+    _chk(preds, torch.float32, "preds"); _chk(mask, torch.float32, "mask")
+    _chk(counts, torch.int64, "counts"); _chk(confmat, torch.int64, "confmat")
+    B = preds.shape[0]
+    N = preds.numel() // B
+    _ck(load().tvs_metrics_from_probs(preds.data_ptr(), mask.data_ptr(), B, N, threshold, _p(counts), _p(confmat),
+                                      scratch.data_ptr(), _stream()), "tvs_metrics_from_probs")
+
+
+def dicebce_bwd(logits, mask, parts, gscale, lambda_dice, lambda_ce, dlogits):
+    require_device()
+    _chk(logits, torch.float32, "logits"); _chk(mask, torch.float32, "mask"); _chk(parts, torch.float64, "parts")
+    _chk(gscale, torch.float32, "gscale"); _chk(dlogits, torch.float32, "dlogits")
+    B = logits.shape[0]
+    N = logits.numel() // B
+    _ck(load().tvs_dicebce_bwd(logits.data_ptr(), mask.data_ptr(), parts.data_ptr(), _p(gscale), B, N, lambda_dice,
+                               lambda_ce, dlogits.data_ptr(), _stream()), "tvs_dicebce_bwd")
+
+
+def adamw_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+               step_dev=None, lr_dev=None):
+    require_device()
+    for n_, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _chk(t, torch.float32, n_)
+    _ck(load().tvs_adamw_flat(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                              lr, beta1, beta2, eps, weight_decay, step, grad_scale, _p(step_dev), _p(lr_dev), _stream()),
+        "tvs_adamw_flat")
+
+
+def counter_inc(counter):
+    require_device()
+    _chk(counter, torch.int32, "counter")
+    _ck(load().tvs_counter_inc(counter.data_ptr(), _stream()), "tvs_counter_inc")

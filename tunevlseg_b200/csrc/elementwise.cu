@@ -76,8 +76,8 @@ __global__ void prompt_overwrite_kernel(float* __restrict__ x, __nv_bfloat16* __
 }
 
 // dctx[(b), j, d] (+)= sum_b dx[b, row0+j, d]; optionally zero those rows of dx.  One thread per (j, d) [per b].
-__global__ void prompt_grad_kernel(float* __restrict__ dx, int B, int S, int D, int row0, int n, float* __restrict__ dctx, long long ctx_bs,
-                                   int zero_rows) {
+__global__ void prompt_grad_kernel(float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int B, int S, int D, int row0, int n,
+                                   float* __restrict__ dctx, long long ctx_bs, int zero_rows) {
     const long long per = static_cast<long long>(n) * D;
     const long long total = ctx_bs ? per * B : per;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -87,13 +87,19 @@ __global__ void prompt_grad_kernel(float* __restrict__ dx, int B, int S, int D, 
             const int b = static_cast<int>(i / per);
             float* p = dx + (static_cast<long long>(b) * S + row0 + j) * D + d;
             dctx[b * ctx_bs + static_cast<long long>(j) * D + d] += *p;
-            if (zero_rows) *p = 0.f;
+            if (zero_rows) {
+                *p = 0.f;
+                if (dx16) dx16[(static_cast<long long>(b) * S + row0 + j) * D + d] = __float2bfloat16(0.f);
+            }
         } else {
             float acc = 0.f;
             for (int b = 0; b < B; ++b) {
                 float* p = dx + (static_cast<long long>(b) * S + row0 + j) * D + d;
                 acc += *p;
-                if (zero_rows) *p = 0.f;
+                if (zero_rows) {
+                    *p = 0.f;
+                    if (dx16) dx16[(static_cast<long long>(b) * S + row0 + j) * D + d] = __float2bfloat16(0.f);
+                }
             }
             dctx[static_cast<long long>(j) * D + d] += acc;
         }
@@ -113,6 +119,73 @@ __global__ void add_f32_kernel(float* __restrict__ y, const float* __restrict__ 
         const float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         reinterpret_cast<float4*>(y)[i] = a;
+    }
+}
+
+
+// y[b, r, :] = x[b, row0 + r, :]  for r < nrows  (strip CLS / prompt rows; base_clipseg.py:132-142)
+__global__ void slice_rows_kernel(const float* __restrict__ x, int B, int S, int D, int row0, int nrows, float* __restrict__ y32,
+                                  __nv_bfloat16* __restrict__ y16) {
+    const int d4 = D / 4;
+    const long long total = static_cast<long long>(B) * nrows * d4;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % d4);
+        const int r = static_cast<int>((i / d4) % nrows);
+        const int b = static_cast<int>(i / (static_cast<long long>(d4) * nrows));
+        const float4 v = reinterpret_cast<const float4*>(x + (static_cast<long long>(b) * S + row0 + r) * D)[c];
+        if (y32) reinterpret_cast<float4*>(y32)[i] = v;
+        if (y16) reinterpret_cast<uint2*>(y16)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+// dx[b, s, :] = (row0 <= s < row0 + nrows) ? dy[b, s - row0, :] : 0
+__global__ void unslice_rows_kernel(const float* __restrict__ dy, int B, int S, int D, int row0, int nrows, float* __restrict__ dx) {
+    const int d4 = D / 4;
+    const long long total = static_cast<long long>(B) * S * d4;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % d4);
+        const int s = static_cast<int>((i / d4) % S);
+        const int b = static_cast<int>(i / (static_cast<long long>(d4) * S));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s >= row0 && s < row0 + nrows) v = reinterpret_cast<const float4*>(dy + (static_cast<long long>(b) * nrows + (s - row0)) * D)[c];
+        reinterpret_cast<float4*>(dx)[i] = v;
+    }
+}
+
+// dw[n, k] += sum_m dy[m, n] * x[m, k]   for a SMALL weight (N * K <= 4096): the trainable additive 5x5 conv of the
+// decoder head (base_clipseg.py:63-70) contracted at low resolution.  Each block reduces a slab of rows through
+// shared memory and issues one atomicAdd per output.
+constexpr int WG_ROWS = 64;
+__global__ void __launch_bounds__(256)
+wgrad_small_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ x, long long ld_x, long long M, int N, int K,
+                   float* __restrict__ dw) {
+    extern __shared__ float sm[];
+    float* s_dy = sm;                 // [WG_ROWS][N]
+    float* s_x = sm + WG_ROWS * N;    // [WG_ROWS][K]
+    const int NK = N * K;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (long long m0 = static_cast<long long>(blockIdx.x) * WG_ROWS; m0 < M; m0 += static_cast<long long>(gridDim.x) * WG_ROWS) {
+        const int rows = static_cast<int>(min(static_cast<long long>(WG_ROWS), M - m0));
+        for (int i = threadIdx.x; i < rows * N; i += blockDim.x) s_dy[i] = dy[(m0 + i / N) * ld_dy + i % N];
+        for (int i = threadIdx.x; i < rows * K; i += blockDim.x) s_x[i] = x[(m0 + i / K) * ld_x + i % K];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int o = threadIdx.x + j * 256;
+            if (o < NK) {
+                const int n = o / K, k = o % K;
+                float a = 0.f;
+                for (int r = 0; r < rows; ++r) a += s_dy[r * N + n] * s_x[r * K + k];
+                acc[j] += a;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int o = threadIdx.x + j * 256;
+        if (o < NK) atomicAdd(dw + o, acc[j]);
     }
 }
 
@@ -391,12 +464,13 @@ extern "C" __attribute__((visibility("default"))) int tvs_prompt_overwrite(float
     return check_launch("prompt_overwrite_kernel");
 }
 
-extern "C" __attribute__((visibility("default"))) int tvs_prompt_grad(float* dx, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t n, float* dctx, int64_t ctx_batch_stride,
-                               int32_t zero_rows, void* stream) {
+extern "C" __attribute__((visibility("default"))) int tvs_prompt_grad(float* dx, void* dx_bf16, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t n, float* dctx,
+                               int64_t ctx_batch_stride, int32_t zero_rows, void* stream) {
     TVS_REQUIRE(dx && dctx, "tvs_prompt_grad: null pointer");
     TVS_REQUIRE(row0 >= 0 && n > 0 && row0 + n <= S, "tvs_prompt_grad: bad rows");
     const long long total = static_cast<long long>(n) * D * (ctx_batch_stride ? B : 1);
-    prompt_grad_kernel<<<blocks_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dx, B, S, D, row0, n, dctx, ctx_batch_stride, zero_rows);
+    prompt_grad_kernel<<<blocks_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dx, static_cast<__nv_bfloat16*>(dx_bf16), B, S, D, row0, n, dctx,
+                                                                                            ctx_batch_stride, zero_rows);
     return check_launch("prompt_grad_kernel");
 }
 
@@ -475,4 +549,30 @@ extern "C" __attribute__((visibility("default"))) int tvs_counter_inc(int32_t* c
     TVS_REQUIRE(counter_dev, "tvs_counter_inc: null pointer");
     counter_inc_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(counter_dev);
     return check_launch("counter_inc_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int tvs_slice_rows(const float* x, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t nrows, float* y_f32, void* y_bf16,
+                                                                      void* stream) {
+    TVS_REQUIRE(x && (y_f32 || y_bf16) && D % 4 == 0 && row0 >= 0 && nrows > 0 && row0 + nrows <= S, "tvs_slice_rows: bad arguments");
+    const long long total = static_cast<long long>(B) * nrows * (D / 4);
+    slice_rows_kernel<<<blocks_for(total, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, B, S, D, row0, nrows, y_f32, static_cast<__nv_bfloat16*>(y_bf16));
+    return check_launch("slice_rows_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int tvs_unslice_rows(const float* dy, int32_t B, int32_t S, int32_t D, int32_t row0, int32_t nrows, float* dx, void* stream) {
+    TVS_REQUIRE(dy && dx && D % 4 == 0 && row0 >= 0 && nrows > 0 && row0 + nrows <= S, "tvs_unslice_rows: bad arguments");
+    const long long total = static_cast<long long>(B) * S * (D / 4);
+    unslice_rows_kernel<<<blocks_for(total, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, B, S, D, row0, nrows, dx);
+    return check_launch("unslice_rows_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int tvs_wgrad_small(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, int64_t M, int32_t N, int32_t K, float* dw,
+                                                                       void* stream) {
+    TVS_REQUIRE(dy && x && dw && M > 0 && N > 0 && K > 0 && N * K <= 4096, "tvs_wgrad_small: N*K must be <= 4096");
+    const size_t sh = static_cast<size_t>(WG_ROWS) * (N + K) * sizeof(float);
+    TVS_REQUIRE(sh <= 48 * 1024, "tvs_wgrad_small: N + K too large");
+    long long blocks = (M + WG_ROWS - 1) / WG_ROWS;
+    if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+    wgrad_small_kernel<<<static_cast<unsigned>(blocks), 256, sh, static_cast<cudaStream_t>(stream)>>>(dy, ld_dy, x, ld_x, M, N, K, dw);
+    return check_launch("wgrad_small_kernel");
 }

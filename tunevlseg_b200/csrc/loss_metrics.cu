@@ -32,17 +32,23 @@ struct PixelStats {
     unsigned c00, c01, c10, c11;  // [t][p > thr]
 };
 
+template <bool PROBS>
 __device__ __forceinline__ void pixel(float x, float y, float thr, PixelStats& s) {
-    float e = __expf(-x);
-    float p = __fdiv_rn(1.0f, 1.0f + e);
-    if (fabsf(p - thr) < 1e-4f) {
-        e = static_cast<float>(exp(-static_cast<double>(x)));
-        p = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+    float p;
+    if (PROBS) {
+        p = x;   // the caller already holds probabilities (metric(preds, target) API): threshold them as they are
+    } else {
+        float e = __expf(-x);
+        p = __fdiv_rn(1.0f, 1.0f + e);
+        if (fabsf(p - thr) < 1e-4f) {
+            e = static_cast<float>(exp(-static_cast<double>(x)));
+            p = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+        }
+        s.bce += fmaxf(x, 0.f) - x * y + log1pf(__expf(-fabsf(x)));
     }
     s.I += p * y;
     s.P += p;
     s.G += y;
-    s.bce += fmaxf(x, 0.f) - x * y + log1pf(__expf(-fabsf(x)));
     const unsigned t = static_cast<unsigned>(static_cast<long long>(y)) & 1u;
     const unsigned ge = p >= thr, gt = p > thr;
     s.tp += ge & t;
@@ -54,6 +60,7 @@ __device__ __forceinline__ void pixel(float x, float y, float thr, PixelStats& s
     s.c11 += t & gt;
 }
 
+template <bool PROBS>
 __global__ void __launch_bounds__(LOSS_THREADS)
 dicebce_partial_kernel(const float* __restrict__ logits, const float* __restrict__ mask, long long N, float thr, double* __restrict__ part_out,
                        long long* __restrict__ cnt_out) {
@@ -67,14 +74,14 @@ dicebce_partial_kernel(const float* __restrict__ logits, const float* __restrict
         for (long long i = static_cast<long long>(blockIdx.x) * LOSS_THREADS + threadIdx.x; i < n4; i += static_cast<long long>(nblk) * LOSS_THREADS) {
             const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
             const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + i);
-            pixel(xv.x, yv.x, thr, s);
-            pixel(xv.y, yv.y, thr, s);
-            pixel(xv.z, yv.z, thr, s);
-            pixel(xv.w, yv.w, thr, s);
+            pixel<PROBS>(xv.x, yv.x, thr, s);
+            pixel<PROBS>(xv.y, yv.y, thr, s);
+            pixel<PROBS>(xv.z, yv.z, thr, s);
+            pixel<PROBS>(xv.w, yv.w, thr, s);
         }
     } else {
         for (long long i = static_cast<long long>(blockIdx.x) * LOSS_THREADS + threadIdx.x; i < N; i += static_cast<long long>(nblk) * LOSS_THREADS)
-            pixel(x[i], y[i], thr, s);
+            pixel<PROBS>(x[i], y[i], thr, s);
     }
     // block reduction: floats in double, counters as 64-bit
     __shared__ double sd[LOSS_THREADS / 32][4];
@@ -198,7 +205,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_dicebce_metrics_fwd(co
     double* part = static_cast<double*>(scratch);
     long long* cnt = reinterpret_cast<long long*>(part + static_cast<long long>(B) * nblk * 4);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dicebce_partial_kernel<<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(logits, mask, N, threshold, part, cnt);
+    dicebce_partial_kernel<false><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(logits, mask, N, threshold, part, cnt);
     if (int rc = check_launch("dicebce_partial_kernel")) return rc;
     const size_t sh = static_cast<size_t>(B) * (2 * sizeof(double) + 4 * sizeof(long long));
     dicebce_finalize_kernel<<<1, 256, sh, st>>>(part, cnt, B, nblk, N, lambda_dice, lambda_ce, parts, reinterpret_cast<long long*>(counts),
@@ -215,4 +222,22 @@ extern "C" __attribute__((visibility("default"))) int tvs_dicebce_bwd(const floa
     dicebce_bwd_kernel<<<dim3(nblk, B), LOSS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, mask, parts, gscale, B, N, lambda_dice,
                                                                                               lambda_ce, dlogits);
     return check_launch("dicebce_bwd_kernel");
+}
+
+// metric(preds, target) entry for callers that only hold probabilities (torchmetrics-style API): same counters, no loss.
+extern "C" __attribute__((visibility("default"))) int tvs_metrics_from_probs(const float* preds, const float* mask, int32_t B, int64_t N, float threshold,
+                                                                              int64_t* counts, int64_t* confmat, void* scratch, void* stream) {
+    using namespace tvs;
+    TVS_REQUIRE(preds && mask && scratch, "tvs_metrics_from_probs: null pointer");
+    TVS_REQUIRE(B > 0 && B <= 4096 && N > 0, "tvs_metrics_from_probs: bad shape B=%d N=%lld", B, (long long)N);
+    const int nblk = loss_blocks_per_sample(B, N);
+    double* part = static_cast<double*>(scratch);
+    long long* cnt = reinterpret_cast<long long*>(part + static_cast<long long>(B) * nblk * 4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dicebce_partial_kernel<true><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(preds, mask, N, threshold, part, cnt);
+    if (int rc = check_launch("dicebce_partial_kernel")) return rc;
+    const size_t sh = static_cast<size_t>(B) * (2 * sizeof(double) + 4 * sizeof(long long));
+    dicebce_finalize_kernel<<<1, 256, sh, st>>>(part, cnt, B, nblk, N, 0.f, 0.f, nullptr, reinterpret_cast<long long*>(counts),
+                                                reinterpret_cast<long long*>(confmat), nullptr);
+    return check_launch("dicebce_finalize_kernel");
 }
