@@ -48,6 +48,7 @@ int tvs_device_check(void);
  * post-ReLU activation for DRELU) - the dgrad-through-activation epilogue.
  * Requirements: K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, A and W 16-byte aligned.
  * ------------------------------------------------------------------------------------------------ */
+enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1 };
 enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4 };
 
 typedef struct tvs_gemm_args {
@@ -62,6 +63,10 @@ typedef struct tvs_gemm_args {
     const void* aux_bf16; int64_t ldaux;   /* bf16 [M,N], required by TVS_ACT_D* */
     int32_t act;
     int32_t tile_n;                        /* 0 = auto, else 64 / 128 / 256 */
+    int32_t ab_dtype;                      /* TVS_AB_BF16: A, W are bf16 (kind::f16).  TVS_AB_TF32: A, W are f32 and the
+                                              MMA runs kind::tf32 (10-bit mantissa) - used for the small text tower and
+                                              decoder, whose rounding dominates the logit error; K, lda, ldw % 4 == 0 */
+    int32_t reserved;
 } tvs_gemm_args;
 
 int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);
@@ -91,7 +96,8 @@ int tvs_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, 
  * hd is 64 (towers) or 16 (decoder).  bwd writes dqkv (same layout as qkv); delta is f32 [B,H,S] scratch.
  * ------------------------------------------------------------------------------------------------ */
 int tvs_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t hd, int32_t causal,
-                 const uint8_t* key_mask, void* out, float* lse, void* stream);
+                 const uint8_t* key_mask, void* out, float* out_f32 /* optional f32 copy of out */, float* lse,
+                 void* stream);
 int tvs_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
                  int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv,
                  void* stream);

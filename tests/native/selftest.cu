@@ -173,7 +173,44 @@ static void gemm_case(int M, int N, int K, int act, bool use_bias, bool use_res,
     cudaFree(dA); cudaFree(dW); cudaFree(dAux); cudaFree(dBias); cudaFree(dRes); cudaFree(dOut32); cudaFree(dOut16); cudaFree(dPre); cudaFree(dRef); cudaFree(dRefPre);
 }
 
+// fp32 operands through the kind::tf32 MMA, against a double-precision CPU reference of the fp32 inputs
+static void gemm_tf32_case(int M, int N, int K, int tile_n) {
+    std::vector<float> a((size_t)M * K), w((size_t)N * K), bias(N);
+    for (auto& x : a) x = frand();
+    for (auto& x : w) x = frand(1.f / sqrtf((float)K));
+    for (auto& x : bias) x = frand(0.5f);
+    float *dA = dev(a), *dW = dev(w), *dBias = dev(bias);
+    float* dOut = dev_zero<float>((size_t)M * N);
+    tvs_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.A = dA; g.lda = K; g.W = dW; g.ldw = K; g.M = M; g.N = N; g.K = K;
+    g.bias = dBias; g.out_f32 = dOut; g.ldo32 = N; g.tile_n = tile_n; g.ab_dtype = TVS_AB_TF32;
+    TV(tvs_gemm_bf16(&g, nullptr));
+    CK(cudaDeviceSynchronize());
+    auto o = host(dOut, (size_t)M * N);
+    double err = 0, scale = 0;
+    for (int m = 0; m < M; m += 7)
+        for (int n = 0; n < N; ++n) {
+            double acc = bias[n];
+            for (int k = 0; k < K; ++k) acc += (double)a[(size_t)m * K + k] * w[(size_t)n * K + k];
+            err = std::max(err, fabs(acc - o[(size_t)m * N + n]));
+            scale = std::max(scale, fabs(acc));
+        }
+    char name[128];
+    snprintf(name, sizeof name, "gemm tf32 M=%d N=%d K=%d bn=%d (rel to max)", M, N, K, tile_n);
+    report(name, err / std::max(1.0, scale), 1.5e-3);
+    cudaFree(dA); cudaFree(dW); cudaFree(dBias); cudaFree(dOut);
+}
+
 static void test_gemm() {
+    gemm_tf32_case(128, 64, 32, 64);
+    gemm_tf32_case(300, 192, 64, 0);
+    gemm_tf32_case(978, 64, 768, 0);
+    gemm_tf32_case(978, 2048, 64, 0);
+    gemm_tf32_case(978, 64, 2048, 0);
+    gemm_tf32_case(968, 25, 64, 0);
+    gemm_tf32_case(77 * 4, 1536, 512, 0);
+    gemm_tf32_case(3, 512, 512, 0);
     // tiny first: one tile, one k-block
     gemm_case(128, 128, 64, TVS_ACT_NONE, false, false, true, false, false, 128);
     gemm_case(128, 64, 64, TVS_ACT_NONE, false, false, true, false, false, 64);
@@ -226,7 +263,7 @@ static void attn_case(int B, int S, int H, int hd, int causal, bool use_mask, bo
     __nv_bfloat16* dDQKV = dev_zero<__nv_bfloat16>((size_t)B * S * 3 * E);
     float* dLse = dev_zero<float>((size_t)B * H * S);
     float* dDelta = dev_zero<float>((size_t)B * H * S);
-    TV(tvs_attn_fwd(dQKV, B, S, H, hd, causal, use_mask ? dMask : nullptr, dOut, dLse, nullptr));
+    TV(tvs_attn_fwd(dQKV, B, S, H, hd, causal, use_mask ? dMask : nullptr, dOut, nullptr, dLse, nullptr));
     CK(cudaDeviceSynchronize());
     TV(tvs_attn_bwd(dQKV, dOut, dDO, dLse, B, S, H, hd, causal, use_mask ? dMask : nullptr, dDelta, dDQKV, nullptr));
     CK(cudaDeviceSynchronize());
@@ -325,7 +362,7 @@ static void attn_timing(int B, int S, int H, int hd) {
     const int it = 10;
     for (int w = 0; w < 2; ++w) {
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < it; ++i) TV(tvs_attn_fwd(dQKV, B, S, H, hd, 0, nullptr, dOut, dLse, nullptr));
+        for (int i = 0; i < it; ++i) TV(tvs_attn_fwd(dQKV, B, S, H, hd, 0, nullptr, dOut, nullptr, dLse, nullptr));
         CK(cudaEventRecord(e1));
         for (int i = 0; i < it; ++i) TV(tvs_attn_bwd(dQKV, dOut, dDO, dLse, B, S, H, hd, 0, nullptr, dDelta, dDQKV, nullptr));
         CK(cudaEventRecord(e2));

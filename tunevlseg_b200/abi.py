@@ -34,7 +34,7 @@ class GemmArgs(Structure):
         ("out_bf16", c_void_p), ("ldo16", c_int64),
         ("pre_bf16", c_void_p), ("ldpre", c_int64),
         ("aux_bf16", c_void_p), ("ldaux", c_int64),
-        ("act", c_int32), ("tile_n", c_int32),
+        ("act", c_int32), ("tile_n", c_int32), ("ab_dtype", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -66,7 +66,7 @@ def load():
     sig = {
         "tvs_layernorm_fwd": [P, P, P, F, I64, I32, P, P, P, P, P],
         "tvs_layernorm_bwd": [P, P, P, P, P, P, P, I64, I32, P, P, P],
-        "tvs_attn_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P],
+        "tvs_attn_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, P],
         "tvs_attn_bwd": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, P],
         "tvs_im2col_patches": [P, I32, I32, I32, I32, I32, P, P],
         "tvs_vision_assemble": [P, P, P, P, I64, I32, I32, I32, I32, P, P],
@@ -149,7 +149,9 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     """C[M,N] = epilogue(A[M,K] @ W[N,K]^T); see tvs_gemm_bf16 in include/tvs_b200.h.  2-D views with a row stride
     are accepted (ld = stride(0))."""
     require_device()
-    _chk(A, torch.bfloat16, "A", True); _chk(W, torch.bfloat16, "W", True)
+    if A.dtype != W.dtype or A.dtype not in (torch.bfloat16, torch.float32):
+        raise TvsError(f"gemm: A and W must both be bf16 or both f32 (tf32 MMA), got {A.dtype} / {W.dtype}")
+    _chk(A, A.dtype, "A", True); _chk(W, W.dtype, "W", True)
     _chk(bias, torch.float32, "bias"); _chk(residual, torch.float32, "residual", True)
     _chk(out_f32, torch.float32, "out_f32", True); _chk(out_bf16, torch.bfloat16, "out_bf16", True)
     _chk(pre_bf16, torch.bfloat16, "pre_bf16", True); _chk(aux_bf16, torch.bfloat16, "aux_bf16", True)
@@ -173,6 +175,7 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.pre_bf16, g.ldpre = _p(pre_bf16), (pre_bf16.stride(0) if pre_bf16 is not None else 0)
     g.aux_bf16, g.ldaux = _p(aux_bf16), (aux_bf16.stride(0) if aux_bf16 is not None else 0)
     g.act, g.tile_n = act, tile_n
+    g.ab_dtype = 1 if A.dtype == torch.float32 else 0
     _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
 
 
@@ -202,12 +205,12 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_add=None, dx_f32=None, dx_bf16
                                  M, D, _p(dx_f32), _p(dx_bf16), _stream()), "tvs_layernorm_bwd")
 
 
-def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse):
+def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse, out_f32=None):
     require_device()
     _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(lse, torch.float32, "lse")
-    _chk(key_mask, torch.uint8, "key_mask")
-    _ck(load().tvs_attn_fwd(qkv.data_ptr(), B, S, H, hd, int(causal), _p(key_mask), out.data_ptr(), lse.data_ptr(),
-                            _stream()), "tvs_attn_fwd")
+    _chk(key_mask, torch.uint8, "key_mask"); _chk(out_f32, torch.float32, "out_f32")
+    _ck(load().tvs_attn_fwd(qkv.data_ptr(), B, S, H, hd, int(causal), _p(key_mask), out.data_ptr(), _p(out_f32),
+                            lse.data_ptr(), _stream()), "tvs_attn_fwd")
 
 
 def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv):

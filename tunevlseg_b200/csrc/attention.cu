@@ -118,7 +118,7 @@ __device__ __forceinline__ void acc_to_afrag(const float (&s)[8][4], uint32_t (&
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int H, int causal, const uint8_t* __restrict__ key_mask,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse) {
     __shared__ __align__(128) __nv_bfloat16 sQ[64 * HD];
     __shared__ __align__(128) __nv_bfloat16 sK[2][64 * HD];
     __shared__ __align__(128) __nv_bfloat16 sV[2][64 * HD];
@@ -227,6 +227,12 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int H, int causal,
 #pragma unroll
             for (int nb = 0; nb < HD / 8; ++nb)
                 *reinterpret_cast<uint32_t*>(orow + nb * 8 + 2 * tq) = pack_bf16x2(o[nb][2 * r] * inv, o[nb][2 * r + 1] * inv);
+            if (out32) {
+                float* frow = out32 + (static_cast<long long>(b) * S + q) * E + h * HD;
+#pragma unroll
+                for (int nb = 0; nb < HD / 8; ++nb)
+                    *reinterpret_cast<float2*>(frow + nb * 8 + 2 * tq) = make_float2(o[nb][2 * r] * inv, o[nb][2 * r + 1] * inv);
+            }
             if (tq == 0) lse[(static_cast<long long>(b) * H + h) * S + q] = (m_run[r] == -INFINITY ? 0.f : m_run[r]) + logf(fmaxf(l_run[r], 1e-30f));
         }
     }
@@ -491,10 +497,10 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 }
 
 template <int HD>
-static int attn_fwd_launch(const void* qkv, int B, int S, int H, int causal, const uint8_t* km, void* out, float* lse, cudaStream_t st) {
+static int attn_fwd_launch(const void* qkv, int B, int S, int H, int causal, const uint8_t* km, void* out, float* out32, float* lse, cudaStream_t st) {
     dim3 grid((S + ATT_BM - 1) / ATT_BM, H, B);
     attn_fwd_kernel<HD><<<grid, ATT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), S, H, causal, km,
-                                                      static_cast<__nv_bfloat16*>(out), lse);
+                                                      static_cast<__nv_bfloat16*>(out), out32, lse);
     return check_launch("attn_fwd_kernel");
 }
 
@@ -517,13 +523,13 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
 }  // namespace tvs
 
 extern "C" __attribute__((visibility("default"))) int tvs_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask,
-                            void* out, float* lse, void* stream) {
+                            void* out, float* out_f32, float* lse, void* stream) {
     using namespace tvs;
     TVS_REQUIRE(qkv && out && lse, "tvs_attn_fwd: null pointer");
     TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (hd == 64) return attn_fwd_launch<64>(qkv, B, S, H, causal, key_mask, out, lse, st);
-    if (hd == 16) return attn_fwd_launch<16>(qkv, B, S, H, causal, key_mask, out, lse, st);
+    if (hd == 64) return attn_fwd_launch<64>(qkv, B, S, H, causal, key_mask, out, out_f32, lse, st);
+    if (hd == 16) return attn_fwd_launch<16>(qkv, B, S, H, causal, key_mask, out, out_f32, lse, st);
     set_error("tvs_attn_fwd: head dim %d not supported (64 or 16)", hd);
     return -1;
 }

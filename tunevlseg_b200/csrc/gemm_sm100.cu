@@ -20,8 +20,8 @@
 namespace tvs {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int UMMA_K = 16;
+constexpr int BK_BYTES = 128;  // one k-block = one swizzle-128B row: 64 bf16 or 32 fp32 (tf32) elements
+constexpr int MMAS_PER_KB = 4; // 4 x (16 bf16 | 8 tf32) = 32 bytes of K per tcgen05.mma
 constexpr int GEMM_THREADS = 256;
 
 struct GemmEpilogue {
@@ -96,8 +96,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+// fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32, operands are fp32 in shared memory, top 19 bits used)
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -221,14 +232,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 // ---------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
 struct GemmSmem {
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int A_BYTES = BM * BK_BYTES;
+    static constexpr int B_BYTES = BN * BK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
                          int N, int K, GemmEpilogue ep) {
@@ -248,6 +259,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
+    constexpr int BK = TF32 ? BK_BYTES / 4 : BK_BYTES / 2;   // elements of K per k-block
     const int num_kb = (K + BK - 1) / BK;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
 
@@ -291,7 +303,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = umma_idesc(BM, BN, TF32 ? 2u : 1u);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -303,9 +315,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * L::A_BYTES));
                     const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * L::B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < MMAS_PER_KB; ++k) {
+                        // advance 32 bytes (16 bf16 / 8 tf32) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                        if (TF32) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -366,28 +379,29 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle.
-static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D row-major [rows, cols] (bf16 or fp32) with leading dimension ld (elements); box = box_rows x 128 bytes, 128B swizzle.
+static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, bool f32) {
     EncodeTiledFn fn = encode_fn();
     TVS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    const int esz = f32 ? 4 : 2;
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK_BYTES / esz), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TVS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
     return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TF32>
 static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES>;
     CUtensorMap ta, tw;
-    if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.lda, BM)) return rc;
-    if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN)) return rc;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
+    if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.lda, BM, TF32)) return rc;
+    if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN, TF32)) return rc;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, TF32>;
     static bool attr_set = false;
     if (!attr_set) {
         TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -422,8 +436,10 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     TVS_REQUIRE(args != nullptr, "tvs_gemm_bf16: null args");
     const tvs_gemm_args& a = *args;
     TVS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "tvs_gemm_bf16: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
-    TVS_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0, "tvs_gemm_bf16: K, lda, ldw must be multiples of 8 (K=%d lda=%lld ldw=%lld)",
-                a.K, (long long)a.lda, (long long)a.ldw);
+    TVS_REQUIRE(a.ab_dtype == TVS_AB_BF16 || a.ab_dtype == TVS_AB_TF32, "tvs_gemm_bf16: ab_dtype must be TVS_AB_BF16 or TVS_AB_TF32");
+    const int kal = a.ab_dtype == TVS_AB_TF32 ? 4 : 8;   // 16-byte rows for TMA
+    TVS_REQUIRE(a.K % kal == 0 && a.lda % kal == 0 && a.ldw % kal == 0, "tvs_gemm_bf16: K, lda, ldw must be multiples of %d (K=%d lda=%lld ldw=%lld)",
+                kal, a.K, (long long)a.lda, (long long)a.ldw);
     TVS_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
                 "tvs_gemm_bf16: A and W must be 16-byte aligned");
     TVS_REQUIRE(a.out_f32 || a.out_bf16 || a.pre_bf16, "tvs_gemm_bf16: no output");
@@ -452,10 +468,11 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.act = a.act;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N);
+    const bool tf32 = a.ab_dtype == TVS_AB_TF32;
     switch (bn) {
-        case 64: return launch_gemm<64, 8>(a, ep, s);
-        case 128: return launch_gemm<128, 6>(a, ep, s);
-        case 256: return launch_gemm<256, 4>(a, ep, s);
+        case 64: return tf32 ? launch_gemm<64, 8, true>(a, ep, s) : launch_gemm<64, 8, false>(a, ep, s);
+        case 128: return tf32 ? launch_gemm<128, 6, true>(a, ep, s) : launch_gemm<128, 6, false>(a, ep, s);
+        case 256: return tf32 ? launch_gemm<256, 4, true>(a, ep, s) : launch_gemm<256, 4, false>(a, ep, s);
         default: set_error("tvs_gemm_bf16: tile_n must be 0, 64, 128 or 256 (got %d)", bn); return -1;
     }
 }

@@ -49,7 +49,9 @@ def _f(w: torch.Tensor) -> torch.Tensor:
 class PackedLayer:
     """bf16 operands of one transformer block (pre- or post-LN), forward and transposed (dgrad) copies."""
 
-    def __init__(self, layer, heads: int):
+    def __init__(self, layer, heads: int, tf32: bool = False):
+        """``tf32``: also keep fp32 forward operands; the block's forward GEMMs then run kind::tf32 on fp32
+        activations (text tower and decoder: <3 % of the FLOPs but most of the logit rounding error)."""
         sa, mlp = layer.self_attn, layer.mlp
         D = sa.q_proj.weight.shape[0]
         hd = D // heads
@@ -68,6 +70,10 @@ class PackedLayer:
         self.w2_t = _bf(mlp.fc2.weight.t())                     # [F, D]
         self.g1, self.be1 = _f(layer.layer_norm1.weight), _f(layer.layer_norm1.bias)
         self.g2, self.be2 = _f(layer.layer_norm2.weight), _f(layer.layer_norm2.bias)
+        self.tf32 = tf32
+        if tf32:
+            self.wqkv32, self.wo32 = _f(wqkv), _f(sa.out_proj.weight)
+            self.w1_32, self.w2_32 = _f(mlp.fc1.weight), _f(mlp.fc2.weight)
 
 
 class PackedClipSeg:
@@ -101,20 +107,20 @@ class PackedClipSeg:
         self.v_layers = [PackedLayer(l, self.v_heads) for l in vm.encoder.layers]
         self.w_vproj = _bf(model.clip.visual_projection.weight)                      # [proj, Dv]
         # text
-        self.t_layers = [PackedLayer(l, self.t_heads) for l in tm.encoder.layers]
+        self.t_layers = [PackedLayer(l, self.t_heads, tf32=True) for l in tm.encoder.layers]
         self.fin_g, self.fin_b = _f(tm.final_layer_norm.weight), _f(tm.final_layer_norm.bias)
-        self.w_tproj = _bf(model.clip.text_projection.weight)                        # [proj, Dt]
+        self.w_tproj = _f(model.clip.text_projection.weight)                         # [proj, Dt] f32 (tf32 MMA)
         self.w_tproj_t = _bf(model.clip.text_projection.weight.t())
         # decoder
-        self.d_layers = [PackedLayer(l, self.d_heads) for l in dec.layers]
-        self.w_red = [_bf(r.weight) for r in dec.reduces]                            # [Dr, Dv]
+        self.d_layers = [PackedLayer(l, self.d_heads, tf32=True) for l in dec.layers]
+        self.w_red = [_f(r.weight) for r in dec.reduces]                             # [Dr, Dv] f32 (tf32 MMA)
         self.b_red = [_f(r.bias) for r in dec.reduces]
         self.w_red_t = [_bf(r.weight.t()) for r in dec.reduces]                      # [Dv, Dr]
-        self.w_film = _bf(torch.cat((dec.film_mul.weight, dec.film_add.weight), dim=0))      # [2Dr, proj]
+        self.w_film = _f(torch.cat((dec.film_mul.weight, dec.film_add.weight), dim=0))       # [2Dr, proj] f32
         self.b_film = _f(torch.cat((dec.film_mul.bias, dec.film_add.bias)))
         self.w_film_t = _bf(torch.cat((dec.film_mul.weight, dec.film_add.weight), dim=0).t())  # [proj, 2Dr]
         tw = dec.transposed_convolution.weight.detach()                              # [Dr, 1, P, P]
-        self.w_tconv = _bf(tw.reshape(self.Dr, -1).t())                              # [P*P, Dr]
+        self.w_tconv = _f(tw.reshape(self.Dr, -1).t())                               # [P*P, Dr] f32 (tf32 MMA)
         self.w_tconv_t = _bf(tw.reshape(self.Dr, -1))                                # [Dr, P*P]
         self.b_tconv = _f(dec.transposed_convolution.bias)
 
@@ -157,23 +163,27 @@ class Saved:
 def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: bool):
     """Pre-LN block (modeling_clipseg.py:357-387).  x: f32 [B*S, D] -> f32 [B*S, D]."""
     M, D, F = B * S, pk.D, pk.F
-    ln = _e((M, D), BF16, x)
+    hi = pk.tf32                       # fp32 activations + kind::tf32 MMAs for the small, precision-critical towers
+    adt = F32 if hi else BF16
+    ln = _e((M, D), adt, x)
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
-    abi.layernorm_fwd(x, pk.g1, pk.be1, eps, y_bf16=ln, mean=mean1, rstd=rstd1)
+    abi.layernorm_fwd(x, pk.g1, pk.be1, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean1, rstd=rstd1)
     qkv = _e((M, 3 * D), BF16, x)
-    abi.gemm(ln, pk.wqkv, bias=pk.bqkv, out_bf16=qkv)
+    abi.gemm(ln, pk.wqkv32 if hi else pk.wqkv, bias=pk.bqkv, out_bf16=qkv)
     att = _e((M, D), BF16, x)
+    att32 = _e((M, D), F32, x) if hi else None
     lse = _e((B, pk.heads, S), F32, x)
-    abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, causal, key_mask, att, lse)
+    abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, causal, key_mask, att, lse, out_f32=att32)
     x1 = _e((M, D), F32, x)
-    abi.gemm(att, pk.wo, bias=pk.bo, residual=x, out_f32=x1)
+    abi.gemm(att32 if hi else att, pk.wo32 if hi else pk.wo, bias=pk.bo, residual=x, out_f32=x1)
     mean2, rstd2 = _e((M,), F32, x), _e((M,), F32, x)
-    abi.layernorm_fwd(x1, pk.g2, pk.be2, eps, y_bf16=ln, mean=mean2, rstd=rstd2)
+    abi.layernorm_fwd(x1, pk.g2, pk.be2, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean2, rstd=rstd2)
     u = _e((M, F), BF16, x)
-    a = _e((M, F), BF16, x)
-    abi.gemm(ln, pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_bf16=a, act=abi.ACT_QGELU)
+    a = _e((M, F), adt, x)
+    abi.gemm(ln, pk.w1_32 if hi else pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_f32=a if hi else None,
+             out_bf16=None if hi else a, act=abi.ACT_QGELU)
     x2 = _e((M, D), F32, x)
-    abi.gemm(a, pk.w2, bias=pk.b2, residual=x1, out_f32=x2)
+    abi.gemm(a, pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2)
     sv = Saved(x, mean1, rstd1, qkv, att, lse, x1, mean2, rstd2, u) if save else None
     return x2, sv
 
@@ -213,27 +223,28 @@ class SavedDec:
     rstd2: torch.Tensor
 
 
-def decoder_layer_fwd(pk: PackedLayer, x, x16, B, S, eps):
-    """Post-LN block with ReLU MLP (modeling_clipseg.py:390-437).  Returns (y f32, y bf16, saved)."""
+def decoder_layer_fwd(pk: PackedLayer, x, B, S, eps):
+    """Post-LN block with ReLU MLP (modeling_clipseg.py:390-437), fp32 activations, kind::tf32 GEMMs.
+    Returns (y f32, saved)."""
     M, D, F = B * S, pk.D, pk.F
     qkv = _e((M, 3 * D), BF16, x)
-    abi.gemm(x16, pk.wqkv, bias=pk.bqkv, out_bf16=qkv)
-    att = _e((M, D), BF16, x)
+    abi.gemm(x, pk.wqkv32, bias=pk.bqkv, out_bf16=qkv)
+    att, att32 = _e((M, D), BF16, x), _e((M, D), F32, x)
     lse = _e((B, pk.heads, S), F32, x)
-    abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, False, None, att, lse)
+    abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, False, None, att, lse, out_f32=att32)
     s1 = _e((M, D), F32, x)
-    abi.gemm(att, pk.wo, bias=pk.bo, residual=x, out_f32=s1)
-    y1, y1_16 = _e((M, D), F32, x), _e((M, D), BF16, x)
+    abi.gemm(att32, pk.wo32, bias=pk.bo, residual=x, out_f32=s1)
+    y1 = _e((M, D), F32, x)
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
-    abi.layernorm_fwd(s1, pk.g1, pk.be1, eps, y_f32=y1, y_bf16=y1_16, mean=mean1, rstd=rstd1)
-    a = _e((M, F), BF16, x)
-    abi.gemm(y1_16, pk.w1, bias=pk.b1, out_bf16=a, act=abi.ACT_RELU)
+    abi.layernorm_fwd(s1, pk.g1, pk.be1, eps, y_f32=y1, mean=mean1, rstd=rstd1)
+    a32, a16 = _e((M, F), F32, x), _e((M, F), BF16, x)
+    abi.gemm(y1, pk.w1_32, bias=pk.b1, out_f32=a32, out_bf16=a16, act=abi.ACT_RELU)
     s2 = _e((M, D), F32, x)
-    abi.gemm(a, pk.w2, bias=pk.b2, residual=y1, out_f32=s2)
-    y2, y2_16 = _e((M, D), F32, x), _e((M, D), BF16, x)
+    abi.gemm(a32, pk.w2_32, bias=pk.b2, residual=y1, out_f32=s2)
+    y2 = _e((M, D), F32, x)
     mean2, rstd2 = _e((M,), F32, x), _e((M,), F32, x)
-    abi.layernorm_fwd(s2, pk.g2, pk.be2, eps, y_f32=y2, y_bf16=y2_16, mean=mean2, rstd=rstd2)
-    return y2, y2_16, SavedDec(qkv, att, lse, s1, mean1, rstd1, a, s2, mean2, rstd2)
+    abi.layernorm_fwd(s2, pk.g2, pk.be2, eps, y_f32=y2, mean=mean2, rstd=rstd2)
+    return y2, SavedDec(qkv, att, lse, s1, mean1, rstd1, a16, s2, mean2, rstd2)
 
 
 def decoder_layer_bwd(pk: PackedLayer, sv: SavedDec, g, B, S):
@@ -395,9 +406,9 @@ class TextTowerFn(torch.autograd.Function):
         mean_f, rstd_f = _e((B * S,), F32, x), _e((B * S,), F32, x)
         abi.layernorm_fwd(x, pk.fin_g, pk.fin_b, pk.eps, y_f32=xf, mean=mean_f, rstd=rstd_f)
         rows = torch.arange(B, device=x.device) * S + pool_pos.to(x.device)
-        pooled16 = xf.index_select(0, rows).to(BF16)
+        pooled = xf.index_select(0, rows)
         cond = _e((B, pk.w_tproj.shape[0]), F32, x)
-        abi.gemm(pooled16, pk.w_tproj, out_f32=cond)
+        abi.gemm(pooled, pk.w_tproj, out_f32=cond)
         ctx.pk, ctx.saved, ctx.km = pk, saved, km
         ctx.fin = (x, mean_f, rstd_f, rows)
         ctx.dims = (B, S, D, depth, n_ctx, None if cd is None else tuple(cd.shape))
@@ -448,30 +459,28 @@ class DecoderFn(torch.autograd.Function):
         M = B * S
         acts = taps[::-1]
         cond_d = cond.detach().to(F32).contiguous()
-        out = out16 = None
+        out = None
         saved_layers, film_saved = [], None
         for i, act in enumerate(acts):
-            a16 = _e((M, Dv), BF16, act)
-            abi.cast_bf16(act.detach().contiguous().view(M, Dv), a16)
-            r, r16 = _e((M, Dr), F32, act), _e((M, Dr), BF16, act)
-            abi.gemm(a16, pk.w_red[i], bias=pk.b_red[i], residual=out, out_f32=r, out_bf16=r16)
+            r = _e((M, Dr), F32, act)
+            abi.gemm(act.detach().contiguous().view(M, Dv), pk.w_red[i], bias=pk.b_red[i], residual=out, out_f32=r)
             if i == pk.conditional_layer:
                 film = _e((B, 2 * Dr), F32, act)
-                abi.gemm(cond_d.to(BF16), pk.w_film, bias=pk.b_film, out_f32=film)
+                abi.gemm(cond_d, pk.w_film, bias=pk.b_film, out_f32=film)
                 mul, add = film[:, :Dr].contiguous(), film[:, Dr:].contiguous()
-                y, y16 = _e((M, Dr), F32, act), _e((M, Dr), BF16, act)
-                abi.film_fwd(r.view(B, S, Dr), mul, add, y.view(B, S, Dr), y16.view(B, S, Dr))
+                y = _e((M, Dr), F32, act)
+                abi.film_fwd(r.view(B, S, Dr), mul, add, y.view(B, S, Dr), None)
                 film_saved = (r, mul)
-                r, r16 = y, y16
-            out, out16, sv = decoder_layer_fwd(pk.d_layers[i], r, r16, B, S, pk.eps)
+                r = y
+            out, sv = decoder_layer_fwd(pk.d_layers[i], r, B, S, pk.eps)
             saved_layers.append(sv)
         G2 = G * G
         if 1 + G2 + n_strip != S:
             raise ValueError(f"decoder: sequence {S} != 1 + {G2} patches + {n_strip} prompt rows")
-        feat32, feat16 = _e((B, G2, Dr), F32, out), _e((B, G2, Dr), BF16, out)
-        abi.slice_rows(out.view(B, S, Dr), 1, G2, y_f32=feat32, y_bf16=feat16)
+        feat32 = _e((B, G2, Dr), F32, out)
+        abi.slice_rows(out.view(B, S, Dr), 1, G2, y_f32=feat32)
         tconv = _e((B * G2, P * P), F32, out)
-        abi.gemm(feat16.view(B * G2, Dr), pk.w_tconv, out_f32=tconv)
+        abi.gemm(feat32.view(B * G2, Dr), pk.w_tconv, out_f32=tconv)
         H = G * P
         logits = _e((B, 1, H, H), F32, out)
         addmap = add_out = wa16 = ratio_d = add_b_d = None
@@ -481,10 +490,10 @@ class DecoderFn(torch.autograd.Function):
             KK = ks * ks
             # contract the channels of the k x k conv at LOW resolution: addmap[., ky*ks+kx] = feat . w[:, ky, kx]
             wa = add_w.detach().to(F32).reshape(Dr, KK).t().contiguous()           # [KK, Dr]
-            wa16 = torch.zeros((32 * ((KK + 31) // 32), Dr), dtype=BF16, device=out.device)
+            wa16 = torch.zeros((32 * ((KK + 31) // 32), Dr), dtype=BF16, device=out.device)   # padded bf16 copy for the dgrad
             wa16[:KK] = wa.to(BF16)
             addmap = torch.zeros((B * G2, wa16.shape[0]), dtype=F32, device=out.device)
-            abi.gemm(feat16.view(B * G2, Dr), wa16[:KK], out_f32=addmap[:, :KK])
+            abi.gemm(feat32.view(B * G2, Dr), wa, out_f32=addmap[:, :KK])
             add_out = _e((B, H, H), F32, out) if blend == abi.BLEND_RATIO else None
             ratio_d = None if ratio is None else ratio.detach().to(F32).reshape(1).contiguous()
             add_b_d = add_b.detach().to(F32).contiguous()
@@ -545,7 +554,7 @@ class DecoderFn(torch.autograd.Function):
                 dfilm[:, :Dr] = dmul
                 dfilm[:, Dr:] = dadd
                 dcond = _e((B, pk.w_film_t.shape[0]), F32, dl)
-                abi.gemm(dfilm.to(BF16), pk.w_film_t, out_f32=dcond)
+                abi.gemm(dfilm.to(BF16), pk.w_film_t, out_f32=dcond)   # gradients stay on the bf16 path
                 g = dr
             if need_taps:
                 g16 = _e((M, Dr), BF16, dl)
