@@ -378,3 +378,51 @@ def counter_inc(counter):
     require_device()
     _chk(counter, torch.int32, "counter")
     _ck(load().tvs_counter_inc(counter.data_ptr(), _stream()), "tvs_counter_inc")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# optional per-call timing (bench.py's kernel-share / roofline pass): CUDA events on the launching stream
+# ------------------------------------------------------------------------------------------------------------------
+_prof: list | None = None
+
+
+def set_profiler(records: list | None) -> None:
+    """When ``records`` is a list every op below appends (name, key, start_event, end_event, algorithmic_flops)."""
+    global _prof
+    _prof = records
+
+
+def _flops(name, args, kwargs) -> tuple[str, float]:
+    if name == "gemm":
+        (M, K), N = args[0].shape, args[1].shape[0]
+        return f"{M}x{N}x{K}{'_tf32' if args[0].dtype == torch.float32 else ''}", 2.0 * M * N * K
+    if name == "attn_fwd":
+        _, B, S, H, hd = args[:5]
+        return f"B{B}S{S}H{H}d{hd}", 4.0 * B * H * S * S * hd
+    if name == "attn_bwd":
+        B, S, H, hd = args[4:8]
+        return f"B{B}S{S}H{H}d{hd}", 10.0 * B * H * S * S * hd
+    return "", 0.0
+
+
+def _wrap(fn, name):
+    def op(*args, **kwargs):
+        if _prof is None:
+            return fn(*args, **kwargs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*args, **kwargs)
+        e1.record()
+        key, fl = _flops(name, args, kwargs)
+        _prof.append((name, key, e0, e1, fl))
+        return out
+
+    op.__name__, op.__doc__ = fn.__name__, fn.__doc__
+    return op
+
+
+for _n in ("gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "im2col_patches", "vision_assemble",
+           "prompt_overwrite", "prompt_grad", "slice_rows", "unslice_rows", "wgrad_small", "cast_bf16", "add_f32", "film_fwd",
+           "film_bwd", "head_fwd", "head_bwd", "dicebce_metrics_fwd", "dicebce_bwd", "metrics_from_probs", "adamw_flat",
+           "counter_inc"):
+    globals()[_n] = _wrap(globals()[_n], _n)
