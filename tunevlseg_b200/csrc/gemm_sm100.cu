@@ -37,6 +37,7 @@ struct GemmEpilogue {
     const __nv_bfloat16* aux_bf16;
     long long ldaux;
     int act;
+    int vec_ok;   // every leading dimension % 4 == 0 and every pointer 16-byte aligned -> vector epilogue
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -137,94 +138,84 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue math for one 32-column chunk of one row
+// epilogue.  TMEM gives every thread one ROW of the accumulator (32 consecutive columns per tcgen05.ld); storing
+// rows straight to global memory makes each warp store touch 32 different lines.  So each epilogue warp transposes
+// its 32x32 chunk through a private shared-memory stage (row stride 36 floats: conflict-free for the 128-bit row
+// writes and for the 128-bit reads below) and then works on COALESCED positions: a quarter-warp covers one 128-byte
+// row segment, a warp instruction covers 4 rows, 8 passes cover the chunk.  All fused operand reads (bias, residual,
+// saved pre-activation) and all output writes use the same coalesced mapping.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0,
-                                               int N) {
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-    const bool full = (col0 + 32 <= N);
-    if (full) {
-        if (ep.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 b = __ldg(b4 + i);
-                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-            }
+constexpr int EPI_LD = 36;                       // floats per staged row
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;     // 4608 bytes per epilogue warp
+
+__device__ __forceinline__ float epi_act(const GemmEpilogue& ep, float v, float aux) {
+    if (ep.act == TVS_ACT_QGELU) return quick_gelu(v);
+    if (ep.act == TVS_ACT_RELU) return fmaxf(v, 0.0f);
+    if (ep.act == TVS_ACT_DQGELU) return v * quick_gelu_grad(aux);
+    if (ep.act == TVS_ACT_DRELU) return aux > 0.0f ? v : 0.0f;
+    return v;
+}
+
+// 4 consecutive columns [col, col+4) of one row, all vector accesses 16-byte (f32) / 8-byte (bf16) aligned
+__device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, float4 bias, long long row, int col) {
+    v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+    if (ep.pre_bf16) *reinterpret_cast<uint2*>(ep.pre_bf16 + row * ep.ldpre + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    if (ep.act != TVS_ACT_NONE) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.act >= TVS_ACT_DQGELU) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(ep.aux_bf16 + row * ep.ldaux + col));
+            const float2 lo = unpack_bf16x2(q.x), hi = unpack_bf16x2(q.y);
+            a = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
-        if (ep.pre_bf16) {
-            uint4* p = reinterpret_cast<uint4*>(ep.pre_bf16 + row * ep.ldpre + col0);
+        v.x = epi_act(ep, v.x, a.x); v.y = epi_act(ep, v.y, a.y); v.z = epi_act(ep, v.z, a.z); v.w = epi_act(ep, v.w, a.w);
+    }
+    if (ep.residual) {
+        const float4 r = *reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + row * ep.ldo32 + col) = v;
+    if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + row * ep.ldo16 + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// scalar, fully predicated (ragged N such as the 25-tap additive map, or unaligned leading dimensions)
+__device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& ep, float x, long long row, int c) {
+    if (ep.bias) x += __ldg(ep.bias + c);
+    if (ep.pre_bf16) ep.pre_bf16[row * ep.ldpre + c] = __float2bfloat16(x);
+    if (ep.act != TVS_ACT_NONE) x = epi_act(ep, x, ep.act >= TVS_ACT_DQGELU ? __bfloat162float(ep.aux_bf16[row * ep.ldaux + c]) : 0.f);
+    if (ep.residual) x += ep.residual[row * ep.ldr + c];
+    if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = x;
+    if (ep.out_bf16) ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
+}
+
+// one 32x32 chunk: acc = this thread's row (lane) of the chunk; stage = this warp's private staging area
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&acc)[32], float* stage, long long row0, int col0,
+                                               int M, int N, int lane) {
+    float4* srow = reinterpret_cast<float4*>(stage + lane * EPI_LD);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                p[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    for (int i = 0; i < 8; ++i)
+        srow[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+    __syncwarp();
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int col = col0 + c4;
+    if (ep.vec_ok && col + 4 <= N) {
+        const float4 bias = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int rr = p * 4 + rsub;
+            const long long row = row0 + rr;
+            if (row < M) epilogue_vec4(ep, *reinterpret_cast<const float4*>(stage + rr * EPI_LD + c4), bias, row, col);
         }
-        if (ep.act == TVS_ACT_QGELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
-        } else if (ep.act == TVS_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-        } else if (ep.act == TVS_ACT_DQGELU || ep.act == TVS_ACT_DRELU) {
-            const uint4* a = reinterpret_cast<const uint4*>(ep.aux_bf16 + row * ep.ldaux + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint4 q = __ldg(a + i);
-                uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float2 u = unpack_bf16x2(w[j]);
-                    if (ep.act == TVS_ACT_DQGELU) {
-                        v[8 * i + 2 * j] *= quick_gelu_grad(u.x);
-                        v[8 * i + 2 * j + 1] *= quick_gelu_grad(u.y);
-                    } else {
-                        v[8 * i + 2 * j] = u.x > 0.0f ? v[8 * i + 2 * j] : 0.0f;
-                        v[8 * i + 2 * j + 1] = u.y > 0.0f ? v[8 * i + 2 * j + 1] : 0.0f;
-                    }
-                }
-            }
-        }
-        if (ep.residual) {
-            const float4* r4 = reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 r = r4[i];
-                v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-            }
-        }
-        if (ep.out_f32) {
-            float4* o = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ldo32 + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (ep.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + row * ep.ldo16 + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-        }
-    } else {
-        // ragged N tail (e.g. the 25-tap additive map): scalar, fully predicated
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            int c = col0 + i;
-            if (c < N) {
-                float x = v[i];
-                if (ep.bias) x += __ldg(ep.bias + c);
-                if (ep.pre_bf16) ep.pre_bf16[row * ep.ldpre + c] = __float2bfloat16(x);
-                if (ep.act == TVS_ACT_QGELU) x = quick_gelu(x);
-                else if (ep.act == TVS_ACT_RELU) x = fmaxf(x, 0.0f);
-                else if (ep.act == TVS_ACT_DQGELU) x *= quick_gelu_grad(__bfloat162float(ep.aux_bf16[row * ep.ldaux + c]));
-                else if (ep.act == TVS_ACT_DRELU) x = __bfloat162float(ep.aux_bf16[row * ep.ldaux + c]) > 0.0f ? x : 0.0f;
-                if (ep.residual) x += ep.residual[row * ep.ldr + c];
-                if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = x;
-                if (ep.out_bf16) ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
-            }
+    } else if (col < N) {
+#pragma unroll 1
+        for (int p = 0; p < 8; ++p) {
+            const int rr = p * 4 + rsub;
+            const long long row = row0 + rr;
+            if (row < M)
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < N) epilogue_scalar(ep, stage[rr * EPI_LD + c4 + j], row, col + j);
         }
     }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -236,7 +227,8 @@ struct GemmSmem {
     static constexpr int B_BYTES = BN * BK_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+    static constexpr int EPI_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;     // 16-byte aligned
+    static constexpr int TOTAL = EPI_OFFSET + 4 * EPI_WARP_FLOATS * 4 + 1024;     // + alignment slack
 };
 
 template <int BN, int STAGES, bool TF32>
@@ -335,14 +327,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const long long row = static_cast<long long>(m_blk) * BM + ew * 32 + lane;
+            const long long row0 = static_cast<long long>(m_blk) * BM + ew * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+            float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + ew * EPI_WARP_FLOATS;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n_blk * BN + c * 32;
+                if (row0 >= M || col0 >= N) break;      // warp-uniform: nothing of this chunk is inside the matrix
                 uint32_t r[32];
                 tmem_ld_32x32(t_row + c * 32, r);
-                const int col0 = n_blk * BN + c * 32;
-                if (row < M && col0 < N) epilogue_chunk(ep, r, row, col0, N);
+                epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -444,15 +438,10 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
                 "tvs_gemm_bf16: A and W must be 16-byte aligned");
     TVS_REQUIRE(a.out_f32 || a.out_bf16 || a.pre_bf16, "tvs_gemm_bf16: no output");
     TVS_REQUIRE(!(a.act == TVS_ACT_DQGELU || a.act == TVS_ACT_DRELU) || a.aux_bf16, "tvs_gemm_bf16: aux_bf16 required for derivative epilogues");
-    if (a.N % 32 == 0 || a.N > 32) {
-        // vector paths are used for every full 32-column chunk: check their alignment once
-        TVS_REQUIRE(!a.out_f32 || (a.ldo32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0), "tvs_gemm_bf16: out_f32 alignment");
-        TVS_REQUIRE(!a.out_bf16 || (a.ldo16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0), "tvs_gemm_bf16: out_bf16 alignment");
-        TVS_REQUIRE(!a.pre_bf16 || (a.ldpre % 8 == 0 && (reinterpret_cast<uintptr_t>(a.pre_bf16) & 15) == 0), "tvs_gemm_bf16: pre_bf16 alignment");
-        TVS_REQUIRE(!a.aux_bf16 || (a.ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(a.aux_bf16) & 15) == 0), "tvs_gemm_bf16: aux_bf16 alignment");
-        TVS_REQUIRE(!a.residual || (a.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0), "tvs_gemm_bf16: residual alignment");
-        TVS_REQUIRE(!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "tvs_gemm_bf16: bias alignment");
-    }
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec_ok = (!a.out_f32 || (a.ldo32 % 4 == 0 && al16(a.out_f32))) && (!a.out_bf16 || (a.ldo16 % 4 == 0 && al16(a.out_bf16))) &&
+                        (!a.pre_bf16 || (a.ldpre % 4 == 0 && al16(a.pre_bf16))) && (!a.aux_bf16 || (a.ldaux % 4 == 0 && al16(a.aux_bf16))) &&
+                        (!a.residual || (a.ldr % 4 == 0 && al16(a.residual))) && (!a.bias || al16(a.bias));
     GemmEpilogue ep;
     ep.bias = a.bias;
     ep.residual = a.residual;
@@ -466,6 +455,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.aux_bf16 = static_cast<const __nv_bfloat16*>(a.aux_bf16);
     ep.ldaux = a.ldaux;
     ep.act = a.act;
+    ep.vec_ok = vec_ok ? 1 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N);
     const bool tf32 = a.ab_dtype == TVS_AB_TF32;

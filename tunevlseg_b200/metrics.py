@@ -42,9 +42,16 @@ class Dice(_Metric):
             raise NotImplementedError("only average='samples' (the reference's setting) is implemented")
         self.threshold, self.zero_division = float(threshold), float(zero_division)
         self._counts: list[torch.Tensor] = []
+        # streaming state for CUDA-graph replay (a Python list cannot grow inside a replayed graph): running sum of the
+        # per-sample scores and the sample count, updated by device ops; same value as the cat-reduced lists
+        self.streaming = False
+        self.register_buffer("_score_sum", torch.zeros((), dtype=torch.float64), persistent=False)
+        self.register_buffer("_n", torch.zeros((), dtype=torch.int64), persistent=False)
 
     def reset(self) -> None:
         self._counts = []
+        self._score_sum.zero_()
+        self._n.zero_()
 
     @staticmethod
     def score(counts: torch.Tensor, zero_division: float) -> torch.Tensor:
@@ -55,8 +62,13 @@ class Dice(_Metric):
 
     def update_from_counts(self, counts: torch.Tensor) -> torch.Tensor:
         """counts: int64 (B,3) tp/fp/fn from the fused kernel.  Returns this batch's value (torchmetrics ``forward``)."""
-        self._counts.append(counts)
-        return self.score(counts, self.zero_division)
+        value = self.score(counts, self.zero_division)
+        if self.streaming:
+            self._score_sum += value.to(torch.float64) * counts.shape[0]
+            self._n += counts.shape[0]
+        else:
+            self._counts.append(counts)
+        return value
 
     def update(self, preds: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if preds.shape != target.shape:
@@ -64,6 +76,11 @@ class Dice(_Metric):
         return self.update_from_counts(_counts_from_probs(preds, target, self.threshold)[0])
 
     def compute(self) -> torch.Tensor:
+        if self.streaming:
+            tot = torch.stack((self._score_sum, self._n.to(torch.float64)))
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            return (tot[0] / tot[1]).to(torch.float32)
         if not self._counts:
             raise RuntimeError("Dice.compute() called before any update")
         counts = torch.cat(self._counts)
