@@ -544,6 +544,10 @@ int main(int argc, char** argv) {
     if (what == "ln" || what == "all") test_ln();
     if (what == "attn" || what == "all") test_attn();
     if (what == "gemm" || what == "all") test_gemm();
+    if (what == "gemmprof") {   // one shape, for ncu
+        gemm_case(15648, 2304, 768, TVS_ACT_NONE, true, false, false, true, false, 128, true);
+        gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, 256, true);
+    }
     printf("launches: %lld\n", (long long)tvs_launch_count());
     printf(g_fail ? "SELFTEST FAILED (%d cases)\n" : "SELFTEST PASSED\n", g_fail);
     return g_fail ? 1 : 0;

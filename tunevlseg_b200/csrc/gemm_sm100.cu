@@ -13,6 +13,7 @@
 //
 // Replaces the nn.Linear calls of HF CLIPSeg (modeling_clipseg.py:297-300, :345-353) and their dgrad.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tvs_b200.h"
@@ -37,7 +38,9 @@ struct GemmEpilogue {
     const __nv_bfloat16* aux_bf16;
     long long ldaux;
     int act;
-    int vec_ok;   // every leading dimension % 4 == 0 and every pointer 16-byte aligned -> vector epilogue
+    int vec_ok;      // every leading dimension % 4 == 0 and every pointer 16-byte aligned -> 128-bit staged epilogue
+    int vec256_ok;   // 32-byte aligned rows for every operand -> direct 256-bit epilogue (the default)
+    int staged;      // force the shared-memory staged (coalesced) epilogue
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -185,6 +188,85 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& ep, float x,
     if (ep.residual) x += ep.residual[row * ep.ldr + c];
     if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = x;
     if (ep.out_bf16) ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
+}
+
+// ---- direct epilogue: the thread keeps its TMEM row and moves 32 bytes per instruction (LDG.256 / STG.256, sm_100) ----
+// With cta_group::1 and 128-row tiles the tensor core already consumes most of the 128 B/clk shared-memory
+// bandwidth for its operands, so staging the accumulator through shared memory (below) slows the MMA down more than
+// coalescing helps (measured: 2x slower).  Full 32-byte sectors per thread keep the L2 write path efficient enough.
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+                 "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_bf16_row32(__nv_bfloat16* p, const float (&v)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[16 * h + 2 * i], v[16 * h + 2 * i + 1]);
+        st256(p + 16 * h, w);
+    }
+}
+
+// one row (this thread's TMEM lane), 32 consecutive columns starting at col0; requires ep.vec256_ok and col0 + 32 <= N
+__device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    if (ep.bias) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t b[8];
+            ld256(ep.bias + col0 + 8 * q, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * q + i] += __uint_as_float(b[i]);
+        }
+    }
+    if (ep.pre_bf16) st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, v);
+    if (ep.act == TVS_ACT_QGELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+    } else if (ep.act == TVS_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (ep.act >= TVS_ACT_DQGELU) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t a[8];
+            ld256(ep.aux_bf16 + row * ep.ldaux + col0 + 16 * h, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 u = unpack_bf16x2(a[i]);
+                v[16 * h + 2 * i] = epi_act(ep, v[16 * h + 2 * i], u.x);
+                v[16 * h + 2 * i + 1] = epi_act(ep, v[16 * h + 2 * i + 1], u.y);
+            }
+        }
+    }
+    if (ep.residual) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r[8];
+            ld256(ep.residual + row * ep.ldr + col0 + 8 * q, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * q + i] += __uint_as_float(r[i]);
+        }
+    }
+    if (ep.out_f32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(v[8 * q + i]);
+            st256(ep.out_f32 + row * ep.ldo32 + col0 + 8 * q, o);
+        }
+    }
+    if (ep.out_bf16) st_bf16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
 }
 
 // one 32x32 chunk: acc = this thread's row (lane) of the chunk; stage = this warp's private staging area
@@ -336,7 +418,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if (row0 >= M || col0 >= N) break;      // warp-uniform: nothing of this chunk is inside the matrix
                 uint32_t r[32];
                 tmem_ld_32x32(t_row + c * 32, r);
-                epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
+                if (ep.vec256_ok && !ep.staged && col0 + 32 <= N) {
+                    if (row0 + lane < M) epilogue_direct(ep, r, row0 + lane, col0);
+                } else {
+                    epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -456,6 +542,13 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.ldaux = a.ldaux;
     ep.act = a.act;
     ep.vec_ok = vec_ok ? 1 : 0;
+    auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+    ep.vec256_ok = ((!a.out_f32 || (a.ldo32 % 8 == 0 && al32(a.out_f32))) && (!a.out_bf16 || (a.ldo16 % 16 == 0 && al32(a.out_bf16))) &&
+                    (!a.pre_bf16 || (a.ldpre % 16 == 0 && al32(a.pre_bf16))) && (!a.aux_bf16 || (a.ldaux % 16 == 0 && al32(a.aux_bf16))) &&
+                    (!a.residual || (a.ldr % 8 == 0 && al32(a.residual))) && (!a.bias || al32(a.bias)))
+                       ? 1 : 0;
+    static const bool force_staged = [] { const char* e = getenv("TVS_GEMM_EPILOGUE"); return e && e[0] == 's'; }();
+    ep.staged = force_staged ? 1 : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N);
     const bool tf32 = a.ab_dtype == TVS_AB_TF32;

@@ -140,6 +140,10 @@ class ImageTextMaskModule(_Base):
 
     # ---- metrics / optimisers --------------------------------------------------------------------------------------
     def store_and_register_metrics(self, metric_name: str, metric: Any) -> None:
+        if isinstance(metric, nn.Module):          # setup() may run after the module was moved to the GPU
+            p = next(self.parameters(), None)
+            if p is not None:
+                metric = metric.to(p.device)
         setattr(self, metric_name, metric)
         self.registered_metric_names.append(metric_name)
 
