@@ -378,7 +378,9 @@ static void attn_timing(int B, int S, int H, int hd) {
 }
 
 static void test_attn() {
+    attn_case(1, 128, 1, 64, 0, false);
     attn_case(1, 64, 1, 64, 0, false);
+    attn_case(2, 493, 12, 64, 0, false);
     attn_case(2, 100, 2, 64, 0, false);
     attn_case(2, 489, 2, 64, 0, false);
     attn_case(3, 77, 2, 64, 1, true);
@@ -544,9 +546,22 @@ int main(int argc, char** argv) {
     if (what == "ln" || what == "all") test_ln();
     if (what == "attn" || what == "all") test_attn();
     if (what == "gemm" || what == "all") test_gemm();
-    if (what == "gemmprof") {   // one shape, for ncu
-        gemm_case(15648, 2304, 768, TVS_ACT_NONE, true, false, false, true, false, 128, true);
-        gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, 256, true);
+    if (what == "gemmprof") {   // epilogue cost isolation on the fc1 shape (for timing / ncu)
+        const int bn = argc > 3 ? atoi(argv[3]) : 256;
+        printf("-- N=3072: bf16 out only\n");
+        gemm_case(15648, 3072, 768, TVS_ACT_NONE, true, false, false, true, false, bn, true);
+        printf("-- N=3072: bf16 out + pre (two stores, no gelu)\n");
+        gemm_case(15648, 3072, 768, TVS_ACT_NONE, true, false, false, true, true, bn, true);
+        printf("-- N=3072: gelu, one store\n");
+        gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, false, bn, true);
+        printf("-- N=3072: gelu + pre (fc1 forward)\n");
+        gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, bn, true);
+        printf("-- N=3072: dgelu (aux read, one store)\n");
+        gemm_case(15648, 3072, 768, TVS_ACT_DQGELU, false, false, false, true, false, bn, true);
+        printf("-- N=768 K=768: residual f32 in/out\n");
+        gemm_case(15648, 768, 768, TVS_ACT_NONE, true, true, true, false, false, 128, true);
+        printf("-- N=768 K=768: bf16 out only\n");
+        gemm_case(15648, 768, 768, TVS_ACT_NONE, true, false, false, true, false, 128, true);
     }
     printf("launches: %lld\n", (long long)tvs_launch_count());
     printf(g_fail ? "SELFTEST FAILED (%d cases)\n" : "SELFTEST PASSED\n", g_fail);

@@ -520,6 +520,11 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
     return check_launch("attn_bwd_dq_kernel");
 }
 
+// tcgen05 / TMEM kernels for head dim 64 without masks (attention_sm100.cu)
+bool attn_tc_enabled();
+int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st);
+int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st);
+
 }  // namespace tvs
 
 extern "C" __attribute__((visibility("default"))) int tvs_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask,
@@ -528,6 +533,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_attn_fwd(const void* q
     TVS_REQUIRE(qkv && out && lse, "tvs_attn_fwd: null pointer");
     TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (hd == 64 && !causal && !key_mask && attn_tc_enabled()) return attn_tc_fwd(qkv, B, S, H, out, out_f32, lse, st);
     if (hd == 64) return attn_fwd_launch<64>(qkv, B, S, H, causal, key_mask, out, out_f32, lse, st);
     if (hd == 16) return attn_fwd_launch<16>(qkv, B, S, H, causal, key_mask, out, out_f32, lse, st);
     set_error("tvs_attn_fwd: head dim %d not supported (64 or 16)", hd);
@@ -540,6 +546,13 @@ extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd(const void* q
     TVS_REQUIRE(qkv && out && dout && lse && delta && dqkv, "tvs_attn_bwd: null pointer");
     TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_bwd: bad shape B=%d S=%d H=%d", B, S, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (hd == 64 && !causal && !key_mask && attn_tc_enabled()) {
+        const long long rows = static_cast<long long>(B) * S;
+        attn_delta_kernel<64><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
+                                                                                      static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta);
+        if (int rc = check_launch("attn_delta_kernel")) return rc;
+        return attn_tc_bwd(qkv, dout, lse, delta, B, S, H, dqkv, st);
+    }
     if (hd == 64) return attn_bwd_launch<64>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);
     if (hd == 16) return attn_bwd_launch<16>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);
     set_error("tvs_attn_bwd: head dim %d not supported (64 or 16)", hd);

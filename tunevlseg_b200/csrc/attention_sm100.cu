@@ -1,0 +1,465 @@
+// tcgen05 / TMEM / TMA flash attention for the CLIP vision tower: head dim 64, no mask, any sequence length.
+//
+// Replaces eager_attention_forward (transformers modeling_clipseg.py:256-276) and its backward for the shapes that
+// carry 14 % of the step's FLOPs (S = 485 + n, 12 heads).  Scores live in TMEM and never touch shared or global memory.
+//
+// One CTA = one (batch, head, 128-row outer tile); 192 threads:
+//   warps 0-3  element-wise stage: thread t owns TMEM lane t (one row): tcgen05.ld scores, exp2 / scaling in registers,
+//              tcgen05.st the bf16 probabilities back into TMEM (two per 32-bit column) as the A operand of the next MMA
+//   warp 4     TMA producer (3-D tensor maps [feature, token, batch]: rows past the sequence end are zero-filled)
+//   warp 5     tcgen05.mma issuer (one lane) + TMEM allocation
+// Every "score" MMA is 128x128x64 with both operands K-major in shared memory; every "accumulate" MMA is 128x64x128
+// with A read from TMEM and B = the SAME shared-memory tile addressed MN-major (the 64 features are contiguous).
+//
+//   FWD  outer = Q tile, inner = K/V tiles.  Two passes over the keys instead of an online rescale: pass 1 recomputes
+//        S = Q K^T per tile only for the row maximum, pass 2 recomputes S, writes P = exp2(S - m) and accumulates
+//        O += P V in TMEM.  (The exp units, not the tensor core, bound this kernel; the second Q K^T is nearly free and
+//        removes the accumulator read-modify-write.)  256 TMEM columns -> two CTAs per SM overlap MMA and exp.
+//   DQ   outer = Q, dO tile; inner = K/V: S = Q K^T, dP = dO V^T, dS = P o (dP - delta) -> TMEM, dQ += dS K.
+//   DKV  outer = K, V tile; inner = Q/dO (+ lse, delta rows): S^T = K Q^T, dP^T = V dO^T, P^T and dS^T -> TMEM,
+//        dV += P^T dO, dK += dS^T Q.
+// The 1/sqrt(d) scale is folded into Wq by the host.  lse is the natural-log-sum-exp per row, delta = rowsum(dO o O).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tvs_b200.h"
+
+namespace tvs {
+using namespace ptx;
+
+constexpr int AT = 128;                    // tile rows
+constexpr int AHD = 64;                    // head dim
+constexpr int ATILE = AT * AHD * 2;        // 16 KB per [128 x 64] bf16 tile
+constexpr int ATC_THREADS = 192;
+constexpr float L2E = 1.4426950408889634f;
+enum { MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2 };
+
+__device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2, flushes denormals; exp2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MODE>
+struct AtcSmem {
+    static constexpr int N_OUTER = MODE == MODE_FWD ? 1 : 2;
+    static constexpr int OUTER = 0;
+    static constexpr int INNER = N_OUTER * ATILE;                 // 2 stages x 2 tiles
+    static constexpr int VEC = INNER + 4 * ATILE;                 // [2 stages][2][128] floats (DKV: lse, delta)
+    static constexpr int BAR = VEC + 2 * 2 * AT * 4;
+    static constexpr int TOTAL = BAR + 16 * 8 + 1024;             // barriers + tmem slot + alignment slack
+};
+
+__device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float scale) {
+    // 64 fp32 accumulators (two 32-column TMEM loads) -> 64 bf16 = 128 bytes = 4 x 256-bit stores
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = 16 * q + 2 * i;
+            const float x0 = __uint_as_float(e < 32 ? a[e] : b[e - 32]) * scale;
+            const float x1 = __uint_as_float(e + 1 < 32 ? a[e + 1] : b[e + 1 - 32]) * scale;
+            w[i] = pack_bf16x2(x0, x1);
+        }
+        st_global_256(dst + 16 * q, w);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ATC_THREADS, MODE == MODE_FWD ? 2 : 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, int S, int H,
+               __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out,
+               const float* __restrict__ lse_in, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv) {
+    using L = AtcSmem<MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* s_outer0 = smem + L::OUTER;
+    uint8_t* s_outer1 = s_outer0 + ATILE;                       // only when N_OUTER == 2
+    uint8_t* s_inner = smem + L::INNER;                         // stage s: tile0 at s*2*ATILE, tile1 at +ATILE
+    float* s_vec = reinterpret_cast<float*>(smem + L::VEC);     // [stage][which][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+    uint64_t* outer_full = bars;
+    uint64_t* in_full = bars + 1;      // [2]
+    uint64_t* in_empty = bars + 3;     // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* ew_done = bars + 6;
+    uint64_t* acc_full = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int ot = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int E = H * AHD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_in = (S + AT - 1) / AT;
+    const int n_it = MODE == MODE_FWD ? 2 * n_in : n_in;
+    constexpr uint32_t TMEM_COLS = MODE == MODE_FWD ? 256 : 512;
+    constexpr uint32_t C_S = 0, C_DP = 128;
+    constexpr uint32_t C_ACC0 = MODE == MODE_FWD ? 128 : 256;
+    constexpr uint32_t C_ACC1 = 320;
+    const long long bh = static_cast<long long>(b) * H + h;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_qkv);
+        if (MODE != MODE_FWD) tma_prefetch_desc(&map_do);
+        mbar_init(outer_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&in_full[s], MODE == MODE_DKV ? 2 : 1);
+            mbar_init(&in_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(ew_done, 128);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ TMA producer
+        const int cq = h * AHD, ck = E + h * AHD, cv = 2 * E + h * AHD;
+        if (lane == 0) {
+            mbar_expect_tx(outer_full, L::N_OUTER * ATILE);
+            if (MODE == MODE_FWD) {
+                tma_load_3d(s_outer0, &map_qkv, cq, ot * AT, b, outer_full);
+            } else if (MODE == MODE_DQ) {
+                tma_load_3d(s_outer0, &map_qkv, cq, ot * AT, b, outer_full);
+                tma_load_3d(s_outer1, &map_do, h * AHD, ot * AT, b, outer_full);
+            } else {
+                tma_load_3d(s_outer0, &map_qkv, ck, ot * AT, b, outer_full);
+                tma_load_3d(s_outer1, &map_qkv, cv, ot * AT, b, outer_full);
+            }
+        }
+        for (int it = 0; it < n_it; ++it) {
+            const int stage = it & 1, par = (it >> 1) & 1;
+            const int j = MODE == MODE_FWD ? it % n_in : it;
+            uint8_t* t0 = s_inner + stage * 2 * ATILE;
+            uint8_t* t1 = t0 + ATILE;
+            if (lane == 0) {
+                mbar_wait(&in_empty[stage], par ^ 1);
+                if (MODE == MODE_FWD) {
+                    const bool second = it >= n_in;
+                    mbar_expect_tx(&in_full[stage], second ? 2 * ATILE : ATILE);
+                    tma_load_3d(t0, &map_qkv, ck, j * AT, b, &in_full[stage]);
+                    if (second) tma_load_3d(t1, &map_qkv, cv, j * AT, b, &in_full[stage]);
+                } else if (MODE == MODE_DQ) {
+                    mbar_expect_tx(&in_full[stage], 2 * ATILE);
+                    tma_load_3d(t0, &map_qkv, ck, j * AT, b, &in_full[stage]);
+                    tma_load_3d(t1, &map_qkv, cv, j * AT, b, &in_full[stage]);
+                } else {
+                    mbar_expect_tx(&in_full[stage], 2 * ATILE);
+                    tma_load_3d(t0, &map_qkv, cq, j * AT, b, &in_full[stage]);
+                    tma_load_3d(t1, &map_do, h * AHD, j * AT, b, &in_full[stage]);
+                }
+            }
+            if (MODE == MODE_DKV) {
+                __syncwarp();   // lane 0 has seen the stage free
+                float* v_lse = s_vec + stage * 2 * AT;
+                float* v_del = v_lse + AT;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int qi = lane + 32 * k, q = j * AT + qi;
+                    v_lse[qi] = q < S ? lse_in[bh * S + q] * L2E : INFINITY;
+                    v_del[qi] = q < S ? delta_in[bh * S + q] : 0.f;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&in_full[stage]);
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(AT, AT, 0, 0);
+            constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
+            mbar_wait(outer_full, 0);
+            tc_fence_after();
+            const uint64_t a0 = umma_desc_sw128(smem_u32(s_outer0));
+            const uint64_t a1 = umma_desc_sw128(smem_u32(s_outer1));
+            for (int it = 0; it < n_it; ++it) {
+                const int stage = it & 1, par = (it >> 1) & 1;
+                mbar_wait(&in_full[stage], par);
+                tc_fence_after();
+                const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ATILE));
+                const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ATILE + ATILE));
+                const bool last = it == n_it - 1;
+                if (MODE == MODE_FWD) {
+                    if (it > 0 && (it - 1) < n_in) {   // the previous iteration was a max-only pass: S must have been read
+                        mbar_wait(ew_done, (it - 1) & 1);
+                        tc_fence_after();
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss(tb + C_S, a0 + 2 * k, b0 + 2 * k, idesc_s, k > 0);
+                    umma_commit(s_full);
+                    if (it < n_in) {
+                        umma_commit(&in_empty[stage]);
+                    } else {
+                        mbar_wait(ew_done, it & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)   // O += P V : 16 keys per MMA = 8 TMEM columns of P, 2048 bytes of V
+                            umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > n_in || k > 0) ? 1u : 0u);
+                        umma_commit(&in_empty[stage]);
+                        if (last) umma_commit(acc_full);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss(tb + C_S, a0 + 2 * k, b0 + 2 * k, idesc_s, k > 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_ss(tb + C_DP, a1 + 2 * k, b1 + 2 * k, idesc_s, k > 0);
+                    umma_commit(s_full);
+                    mbar_wait(ew_done, it & 1);
+                    tc_fence_after();
+                    if (MODE == MODE_DQ) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)   // dQ += dS K_j
+                            umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)   // dV += P^T dO_i
+                            umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)   // dK += dS^T Q_i
+                            umma_ts(tb + C_ACC1, tb + C_DP + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&in_empty[stage]);
+                    if (last) umma_commit(acc_full);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ element-wise stage (thread = TMEM lane = row)
+        const int tid = threadIdx.x;
+        const uint32_t tl = tb + (static_cast<uint32_t>(warp * 32) << 16);
+        const int row = ot * AT + tid;
+        const bool row_ok = row < S;
+        if (MODE == MODE_FWD) {
+            float m = -INFINITY;
+            for (int it = 0; it < n_in; ++it) {            // pass 1: row maximum
+                mbar_wait(s_full, it & 1);
+                tc_fence_after();
+                const int k0 = it * AT;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(tl + C_S + 32 * c, r);
+                    tmem_ld_wait();
+                    if (k0 + 32 * c + 32 <= S) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (k0 + 32 * c + i < S) m = fmaxf(m, __uint_as_float(r[i]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(ew_done);
+            }
+            const float mL = (m == -INFINITY) ? 0.f : m * L2E;
+            float l = 0.f;
+            for (int it = n_in; it < n_it; ++it) {         // pass 2: P = exp2(S - m), row sum
+                mbar_wait(s_full, it & 1);
+                tc_fence_after();
+                const int k0 = (it - n_in) * AT;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = 2 * half + cc;
+                        uint32_t r[32];
+                        tmem_ld32(tl + C_S + 32 * c, r);
+                        tmem_ld_wait();
+                        const bool full = k0 + 32 * c + 32 <= S;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), L2E, -mL));
+                            float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), L2E, -mL));
+                            if (!full) {
+                                if (k0 + 32 * c + i >= S) p0 = 0.f;
+                                if (k0 + 32 * c + i + 1 >= S) p1 = 0.f;
+                            }
+                            l += p0 + p1;
+                            pk[16 * cc + i / 2] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    tmem_st32(tl + C_S + 32 * half, pk);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(ew_done);
+            }
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld32(tl + C_ACC0, o0);
+            tmem_ld32(tl + C_ACC0 + 32, o1);
+            tmem_ld_wait();
+            if (row_ok) {
+                const float inv = l > 0.f ? 1.0f / l : 0.f;
+                const long long tok = static_cast<long long>(b) * S + row;
+                store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv);
+                if (out32) {
+                    float* f = out32 + tok * E + h * AHD;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int e = 8 * q + i;
+                            w[i] = __float_as_uint(__uint_as_float(e < 32 ? o0[e] : o1[e - 32]) * inv);
+                        }
+                        st_global_256(f + 8 * q, w);
+                    }
+                }
+                lse_out[bh * S + row] = (m == -INFINITY ? 0.f : m) + logf(fmaxf(l, 1e-30f));
+            }
+        } else {
+            // backward: rows are queries (DQ) or keys (DKV)
+            const float my_lse = (MODE == MODE_DQ && row_ok) ? lse_in[bh * S + row] * L2E : INFINITY;
+            const float my_del = (MODE == MODE_DQ && row_ok) ? delta_in[bh * S + row] : 0.f;
+            for (int it = 0; it < n_it; ++it) {
+                mbar_wait(s_full, it & 1);
+                tc_fence_after();
+                const int c0 = it * AT;                      // first inner row (key for DQ, query for DKV)
+                const float* v_lse = s_vec + (it & 1) * 2 * AT;
+                const float* v_del = v_lse + AT;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t pkp[32], pks[32];
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = 2 * half + cc;
+                        uint32_t s[32], dp[32];
+                        tmem_ld32(tl + C_S + 32 * c, s);
+                        tmem_ld32(tl + C_DP + 32 * c, dp);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float p0, p1, d0, d1;
+                            if (MODE == MODE_DQ) {
+                                p0 = (c0 + 32 * c + i < S) ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -my_lse)) : 0.f;
+                                p1 = (c0 + 32 * c + i + 1 < S) ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -my_lse)) : 0.f;
+                                d0 = p0 * (__uint_as_float(dp[i]) - my_del);
+                                d1 = p1 * (__uint_as_float(dp[i + 1]) - my_del);
+                            } else {
+                                const int q = 32 * c + i;      // lse = +inf for queries past the end -> p = 0
+                                p0 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -v_lse[q])) : 0.f;
+                                p1 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -v_lse[q + 1])) : 0.f;
+                                d0 = p0 * (__uint_as_float(dp[i]) - v_del[q]);
+                                d1 = p1 * (__uint_as_float(dp[i + 1]) - v_del[q + 1]);
+                            }
+                            pks[16 * cc + i / 2] = pack_bf16x2(d0, d1);
+                            if (MODE == MODE_DKV) pkp[16 * cc + i / 2] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    if (MODE == MODE_DQ) {
+                        tmem_st32(tl + C_S + 32 * half, pks);     // dS over the consumed half of S
+                    } else {
+                        tmem_st32(tl + C_S + 32 * half, pkp);     // P^T
+                        tmem_st32(tl + C_DP + 32 * half, pks);    // dS^T
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(ew_done);
+            }
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            uint32_t a0[32], a1[32];
+            tmem_ld32(tl + C_ACC0, a0);
+            tmem_ld32(tl + C_ACC0 + 32, a1);
+            tmem_ld_wait();
+            const long long tok = static_cast<long long>(b) * S + row;
+            __nv_bfloat16* drow = dqkv + tok * 3 * E + h * AHD;
+            if (MODE == MODE_DQ) {
+                if (row_ok) store_row_bf16_64(drow, a0, a1, 1.0f);
+            } else {
+                if (row_ok) store_row_bf16_64(drow + 2 * E, a0, a1, 1.0f);     // dV
+                tmem_ld32(tl + C_ACC1, a0);
+                tmem_ld32(tl + C_ACC1 + 32, a1);
+                tmem_ld_wait();
+                if (row_ok) store_row_bf16_64(drow + E, a0, a1, 1.0f);         // dK
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tb, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn3 encode_fn3() {
+    static EncodeTiledFn3 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn3>(p);
+    }
+    return fn;
+}
+
+// bf16 tensor [B][S][cols] -> 3-D map {cols, S, B}, box {64, 128, 1}, 128-byte swizzle; rows >= S read as zeros
+static int make_tmap3(CUtensorMap* map, const void* ptr, int cols, int S, int B) {
+    EncodeTiledFn3 fn = encode_fn3();
+    TVS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(S) * cols * 2};
+    cuuint32_t box[3] = {AHD, AT, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TVS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with %d (cols=%d S=%d B=%d)", (int)r, cols, S, B);
+    return 0;
+}
+
+template <int MODE>
+static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, int B, int S, int H, __nv_bfloat16* out, float* out32, float* lse_out,
+                      const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st) {
+    using L = AtcSmem<MODE>;
+    auto kern = attn_tc_kernel<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    dim3 grid((S + AT - 1) / AT, H, B);
+    kern<<<grid, ATC_THREADS, L::TOTAL, st>>>(mq, md, S, H, out, out32, lse_out, lse_in, delta_in, dqkv);
+    return check_launch(MODE == MODE_FWD ? "attn_tc_kernel<fwd>" : (MODE == MODE_DQ ? "attn_tc_kernel<dq>" : "attn_tc_kernel<dkv>"));
+}
+
+bool attn_tc_enabled() {
+    static const bool off = [] { const char* e = getenv("TVS_ATTN"); return e && e[0] == 'm'; }();   // TVS_ATTN=mma -> legacy kernels
+    return !off;
+}
+
+int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st) {
+    CUtensorMap mq;
+    if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
+    return launch_atc<MODE_FWD>(mq, mq, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st);
+}
+
+// delta must already hold rowsum(dO o O)
+int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st) {
+    CUtensorMap mq, md;
+    if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
+    if (int rc = make_tmap3(&md, dout, H * AHD, S, B)) return rc;
+    if (int rc = launch_atc<MODE_DKV>(mq, md, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st)) return rc;
+    return launch_atc<MODE_DQ>(mq, md, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st);
+}
+
+}  // namespace tvs
