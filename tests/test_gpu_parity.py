@@ -16,7 +16,8 @@ from tests.helpers import FULL, LEARNER_CASES, SMALL, build_net, make_batch, ora
 pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 2e-2        # max-abs, stated by north_star
-GRAD_TOL = 6e-2         # max-abs error relative to the largest reference gradient entry (bf16 operands)
+GRAD_TOL = 8e-2         # max-abs error relative to the largest reference gradient entry (bf16 operands, 10-12 layers)
+GRAD_L2_TOL = 4e-2      # ||g - g_ref||_2 / ||g_ref||_2
 
 
 def _run_case(case, spec, B, L, seed, weights=None, logit_tol=LOGIT_TOL):
@@ -69,6 +70,8 @@ def _run_case(case, spec, B, L, seed, weights=None, logit_tol=LOGIT_TOL):
         scale = g_ref.abs().max().item()
         gerr = (g.detach().cpu() - g_ref).abs().max().item() / scale
         assert gerr <= GRAD_TOL, f"{case}: grad {pk} rel err {gerr:.4f}"
+        l2 = ((g.detach().cpu() - g_ref).norm() / g_ref.norm()).item()
+        assert l2 <= GRAD_L2_TOL, f"{case}: grad {pk} L2 rel err {l2:.4f}"
         checked += 1
     assert checked > 0
     return err

@@ -74,6 +74,8 @@ class PackedLayer:
         if tf32:
             self.wqkv32, self.wo32 = _f(wqkv), _f(sa.out_proj.weight)
             self.w1_32, self.w2_32 = _f(mlp.fc1.weight), _f(mlp.fc2.weight)
+            self.wo_t32 = _f(sa.out_proj.weight.t())
+            self.w1_t32, self.w2_t32 = _f(mlp.fc1.weight.t()), _f(mlp.fc2.weight.t())
 
 
 class PackedClipSeg:
@@ -110,7 +112,7 @@ class PackedClipSeg:
         self.t_layers = [PackedLayer(l, self.t_heads, tf32=True) for l in tm.encoder.layers]
         self.fin_g, self.fin_b = _f(tm.final_layer_norm.weight), _f(tm.final_layer_norm.bias)
         self.w_tproj = _f(model.clip.text_projection.weight)                         # [proj, Dt] f32 (tf32 MMA)
-        self.w_tproj_t = _bf(model.clip.text_projection.weight.t())
+        self.w_tproj_t = _f(model.clip.text_projection.weight.t())
         # decoder
         self.d_layers = [PackedLayer(l, self.d_heads, tf32=True) for l in dec.layers]
         self.w_red = [_f(r.weight) for r in dec.reduces]                             # [Dr, Dv] f32 (tf32 MMA)
@@ -189,22 +191,40 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
 
 
 def encoder_layer_bwd(pk: PackedLayer, sv: Saved, g, g16, B, S, causal, key_mask):
-    """dgrad of the pre-LN block.  g / g16: f32 and bf16 copies of d(out) [B*S, D] -> (dx f32, dx bf16)."""
+    """dgrad of the pre-LN block.  g / g16: f32 and bf16 copies of d(out) [B*S, D] -> (dx f32, dx bf16).
+    tf32 layers (text tower) keep the gradient stream in fp32 and ignore / do not produce the bf16 copy."""
     M, D, F = B * S, pk.D, pk.F
-    du = _e((M, F), BF16, g)
-    abi.gemm(g16, pk.w2_t, aux_bf16=sv.u, out_bf16=du, act=abi.ACT_DQGELU)
-    dln = _e((M, D), BF16, g)
-    abi.gemm(du, pk.w1_t, out_bf16=dln)
-    g1, g1_16 = _e((M, D), F32, g), _e((M, D), BF16, g)
-    abi.layernorm_bwd(dln, sv.x1, pk.g2, sv.mean2, sv.rstd2, dx_add=g, dx_f32=g1, dx_bf16=g1_16)
-    datt = dln
-    abi.gemm(g1_16, pk.wo_t, out_bf16=datt)
+    hi = pk.tf32
+    if hi:
+        du = _e((M, F), F32, g)
+        abi.gemm(g, pk.w2_t32, aux_bf16=sv.u, out_f32=du, act=abi.ACT_DQGELU)
+        dln = _e((M, D), F32, g)
+        abi.gemm(du, pk.w1_t32, out_f32=dln)
+        g1 = _e((M, D), F32, g)
+        abi.layernorm_bwd(dln, sv.x1, pk.g2, sv.mean2, sv.rstd2, dx_add=g, dx_f32=g1)
+        datt = _e((M, D), BF16, g)
+        abi.gemm(g1, pk.wo_t32, out_bf16=datt)
+    else:
+        du = _e((M, F), BF16, g)
+        abi.gemm(g16, pk.w2_t, aux_bf16=sv.u, out_bf16=du, act=abi.ACT_DQGELU)
+        dln = _e((M, D), BF16, g)
+        abi.gemm(du, pk.w1_t, out_bf16=dln)
+        g1, g1_16 = _e((M, D), F32, g), _e((M, D), BF16, g)
+        abi.layernorm_bwd(dln, sv.x1, pk.g2, sv.mean2, sv.rstd2, dx_add=g, dx_f32=g1, dx_bf16=g1_16)
+        datt = dln
+        abi.gemm(g1_16, pk.wo_t, out_bf16=datt)
     dqkv = _e((M, 3 * D), BF16, g)
     delta = _e((B, pk.heads, S), F32, g)
     abi.attn_bwd(sv.qkv, sv.att, datt, sv.lse, B, S, pk.heads, pk.hd, causal, key_mask, delta, dqkv)
+    g0 = _e((M, D), F32, g)
+    if hi:
+        dln1 = _e((M, D), F32, g)
+        abi.gemm(dqkv, pk.wqkv_t, out_f32=dln1)
+        abi.layernorm_bwd(dln1, sv.x, pk.g1, sv.mean1, sv.rstd1, dx_add=g1, dx_f32=g0)
+        return g0, None
     dln1 = _e((M, D), BF16, g)
     abi.gemm(dqkv, pk.wqkv_t, out_bf16=dln1)
-    g0, g0_16 = _e((M, D), F32, g), g1_16
+    g0_16 = g1_16
     abi.layernorm_bwd(dln1, sv.x, pk.g1, sv.mean1, sv.rstd1, dx_add=g1, dx_f32=g0, dx_bf16=g0_16)
     return g0, g0_16
 
@@ -248,18 +268,18 @@ def decoder_layer_fwd(pk: PackedLayer, x, B, S, eps):
 
 
 def decoder_layer_bwd(pk: PackedLayer, sv: SavedDec, g, B, S):
-    """dgrad of the post-LN block.  g: f32 d(out) -> f32 d(in)."""
+    """dgrad of the post-LN block (fp32 gradient stream, kind::tf32 GEMMs).  g: f32 d(out) -> f32 d(in)."""
     M, D, F = B * S, pk.D, pk.F
-    ds2, ds2_16 = _e((M, D), F32, g), _e((M, D), BF16, g)
-    abi.layernorm_bwd(g, sv.s2, pk.g2, sv.mean2, sv.rstd2, dx_f32=ds2, dx_bf16=ds2_16)
-    da = _e((M, F), BF16, g)
-    abi.gemm(ds2_16, pk.w2_t, aux_bf16=sv.a, out_bf16=da, act=abi.ACT_DRELU)
+    ds2 = _e((M, D), F32, g)
+    abi.layernorm_bwd(g, sv.s2, pk.g2, sv.mean2, sv.rstd2, dx_f32=ds2)
+    da = _e((M, F), F32, g)
+    abi.gemm(ds2, pk.w2_t32, aux_bf16=sv.a, out_f32=da, act=abi.ACT_DRELU)
     dy1 = _e((M, D), F32, g)
-    abi.gemm(da, pk.w1_t, residual=ds2, out_f32=dy1)
-    ds1, ds1_16 = ds2, ds2_16
-    abi.layernorm_bwd(dy1, sv.s1, pk.g1, sv.mean1, sv.rstd1, dx_f32=ds1, dx_bf16=ds1_16)
+    abi.gemm(da, pk.w1_t32, residual=ds2, out_f32=dy1)
+    ds1 = ds2
+    abi.layernorm_bwd(dy1, sv.s1, pk.g1, sv.mean1, sv.rstd1, dx_f32=ds1)
     datt = _e((M, D), BF16, g)
-    abi.gemm(ds1_16, pk.wo_t, out_bf16=datt)
+    abi.gemm(ds1, pk.wo_t32, out_bf16=datt)
     dqkv = _e((M, 3 * D), BF16, g)
     delta = _e((B, pk.heads, S), F32, g)
     abi.attn_bwd(sv.qkv, sv.att, datt, sv.lse, B, S, pk.heads, pk.hd, False, None, delta, dqkv)
@@ -420,16 +440,16 @@ class TextTowerFn(torch.autograd.Function):
         B, S, D, depth, n, cd_shape = ctx.dims
         x_last, mean_f, rstd_f, rows = ctx.fin
         dpooled = _e((B, D), F32, dcond)
-        abi.gemm(dcond.contiguous().to(BF16), pk.w_tproj_t, out_f32=dpooled)
+        abi.gemm(dcond.contiguous().to(F32), pk.w_tproj_t, out_f32=dpooled)
         dxf = torch.zeros((B * S, D), dtype=F32, device=dcond.device)
         dxf.index_copy_(0, rows, dpooled)
-        g, g16 = _e((B * S, D), F32, dxf), _e((B * S, D), BF16, dxf)
-        abi.layernorm_bwd(dxf, x_last, pk.fin_g, mean_f, rstd_f, dx_f32=g, dx_bf16=g16)
+        g = _e((B * S, D), F32, dxf)
+        abi.layernorm_bwd(dxf, x_last, pk.fin_g, mean_f, rstd_f, dx_f32=g)
         dctx = None if cd_shape is None else torch.zeros(cd_shape, dtype=F32, device=dcond.device)
         for idx in range(len(pk.t_layers), 0, -1):
             if idx < depth:
-                abi.prompt_grad(g.view(B, S, D), 1, n, dctx[idx - 1], zero_rows=True, dx_bf16=g16.view(B, S, D))
-            g, g16 = encoder_layer_bwd(pk.t_layers[idx - 1], ctx.saved[idx - 1], g, g16, B, S, True, ctx.km)
+                abi.prompt_grad(g.view(B, S, D), 1, n, dctx[idx - 1], zero_rows=True)
+            g, _ = encoder_layer_bwd(pk.t_layers[idx - 1], ctx.saved[idx - 1], g, None, B, S, True, ctx.km)
         ctx.saved = None
         return g.view(B, S, D), dctx, None, None, None, None
 
