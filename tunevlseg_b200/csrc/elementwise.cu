@@ -75,33 +75,49 @@ __global__ void prompt_overwrite_kernel(float* __restrict__ x, __nv_bfloat16* __
     }
 }
 
-// dctx[(b), j, d] (+)= sum_b dx[b, row0+j, d]; optionally zero those rows of dx.  One thread per (j, d) [per b].
+// dctx[(b), j, d] (+)= sum_b dx[b, row0+j, d]; optionally zero those rows of dx (and of its bf16 mirror).
+// Batch-reduced form: grid (n, ceil(D/128)), block (128 channels, 8 batch groups); the batch loop is split over
+// threadIdx.y and finished through shared memory, so no thread walks the whole batch serially.
+__global__ void __launch_bounds__(1024)
+prompt_grad_reduce_kernel(float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int B, int S, int D, int row0, float* __restrict__ dctx,
+                          int zero_rows) {
+    __shared__ float part[8][128];
+    const int j = blockIdx.x, d = blockIdx.y * 128 + threadIdx.x, g = threadIdx.y;
+    float acc = 0.f;
+    if (d < D) {
+        for (int b = g; b < B; b += 8) {
+            const long long off = (static_cast<long long>(b) * S + row0 + j) * D + d;
+            acc += dx[off];
+            if (zero_rows) {
+                dx[off] = 0.f;
+                if (dx16) dx16[off] = __float2bfloat16(0.f);
+            }
+        }
+    }
+    part[g][threadIdx.x] = acc;
+    __syncthreads();
+    if (g == 0 && d < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+        dctx[static_cast<long long>(j) * D + d] += t;
+    }
+}
+
+// per-sample form (CoCoOp): dctx[b, j, d] += dx[b, row0+j, d]
 __global__ void prompt_grad_kernel(float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int B, int S, int D, int row0, int n,
                                    float* __restrict__ dctx, long long ctx_bs, int zero_rows) {
     const long long per = static_cast<long long>(n) * D;
-    const long long total = ctx_bs ? per * B : per;
+    const long long total = per * B;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int d = static_cast<int>(i % D);
         const int j = static_cast<int>((i / D) % n);
-        if (ctx_bs) {
-            const int b = static_cast<int>(i / per);
-            float* p = dx + (static_cast<long long>(b) * S + row0 + j) * D + d;
-            dctx[b * ctx_bs + static_cast<long long>(j) * D + d] += *p;
-            if (zero_rows) {
-                *p = 0.f;
-                if (dx16) dx16[(static_cast<long long>(b) * S + row0 + j) * D + d] = __float2bfloat16(0.f);
-            }
-        } else {
-            float acc = 0.f;
-            for (int b = 0; b < B; ++b) {
-                float* p = dx + (static_cast<long long>(b) * S + row0 + j) * D + d;
-                acc += *p;
-                if (zero_rows) {
-                    *p = 0.f;
-                    if (dx16) dx16[(static_cast<long long>(b) * S + row0 + j) * D + d] = __float2bfloat16(0.f);
-                }
-            }
-            dctx[static_cast<long long>(j) * D + d] += acc;
+        const int b = static_cast<int>(i / per);
+        const long long off = (static_cast<long long>(b) * S + row0 + j) * D + d;
+        dctx[b * ctx_bs + static_cast<long long>(j) * D + d] += dx[off];
+        if (zero_rows) {
+            dx[off] = 0.f;
+            if (dx16) dx16[off] = __float2bfloat16(0.f);
         }
     }
 }
@@ -468,7 +484,12 @@ extern "C" __attribute__((visibility("default"))) int tvs_prompt_grad(float* dx,
                                int64_t ctx_batch_stride, int32_t zero_rows, void* stream) {
     TVS_REQUIRE(dx && dctx, "tvs_prompt_grad: null pointer");
     TVS_REQUIRE(row0 >= 0 && n > 0 && row0 + n <= S, "tvs_prompt_grad: bad rows");
-    const long long total = static_cast<long long>(n) * D * (ctx_batch_stride ? B : 1);
+    if (ctx_batch_stride == 0) {
+        prompt_grad_reduce_kernel<<<dim3(n, (D + 127) / 128), dim3(128, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+            dx, static_cast<__nv_bfloat16*>(dx_bf16), B, S, D, row0, dctx, zero_rows);
+        return check_launch("prompt_grad_reduce_kernel");
+    }
+    const long long total = static_cast<long long>(n) * D * B;
     prompt_grad_kernel<<<blocks_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(dx, static_cast<__nv_bfloat16*>(dx_bf16), B, S, D, row0, n, dctx,
                                                                                             ctx_batch_stride, zero_rows);
     return check_launch("prompt_grad_kernel");

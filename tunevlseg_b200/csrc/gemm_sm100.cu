@@ -83,6 +83,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// same tile delivered to the same shared-memory offset of every CTA in `mask`; each destination's mbarrier (same offset) gets the bytes
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -126,6 +142,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -313,7 +335,12 @@ struct GemmSmem {
     static constexpr int TOTAL = EPI_OFFSET + 4 * EPI_WARP_FLOATS * 4 + 1024;     // + alignment slack
 };
 
-template <int BN, int STAGES, bool TF32>
+// CL = 2: the kernel runs as 2-CTA clusters.  The pair works on two vertically adjacent 128-row tiles of the SAME
+// weight column block; each CTA fetches half of the W tile and TMA-multicasts it into both CTAs' shared memory, which
+// cuts the L2 -> SM operand traffic of a 128x256 tile from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2-bound).
+// A stage may only be refilled once BOTH CTAs' MMAs have consumed it (the peer writes into it): empty barriers count 2
+// and every MMA commit is multicast to both CTAs.
+template <int BN, int STAGES, bool TF32, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
                          int N, int K, GemmEpilogue ep) {
@@ -332,7 +359,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int lane = threadIdx.x & 31;
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
+    const uint32_t cta_rank = CL == 2 ? cluster_ctarank() : 0;
+    const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;   // cluster id / number of clusters
+    const int num_tiles = ((num_m + CL - 1) / CL) * num_n;                 // tiles of CL stacked 128-row blocks
     constexpr int BK = TF32 ? BK_BYTES / 4 : BK_BYTES / 2;   // elements of K per k-block
     const int num_kb = (K + BK - 1) / BK;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two >= 32 for BN in {64,128,256}
@@ -343,7 +372,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
@@ -357,20 +386,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast to them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / num_n, n_blk = tile % num_n;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     tma_load_2d(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, &full_bar[stage]);
-                    tma_load_2d(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN, &full_bar[stage]);
+                    if (CL == 2)   // tmap_w has a (BN/2)-row box here
+                        tma_load_2d_mc(smem_b + stage * L::B_BYTES + cta_rank * (L::B_BYTES / 2), &tmap_w, kb * BK,
+                                       n_blk * BN + cta_rank * (BN / 2), &full_bar[stage], 0x3);
+                    else
+                        tma_load_2d(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN, &full_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -379,7 +413,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(BM, BN, TF32 ? 2u : 1u);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -394,7 +428,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         if (TF32) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (CL == 2) umma_commit_mc(&empty_bar[stage], 0x3);
+                    else umma_commit(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -405,8 +440,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp >= 4) {
         const int ew = warp - 4;  // TMEM lane quarter this warp may touch = warp % 4
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const long long row0 = static_cast<long long>(m_blk) * BM + ew * 32;
@@ -433,7 +468,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CL == 2) cluster_sync_all();   // do not exit while the peer can still signal this CTA's barriers
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -475,29 +511,59 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
     return 0;
 }
 
-template <int BN, int STAGES, bool TF32>
-static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
+template <int BN, int STAGES, bool TF32, int CL>
+static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES>;
     CUtensorMap ta, tw;
     if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.lda, BM, TF32)) return rc;
-    if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN, TF32)) return rc;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, TF32>;
+    if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN / CL, TF32)) return rc;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, TF32, CL>;
     static bool attr_set = false;
     if (!attr_set) {
         TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tw, a.M, a.N, a.K, ep);
+    const int tiles = (((a.M + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
+    const int max_clusters = sm_count() / CL;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    if (CL == 1) {
+        kern<<<clusters, GEMM_THREADS, L::TOTAL, stream>>>(ta, tw, a.M, a.N, a.K, ep);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clusters * CL);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = L::TOTAL;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TVS_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, a.M, a.N, a.K, ep));
+    }
     return check_launch("gemm_bf16_tcgen05_kernel");
+}
+
+// clusters (W-tile multicast) pay off when the GEMM fills the machine; tiny problems keep independent CTAs
+template <int BN, int STAGES, bool TF32>
+static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
+    static const int mode = [] { const char* e = getenv("TVS_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();   // -1 auto, 1 off, 2 on
+    const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+    const bool use2 = BN >= 128 && (mode == 2 || (mode == -1 && tiles >= 2LL * sm_count()));
+    if (use2) return launch_gemm_cl<BN, STAGES, TF32, 2>(a, ep, stream);
+    return launch_gemm_cl<BN, STAGES, TF32, 1>(a, ep, stream);
 }
 
 static int pick_tile_n(int M, int N) {
     if (N <= 64) return 64;
-    if (N <= 128) return 128;
     const int sms = sm_count();
     const int num_m = (M + BM - 1) / BM;
+    // small problems (text tower, B*S ~ 400 rows): the serial K loop of one CTA is the critical path, so prefer the
+    // narrowest tile - twice the CTAs and half the MMA time per k-block
+    if (static_cast<long long>(num_m) * ((N + 127) / 128) < sms) return 64;
+    if (N <= 128) return 128;
     auto eff = [&](int bn) {
         long long tiles = static_cast<long long>(num_m) * ((N + bn - 1) / bn);
         long long waves = (tiles + sms - 1) / sms;
