@@ -300,14 +300,15 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
-    # per-kernel shares + roofline of the dominant kernel (one profiled step, CUDA events on the launching stream)
+    # per-kernel shares + roofline of the dominant kernel: one profiled step with CUDA events on the launching stream.
+    # EVERY rank runs the step (it contains the gradient all-reduce); only rank 0 records and reports.
     roof = None
+    recs = [] if rank == 0 else None
+    abi.set_profiler(recs)
+    step_eager()
+    torch.cuda.synchronize()
+    abi.set_profiler(None)
     if rank == 0:
-        recs = []
-        abi.set_profiler(recs)
-        step_eager()
-        torch.cuda.synchronize()
-        abi.set_profiler(None)
         agg = {}
         for name, key, a, b, fl in recs:
             k = f"{name}:{key}" if key else name
@@ -353,6 +354,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out))
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -325,26 +325,72 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 struct GemmSmem {
     static constexpr int A_BYTES = BM * BK_BYTES;
-    static constexpr int B_BYTES = BN * BK_BYTES;
+    static constexpr int B_BYTES = (BN / CL) * BK_BYTES;        // cta_group::2: each CTA of the pair holds half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int EPI_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;     // 16-byte aligned
     static constexpr int TOTAL = EPI_OFFSET + 4 * EPI_WARP_FLOATS * 4 + 1024;     // + alignment slack
 };
 
-// CL = 2: the kernel runs as 2-CTA clusters.  The pair works on two vertically adjacent 128-row tiles of the SAME
-// weight column block; each CTA fetches half of the W tile and TMA-multicasts it into both CTAs' shared memory, which
-// cuts the L2 -> SM operand traffic of a 128x256 tile from 48 KB to 32 KB per k-block (the 1-CTA kernel is L2-bound).
-// A stage may only be refilled once BOTH CTAs' MMAs have consumed it (the peer writes into it): empty barriers count 2
-// and every MMA commit is multicast to both CTAs.
+// CL = 2: the kernel runs as CTA PAIRS (cta_group::2).  The pair computes a 256 x BN tile: each CTA loads its own 128
+// rows of A and HALF of the W tile, the leader CTA issues one tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs'
+// shared memory, and each CTA's TMEM receives its own 128 x BN accumulator.  An SM can take in roughly 64-70 B/clk from
+// L2 (measured: the 1-CTA 128x256 tile needs 96 B/clk at full MMA rate and saturates at ~70 % tensor utilisation;
+// multicasting W between two independent CTAs did not help because every SM still RECEIVES the whole tile); the pair
+// needs 64 B/clk per SM and also halves the shared-memory operand reads per SM.
+//   full[s]     lives in the leader: its own arrive.expect_tx(2 x stage bytes) + the peer's remote arrive; both CTAs' TMA
+//               loads (cta_group::2) complete_tx on it
+//   empty[s], tmem_full[a]  local to each CTA, signalled by the leader's multicast tcgen05.commit
+//   tmem_empty[a]  lives in the leader, 4 epilogue warps x 2 CTAs arrive on it
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {   // arrives on this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+
 template <int BN, int STAGES, bool TF32, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
                          int N, int K, GemmEpilogue ep) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, CL>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
@@ -371,19 +417,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_w);
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CL);
+            mbar_init(&full_bar[s], CL);
+            mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4);
-        mbar_init(&tmem_empty[1], 4);
+        mbar_init(&tmem_empty[0], 4 * CL);
+        mbar_init(&tmem_empty[1], 4 * CL);
         fence_barrier_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CL == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (CL == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast to them
@@ -398,20 +448,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, &full_bar[stage]);
-                    if (CL == 2)   // tmap_w has a (BN/2)-row box here
-                        tma_load_2d_mc(smem_b + stage * L::B_BYTES + cta_rank * (L::B_BYTES / 2), &tmap_w, kb * BK,
-                                       n_blk * BN + cta_rank * (BN / 2), &full_bar[stage], 0x3);
-                    else
+                    if (CL == 2) {
+                        const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                        else mbar_arrive_cluster(leader_full);
+                        tma_load_2d_cg2(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, leader_full);
+                        tma_load_2d_cg2(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN + cta_rank * (BN / 2), leader_full);   // (BN/2)-row box
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        tma_load_2d(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, &full_bar[stage]);
                         tma_load_2d(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN, &full_bar[stage]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(BM, BN, TF32 ? 2u : 1u);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc(BM * CL, BN, TF32 ? 2u : 1u);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -425,12 +479,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                     for (int k = 0; k < MMAS_PER_KB; ++k) {
                         // advance 32 bytes (16 bf16 / 8 tf32) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                        if (TF32) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        if (CL == 2) {
+                            if (TF32) umma_tf32_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                            else umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                        } else {
+                            if (TF32) umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                        }
                     }
-                    if (CL == 2) umma_commit_mc(&empty_bar[stage], 0x3);
-                    else umma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (CL == 2) {
+                        umma_commit_cg2(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 acc ^= 1;
@@ -461,7 +525,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CL == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -472,7 +539,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (CL == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -513,7 +581,7 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
 
 template <int BN, int STAGES, bool TF32, int CL>
 static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, CL>;
     CUtensorMap ta, tw;
     if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.lda, BM, TF32)) return rc;
     if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN / CL, TF32)) return rc;
@@ -546,13 +614,14 @@ static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaSt
     return check_launch("gemm_bf16_tcgen05_kernel");
 }
 
-// clusters (W-tile multicast) pay off when the GEMM fills the machine; tiny problems keep independent CTAs
+// CTA pairs pay off when the GEMM fills the machine; tiny problems keep independent CTAs
 template <int BN, int STAGES, bool TF32>
 static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
     static const int mode = [] { const char* e = getenv("TVS_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();   // -1 auto, 1 off, 2 on
     const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+    constexpr int STAGES2 = BN == 256 ? 6 : 8;     // 32 KB / 24 KB per stage per CTA in pair mode
     const bool use2 = BN >= 128 && (mode == 2 || (mode == -1 && tiles >= 2LL * sm_count()));
-    if (use2) return launch_gemm_cl<BN, STAGES, TF32, 2>(a, ep, stream);
+    if (use2) return launch_gemm_cl<(BN >= 128 ? BN : 128), STAGES2, TF32, 2>(a, ep, stream);
     return launch_gemm_cl<BN, STAGES, TF32, 1>(a, ep, stream);
 }
 
