@@ -91,6 +91,21 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
+// One elected lane of a CONVERGED warp.  The producer / MMA warps keep all 32 lanes in the loop and predicate only the
+// issuing instructions: the loop state then stays warp-uniform (uniform registers feed UTMALDG / UTCHMMA directly);
+// running the loop in a single divergent lane costs an R2UR round trip per operand and made the MMA issue loop, not
+// the tensor pipe, the bottleneck (~70 % utilisation).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -444,13 +459,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             uint32_t stage = 0, phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (CL == 2) {
+                    if (!elect_one()) {
+                    } else if (CL == 2) {
                         const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
                         else mbar_arrive_cluster(leader_full);
@@ -461,12 +477,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         tma_load_2d(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, &full_bar[stage]);
                         tma_load_2d(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN, &full_bar[stage]);
                     }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc(BM * CL, BN, TF32 ? 2u : 1u);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -478,6 +495,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * L::A_BYTES));
                     const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * L::B_BYTES));
+                    if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < MMAS_PER_KB; ++k) {
                         // advance 32 bytes (16 bf16 / 8 tf32) along K inside the 128-byte swizzle row: +2 in 16-byte units
@@ -497,6 +515,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         umma_commit(&empty_bar[stage]);
                         if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 acc ^= 1;
