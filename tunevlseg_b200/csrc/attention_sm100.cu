@@ -121,7 +121,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     if (warp == 4) {
         // ------------------------------------------------------------------ TMA producer
         const int cq = h * AHD, ck = E + h * AHD, cv = 2 * E + h * AHD;
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(outer_full, L::N_OUTER * ATILE);
             if (MODE == MODE_FWD) {
                 tma_load_3d(s_outer0, &map_qkv, cq, ot * AT, b, outer_full);
@@ -138,8 +138,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             const int j = MODE == MODE_FWD ? it % n_in : it;
             uint8_t* t0 = s_inner + stage * 2 * ATILE;
             uint8_t* t1 = t0 + ATILE;
-            if (lane == 0) {
-                mbar_wait(&in_empty[stage], par ^ 1);
+            mbar_wait(&in_empty[stage], par ^ 1);       // whole warp, converged: uniform loop state
+            if (elect_one()) {
                 if (MODE == MODE_FWD) {
                     const bool second = it >= n_in;
                     mbar_expect_tx(&in_full[stage], second ? 2 * ATILE : ATILE);
@@ -156,7 +156,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 }
             }
             if (MODE == MODE_DKV) {
-                __syncwarp();   // lane 0 has seen the stage free
+                __syncwarp();
                 float* v_lse = s_vec + stage * 2 * AT;
                 float* v_del = v_lse + AT;
 #pragma unroll
@@ -166,12 +166,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                     v_del[qi] = q < S ? delta_in[bh * S + q] : 0.f;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&in_full[stage]);
+                if (elect_one()) mbar_arrive(&in_full[stage]);
             }
+            __syncwarp();
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc_s = umma_idesc_bf16(AT, AT, 0, 0);
             constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
             mbar_wait(outer_full, 0);
@@ -190,42 +191,53 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                         mbar_wait(ew_done, (it - 1) & 1);
                         tc_fence_after();
                     }
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ss(tb + C_S, a0 + 2 * k, b0 + 2 * k, idesc_s, k > 0);
-                    umma_commit(s_full);
-                    if (it < n_in) {
-                        umma_commit(&in_empty[stage]);
-                    } else {
+                        for (int k = 0; k < 4; ++k) umma_ss(tb + C_S, a0 + 2 * k, b0 + 2 * k, idesc_s, k > 0);
+                        umma_commit(s_full);
+                        if (it < n_in) umma_commit(&in_empty[stage]);
+                    }
+                    __syncwarp();
+                    if (it >= n_in) {
                         mbar_wait(ew_done, it & 1);
                         tc_fence_after();
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)   // O += P V : 16 keys per MMA = 8 TMEM columns of P, 2048 bytes of V
-                            umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > n_in || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < 8; ++k)   // O += P V : 16 keys per MMA = 8 TMEM columns of P, 2048 bytes of V
+                                umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > n_in || k > 0) ? 1u : 0u);
+                            umma_commit(&in_empty[stage]);
+                            if (last) umma_commit(acc_full);
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_ss(tb + C_S, a0 + 2 * k, b0 + 2 * k, idesc_s, k > 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_ss(tb + C_DP, a1 + 2 * k, b1 + 2 * k, idesc_s, k > 0);
+                        umma_commit(s_full);
+                    }
+                    __syncwarp();
+                    mbar_wait(ew_done, it & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (MODE == MODE_DQ) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)   // dQ += dS K_j
+                                umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)   // dV += P^T dO_i
+                                umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)   // dK += dS^T Q_i
+                                umma_ts(tb + C_ACC1, tb + C_DP + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                        }
                         umma_commit(&in_empty[stage]);
                         if (last) umma_commit(acc_full);
                     }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ss(tb + C_S, a0 + 2 * k, b0 + 2 * k, idesc_s, k > 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_ss(tb + C_DP, a1 + 2 * k, b1 + 2 * k, idesc_s, k > 0);
-                    umma_commit(s_full);
-                    mbar_wait(ew_done, it & 1);
-                    tc_fence_after();
-                    if (MODE == MODE_DQ) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)   // dQ += dS K_j
-                            umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)   // dV += P^T dO_i
-                            umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)   // dK += dS^T Q_i
-                            umma_ts(tb + C_ACC1, tb + C_DP + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&in_empty[stage]);
-                    if (last) umma_commit(acc_full);
+                    __syncwarp();
                 }
             }
         }

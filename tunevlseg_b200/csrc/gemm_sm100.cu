@@ -642,7 +642,9 @@ static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStrea
     static const int mode = [] { const char* e = getenv("TVS_GEMM_CLUSTER"); return e ? atoi(e) : -1; }();   // -1 auto, 1 off, 2 on
     const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
     constexpr int STAGES2 = BN == 256 ? 6 : 8;     // 32 KB / 24 KB per stage per CTA in pair mode
-    const bool use2 = BN >= 128 && (mode == 2 || (mode == -1 && tiles >= 2LL * sm_count()));
+    // pairs win on the compute-heavy shapes; the memory-bound N = K = 768 residual GEMM is slightly better with single CTAs
+    const bool heavy = static_cast<long long>(a.N) * a.K >= 768LL * 1024;
+    const bool use2 = BN >= 128 && (mode == 2 || (mode == -1 && tiles >= 2LL * sm_count() && heavy));
     if (use2) return launch_gemm_cl<(BN >= 128 ? BN : 128), STAGES2, TF32, 2>(a, ep, stream);
     return launch_gemm_cl<BN, STAGES, TF32, 1>(a, ep, stream);
 }
@@ -661,7 +663,7 @@ static int pick_tile_n(int M, int N) {
         double wave_eff = static_cast<double>(tiles) / static_cast<double>(waves * sms);
         double pad_eff = static_cast<double>(N) / static_cast<double>(((N + bn - 1) / bn) * bn);
         // 128x128 tiles read 128 B/clk of smem per MMA (the limit); 128x256 needs 96 B/clk
-        return wave_eff * pad_eff * (bn == 256 ? 1.0 : 0.92);
+        return wave_eff * pad_eff * (bn == 256 ? 1.0 : 0.97);
     };
     return eff(256) >= eff(128) ? 256 : 128;
 }
