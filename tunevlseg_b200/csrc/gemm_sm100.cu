@@ -251,8 +251,35 @@ __device__ __forceinline__ void st_bf16_row32(__nv_bfloat16* p, const float (&v)
     }
 }
 
+// The global operands a chunk's epilogue needs (saved pre-activation, residual).  They are fetched ONE CHUNK AHEAD so
+// that their ~1 us latency overlaps the previous chunk's math and stores instead of stalling every chunk.
+struct EpiExtras {
+    uint32_t aux[16];
+    uint32_t res[32];
+};
+__device__ __forceinline__ void load_extras(const GemmEpilogue& ep, long long row, int col0, EpiExtras& e) {
+    if (ep.act >= TVS_ACT_DQGELU) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t a[8];
+            ld256(ep.aux_bf16 + row * ep.ldaux + col0 + 16 * h, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e.aux[8 * h + i] = a[i];
+        }
+    }
+    if (ep.residual) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r[8];
+            ld256(ep.residual + row * ep.ldr + col0 + 8 * q, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e.res[8 * q + i] = r[i];
+        }
+    }
+}
+
 // one row (this thread's TMEM lane), 32 consecutive columns starting at col0; requires ep.vec256_ok and col0 + 32 <= N
-__device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0) {
+__device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0, const EpiExtras& ex) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
@@ -274,25 +301,15 @@ __device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const ui
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
     } else if (ep.act >= TVS_ACT_DQGELU) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t a[8];
-            ld256(ep.aux_bf16 + row * ep.ldaux + col0 + 16 * h, a);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float2 u = unpack_bf16x2(a[i]);
-                v[16 * h + 2 * i] = epi_act(ep, v[16 * h + 2 * i], u.x);
-                v[16 * h + 2 * i + 1] = epi_act(ep, v[16 * h + 2 * i + 1], u.y);
-            }
+        for (int i = 0; i < 16; ++i) {
+            const float2 u = unpack_bf16x2(ex.aux[i]);
+            v[2 * i] = epi_act(ep, v[2 * i], u.x);
+            v[2 * i + 1] = epi_act(ep, v[2 * i + 1], u.y);
         }
     }
     if (ep.residual) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t r[8];
-            ld256(ep.residual + row * ep.ldr + col0 + 8 * q, r);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * q + i] += __uint_as_float(r[i]);
-        }
+        for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(ex.res[i]);
     }
     if (ep.out_f32) {
 #pragma unroll
@@ -533,16 +550,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const long long row0 = static_cast<long long>(m_blk) * BM + ew * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
             float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + ew * EPI_WARP_FLOATS;
+            const bool direct = ep.vec256_ok && !ep.staged;
+            const bool row_ok = row0 + lane < M;
+            const bool extras = direct && row_ok && (ep.residual != nullptr || ep.act >= TVS_ACT_DQGELU);
+            EpiExtras ex0, ex1;
+            if (extras && n_blk * BN + 32 <= N) load_extras(ep, row0 + lane, n_blk * BN, ex0);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n_blk * BN + c * 32;
-                if (row0 >= M || col0 >= N) break;      // warp-uniform: nothing of this chunk is inside the matrix
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c * 32, r);
-                if (ep.vec256_ok && !ep.staged && col0 + 32 <= N) {
-                    if (row0 + lane < M) epilogue_direct(ep, r, row0 + lane, col0);
-                } else {
-                    epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
+            for (int c = 0; c < BN / 32; c += 2) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int col0 = n_blk * BN + (c + u) * 32;
+                    if (row0 >= M || col0 >= N) break;      // warp-uniform: nothing of this chunk is inside the matrix
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + (c + u) * 32, r);
+                    if (direct && col0 + 32 <= N) {
+                        // fetch the NEXT chunk's operands before working on this one
+                        if (extras && c + u + 1 < BN / 32 && col0 + 64 <= N) load_extras(ep, row0 + lane, col0 + 32, u == 0 ? ex1 : ex0);
+                        if (row_ok) epilogue_direct(ep, r, row0 + lane, col0, u == 0 ? ex0 : ex1);
+                    } else {
+                        epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
+                    }
                 }
             }
             tc_fence_before();
