@@ -273,6 +273,8 @@ class SharedAttnLearner(BaseSharedLearner):
         mine = self._computed_textual_context_cache if is_curr_branch_textual else self._computed_visual_context_cache
         hit = mine.pop(index, None)
         if hit is not None:
+            if hit.is_cuda:      # produced on the other branch's stream: keep the allocator from recycling it early
+                hit.record_stream(torch.cuda.current_stream())
             return hit
         if in_context is None:
             in_context = self.context_vectors[index].unsqueeze(0)
