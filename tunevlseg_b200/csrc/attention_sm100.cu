@@ -41,13 +41,18 @@ __device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2, flushes
     return y;
 }
 
+// inner tile rows: 128 keys per step in the forward; 64 in the backward kernels so that their TMEM footprint
+// (S + dP + accumulators) fits 256 columns and TWO CTAs share an SM (one CTA's exp stage overlaps the other's MMAs,
+// and prologue / epilogue of one CTA hide behind the other)
 template <int MODE>
 struct AtcSmem {
+    static constexpr int TI = MODE == MODE_FWD ? 128 : 64;
+    static constexpr int ITILE = TI * AHD * 2;
     static constexpr int N_OUTER = MODE == MODE_FWD ? 1 : 2;
     static constexpr int OUTER = 0;
     static constexpr int INNER = N_OUTER * ATILE;                 // 2 stages x 2 tiles
-    static constexpr int VEC = INNER + 4 * ATILE;                 // [2 stages][2][128] floats (DKV: lse, delta)
-    static constexpr int BAR = VEC + 2 * 2 * AT * 4;
+    static constexpr int VEC = INNER + 4 * ITILE;                 // [2 stages][2][TI] floats (DKV: lse, delta)
+    static constexpr int BAR = VEC + 2 * 2 * TI * 4;
     static constexpr int TOTAL = BAR + 16 * 8 + 1024;             // barriers + tmem slot + alignment slack
 };
 
@@ -68,8 +73,9 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(ATC_THREADS, MODE == MODE_FWD ? 2 : 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, int S, int H,
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+               const __grid_constant__ CUtensorMap map_qkv_in, const __grid_constant__ CUtensorMap map_do_in, int S, int H,
                __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out,
                const float* __restrict__ lse_in, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv) {
     using L = AtcSmem<MODE>;
@@ -91,12 +97,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     const int ot = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int E = H * AHD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_in = (S + AT - 1) / AT;
+    constexpr int TI = L::TI, ITILE = L::ITILE;
+    const int n_in = (S + TI - 1) / TI;
     const int n_it = MODE == MODE_FWD ? 2 * n_in : n_in;
-    constexpr uint32_t TMEM_COLS = MODE == MODE_FWD ? 256 : 512;
-    constexpr uint32_t C_S = 0, C_DP = 128;
-    constexpr uint32_t C_ACC0 = MODE == MODE_FWD ? 128 : 256;
-    constexpr uint32_t C_ACC1 = 320;
+    constexpr uint32_t TMEM_COLS = 256;
+    constexpr uint32_t C_S = 0, C_DP = TI;                          // FWD: S at [0,128); BWD: S [0,64), dP [64,128)
+    constexpr uint32_t C_ACC0 = 128;                                // O / dQ / dV
+    constexpr uint32_t C_ACC1 = 192;                                // dK
     const long long bh = static_cast<long long>(b) * H + h;
 
     if (threadIdx.x == 0) {
@@ -136,32 +143,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         for (int it = 0; it < n_it; ++it) {
             const int stage = it & 1, par = (it >> 1) & 1;
             const int j = MODE == MODE_FWD ? it % n_in : it;
-            uint8_t* t0 = s_inner + stage * 2 * ATILE;
-            uint8_t* t1 = t0 + ATILE;
+            uint8_t* t0 = s_inner + stage * 2 * ITILE;
+            uint8_t* t1 = t0 + ITILE;
             mbar_wait(&in_empty[stage], par ^ 1);       // whole warp, converged: uniform loop state
             if (elect_one()) {
                 if (MODE == MODE_FWD) {
                     const bool second = it >= n_in;
-                    mbar_expect_tx(&in_full[stage], second ? 2 * ATILE : ATILE);
-                    tma_load_3d(t0, &map_qkv, ck, j * AT, b, &in_full[stage]);
-                    if (second) tma_load_3d(t1, &map_qkv, cv, j * AT, b, &in_full[stage]);
+                    mbar_expect_tx(&in_full[stage], second ? 2 * ITILE : ITILE);
+                    tma_load_3d(t0, &map_qkv_in, ck, j * TI, b, &in_full[stage]);
+                    if (second) tma_load_3d(t1, &map_qkv_in, cv, j * TI, b, &in_full[stage]);
                 } else if (MODE == MODE_DQ) {
-                    mbar_expect_tx(&in_full[stage], 2 * ATILE);
-                    tma_load_3d(t0, &map_qkv, ck, j * AT, b, &in_full[stage]);
-                    tma_load_3d(t1, &map_qkv, cv, j * AT, b, &in_full[stage]);
+                    mbar_expect_tx(&in_full[stage], 2 * ITILE);
+                    tma_load_3d(t0, &map_qkv_in, ck, j * TI, b, &in_full[stage]);
+                    tma_load_3d(t1, &map_qkv_in, cv, j * TI, b, &in_full[stage]);
                 } else {
-                    mbar_expect_tx(&in_full[stage], 2 * ATILE);
-                    tma_load_3d(t0, &map_qkv, cq, j * AT, b, &in_full[stage]);
-                    tma_load_3d(t1, &map_do, h * AHD, j * AT, b, &in_full[stage]);
+                    mbar_expect_tx(&in_full[stage], 2 * ITILE);
+                    tma_load_3d(t0, &map_qkv_in, cq, j * TI, b, &in_full[stage]);
+                    tma_load_3d(t1, &map_do_in, h * AHD, j * TI, b, &in_full[stage]);
                 }
             }
             if (MODE == MODE_DKV) {
                 __syncwarp();
-                float* v_lse = s_vec + stage * 2 * AT;
-                float* v_del = v_lse + AT;
+                float* v_lse = s_vec + stage * 2 * TI;
+                float* v_del = v_lse + TI;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int qi = lane + 32 * k, q = j * AT + qi;
+                for (int k = 0; k < TI / 32; ++k) {
+                    const int qi = lane + 32 * k, q = j * TI + qi;
                     v_lse[qi] = q < S ? lse_in[bh * S + q] * L2E : INFINITY;
                     v_del[qi] = q < S ? delta_in[bh * S + q] : 0.f;
                 }
@@ -173,7 +180,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     } else if (warp == 5) {
         // ------------------------------------------------------------------ MMA issuer
         {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(AT, AT, 0, 0);
+            constexpr uint32_t idesc_s = umma_idesc_bf16(AT, TI, 0, 0);
             constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
             mbar_wait(outer_full, 0);
             tc_fence_after();
@@ -183,8 +190,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 const int stage = it & 1, par = (it >> 1) & 1;
                 mbar_wait(&in_full[stage], par);
                 tc_fence_after();
-                const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ATILE));
-                const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ATILE + ATILE));
+                const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE));
+                const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE + ITILE));
                 const bool last = it == n_it - 1;
                 if (MODE == MODE_FWD) {
                     if (it > 0 && (it - 1) < n_in) {   // the previous iteration was a max-only pass: S must have been read
@@ -224,14 +231,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                     if (elect_one()) {
                         if (MODE == MODE_DQ) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)   // dQ += dS K_j
+                            for (int k = 0; k < TI / 16; ++k)   // dQ += dS K_j
                                 umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)   // dV += P^T dO_i
+                            for (int k = 0; k < TI / 16; ++k)   // dV += P^T dO_i
                                 umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)   // dK += dS^T Q_i
+                            for (int k = 0; k < TI / 16; ++k)   // dK += dS^T Q_i
                                 umma_ts(tb + C_ACC1, tb + C_DP + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit(&in_empty[stage]);
@@ -336,43 +343,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             for (int it = 0; it < n_it; ++it) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                const int c0 = it * AT;                      // first inner row (key for DQ, query for DKV)
-                const float* v_lse = s_vec + (it & 1) * 2 * AT;
-                const float* v_del = v_lse + AT;
+                const int c0 = it * TI;                      // first inner row (key for DQ, query for DKV)
+                const float* v_lse = s_vec + (it & 1) * 2 * TI;
+                const float* v_del = v_lse + TI;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t pkp[32], pks[32];
+                for (int c = 0; c < TI / 32; ++c) {          // 32 score columns -> 16 packed bf16x2 columns
+                    uint32_t pkp[16], pks[16];
+                    uint32_t s[32], dp[32];
+                    tmem_ld32(tl + C_S + 32 * c, s);
+                    tmem_ld32(tl + C_DP + 32 * c, dp);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = 2 * half + cc;
-                        uint32_t s[32], dp[32];
-                        tmem_ld32(tl + C_S + 32 * c, s);
-                        tmem_ld32(tl + C_DP + 32 * c, dp);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            float p0, p1, d0, d1;
-                            if (MODE == MODE_DQ) {
-                                p0 = (c0 + 32 * c + i < S) ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -my_lse)) : 0.f;
-                                p1 = (c0 + 32 * c + i + 1 < S) ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -my_lse)) : 0.f;
-                                d0 = p0 * (__uint_as_float(dp[i]) - my_del);
-                                d1 = p1 * (__uint_as_float(dp[i + 1]) - my_del);
-                            } else {
-                                const int q = 32 * c + i;      // lse = +inf for queries past the end -> p = 0
-                                p0 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -v_lse[q])) : 0.f;
-                                p1 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -v_lse[q + 1])) : 0.f;
-                                d0 = p0 * (__uint_as_float(dp[i]) - v_del[q]);
-                                d1 = p1 * (__uint_as_float(dp[i + 1]) - v_del[q + 1]);
-                            }
-                            pks[16 * cc + i / 2] = pack_bf16x2(d0, d1);
-                            if (MODE == MODE_DKV) pkp[16 * cc + i / 2] = pack_bf16x2(p0, p1);
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0, p1, d0, d1;
+                        if (MODE == MODE_DQ) {
+                            p0 = (c0 + 32 * c + i < S) ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -my_lse)) : 0.f;
+                            p1 = (c0 + 32 * c + i + 1 < S) ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -my_lse)) : 0.f;
+                            d0 = p0 * (__uint_as_float(dp[i]) - my_del);
+                            d1 = p1 * (__uint_as_float(dp[i + 1]) - my_del);
+                        } else {
+                            const int q = 32 * c + i;      // lse = +inf for queries past the end -> p = 0
+                            p0 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -v_lse[q])) : 0.f;
+                            p1 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -v_lse[q + 1])) : 0.f;
+                            d0 = p0 * (__uint_as_float(dp[i]) - v_del[q]);
+                            d1 = p1 * (__uint_as_float(dp[i + 1]) - v_del[q + 1]);
                         }
+                        pks[i / 2] = pack_bf16x2(d0, d1);
+                        if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
                     }
+                    // the packed values overwrite the first half of the columns just consumed (chunk c -> columns 16c..)
                     if (MODE == MODE_DQ) {
-                        tmem_st32(tl + C_S + 32 * half, pks);     // dS over the consumed half of S
+                        tmem_st16(tl + C_S + 16 * c, pks);        // dS
                     } else {
-                        tmem_st32(tl + C_S + 32 * half, pkp);     // P^T
-                        tmem_st32(tl + C_DP + 32 * half, pks);    // dS^T
+                        tmem_st16(tl + C_S + 16 * c, pkp);        // P^T
+                        tmem_st16(tl + C_DP + 16 * c, pks);       // dS^T
                     }
                 }
                 tmem_st_wait();
@@ -426,12 +430,12 @@ static EncodeTiledFn3 encode_fn3() {
 }
 
 // bf16 tensor [B][S][cols] -> 3-D map {cols, S, B}, box {64, 128, 1}, 128-byte swizzle; rows >= S read as zeros
-static int make_tmap3(CUtensorMap* map, const void* ptr, int cols, int S, int B) {
+static int make_tmap3(CUtensorMap* map, const void* ptr, int cols, int S, int B, int box_rows = AT) {
     EncodeTiledFn3 fn = encode_fn3();
     TVS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(S) * cols * 2};
-    cuuint32_t box[3] = {AHD, AT, 1};
+    cuuint32_t box[3] = {AHD, static_cast<cuuint32_t>(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -440,7 +444,8 @@ static int make_tmap3(CUtensorMap* map, const void* ptr, int cols, int S, int B)
 }
 
 template <int MODE>
-static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, int B, int S, int H, __nv_bfloat16* out, float* out32, float* lse_out,
+static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mqi, const CUtensorMap& mdi, int B, int S, int H,
+                      __nv_bfloat16* out, float* out32, float* lse_out,
                       const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st) {
     using L = AtcSmem<MODE>;
     auto kern = attn_tc_kernel<MODE>;
@@ -450,7 +455,7 @@ static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, int B, int S
         attr_set = true;
     }
     dim3 grid((S + AT - 1) / AT, H, B);
-    kern<<<grid, ATC_THREADS, L::TOTAL, st>>>(mq, md, S, H, out, out32, lse_out, lse_in, delta_in, dqkv);
+    kern<<<grid, ATC_THREADS, L::TOTAL, st>>>(mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv);
     return check_launch(MODE == MODE_FWD ? "attn_tc_kernel<fwd>" : (MODE == MODE_DQ ? "attn_tc_kernel<dq>" : "attn_tc_kernel<dkv>"));
 }
 
@@ -462,16 +467,18 @@ bool attn_tc_enabled() {
 int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st) {
     CUtensorMap mq;
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
-    return launch_atc<MODE_FWD>(mq, mq, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st);
+    return launch_atc<MODE_FWD>(mq, mq, mq, mq, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st);
 }
 
 // delta must already hold rowsum(dO o O)
 int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st) {
-    CUtensorMap mq, md;
+    CUtensorMap mq, md, mqi, mdi;      // 128-row boxes for the outer tiles, 64-row boxes for the inner ones
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&md, dout, H * AHD, S, B)) return rc;
-    if (int rc = launch_atc<MODE_DKV>(mq, md, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st)) return rc;
-    return launch_atc<MODE_DQ>(mq, md, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st);
+    if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, 64)) return rc;
+    if (int rc = make_tmap3(&mdi, dout, H * AHD, S, B, 64)) return rc;
+    if (int rc = launch_atc<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st)) return rc;
+    return launch_atc<MODE_DQ>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st);
 }
 
 }  // namespace tvs
