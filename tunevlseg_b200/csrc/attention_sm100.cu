@@ -41,12 +41,12 @@ __device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2, flushes
     return y;
 }
 
-// inner tile rows: 128 keys per step in the forward; 64 in the backward kernels so that their TMEM footprint
-// (S + dP + accumulators) fits 256 columns and TWO CTAs share an SM (one CTA's exp stage overlaps the other's MMAs,
-// and prologue / epilogue of one CTA hide behind the other)
+// inner tile rows: 64 per step, so that the TMEM footprint is 128 columns in the forward (S + O: three CTAs per SM,
+// bounded by registers) and 256 in the backward kernels (S + dP + accumulators: two CTAs per SM).  Co-resident CTAs
+// overlap one CTA's exp stage, prologue and epilogue with another CTA's MMAs.
 template <int MODE>
 struct AtcSmem {
-    static constexpr int TI = MODE == MODE_FWD ? 128 : 64;
+    static constexpr int TI = 64;
     static constexpr int ITILE = TI * AHD * 2;
     static constexpr int N_OUTER = MODE == MODE_FWD ? 1 : 2;
     static constexpr int OUTER = 0;
@@ -73,7 +73,7 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(ATC_THREADS, 2)
+__global__ void __launch_bounds__(ATC_THREADS, MODE == MODE_FWD ? 3 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                const __grid_constant__ CUtensorMap map_qkv_in, const __grid_constant__ CUtensorMap map_do_in, int S, int H,
                __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out,
@@ -100,9 +100,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     constexpr int TI = L::TI, ITILE = L::ITILE;
     const int n_in = (S + TI - 1) / TI;
     const int n_it = MODE == MODE_FWD ? 2 * n_in : n_in;
-    constexpr uint32_t TMEM_COLS = 256;
-    constexpr uint32_t C_S = 0, C_DP = TI;                          // FWD: S at [0,128); BWD: S [0,64), dP [64,128)
-    constexpr uint32_t C_ACC0 = 128;                                // O / dQ / dV
+    constexpr uint32_t TMEM_COLS = MODE == MODE_FWD ? 128 : 256;
+    constexpr uint32_t C_S = 0, C_DP = TI;                          // S [0,64); BWD: dP [64,128)
+    constexpr uint32_t C_ACC0 = MODE == MODE_FWD ? 64 : 128;        // O / dQ / dV
     constexpr uint32_t C_ACC1 = 192;                                // dK
     const long long bh = static_cast<long long>(b) * H + h;
 
@@ -210,7 +210,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                         tc_fence_after();
                         if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)   // O += P V : 16 keys per MMA = 8 TMEM columns of P, 2048 bytes of V
+                            for (int k = 0; k < TI / 16; ++k)   // O += P V : 16 keys per MMA = 8 TMEM columns of P, 2048 bytes of V
                                 umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > n_in || k > 0) ? 1u : 0u);
                             umma_commit(&in_empty[stage]);
                             if (last) umma_commit(acc_full);
@@ -259,9 +259,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             for (int it = 0; it < n_in; ++it) {            // pass 1: row maximum
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                const int k0 = it * AT;
+                const int k0 = it * TI;
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < TI / 32; ++c) {
                     uint32_t r[32];
                     tmem_ld32(tl + C_S + 32 * c, r);
                     tmem_ld_wait();
@@ -282,30 +282,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             for (int it = n_in; it < n_it; ++it) {         // pass 2: P = exp2(S - m), row sum
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                const int k0 = (it - n_in) * AT;
+                const int k0 = (it - n_in) * TI;
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t pk[32];
+                for (int c = 0; c < TI / 32; ++c) {           // 32 score columns -> 16 packed bf16x2 columns, in place
+                    uint32_t pk[16];
+                    uint32_t r[32];
+                    tmem_ld32(tl + C_S + 32 * c, r);
+                    tmem_ld_wait();
+                    const bool full = k0 + 32 * c + 32 <= S;
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = 2 * half + cc;
-                        uint32_t r[32];
-                        tmem_ld32(tl + C_S + 32 * c, r);
-                        tmem_ld_wait();
-                        const bool full = k0 + 32 * c + 32 <= S;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), L2E, -mL));
-                            float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), L2E, -mL));
-                            if (!full) {
-                                if (k0 + 32 * c + i >= S) p0 = 0.f;
-                                if (k0 + 32 * c + i + 1 >= S) p1 = 0.f;
-                            }
-                            l += p0 + p1;
-                            pk[16 * cc + i / 2] = pack_bf16x2(p0, p1);
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), L2E, -mL));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), L2E, -mL));
+                        if (!full) {
+                            if (k0 + 32 * c + i >= S) p0 = 0.f;
+                            if (k0 + 32 * c + i + 1 >= S) p1 = 0.f;
                         }
+                        l += p0 + p1;
+                        pk[i / 2] = pack_bf16x2(p0, p1);
                     }
-                    tmem_st32(tl + C_S + 32 * half, pk);
+                    tmem_st16(tl + C_S + 16 * c, pk);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -465,9 +461,10 @@ bool attn_tc_enabled() {
 }
 
 int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st) {
-    CUtensorMap mq;
+    CUtensorMap mq, mqi;
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
-    return launch_atc<MODE_FWD>(mq, mq, mq, mq, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st);
+    if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, 64)) return rc;
+    return launch_atc<MODE_FWD>(mq, mq, mqi, mqi, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st);
 }
 
 // delta must already hold rowsum(dO o O)
