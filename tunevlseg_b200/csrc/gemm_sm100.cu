@@ -23,7 +23,7 @@ namespace tvs {
 constexpr int BM = 128;
 constexpr int BK_BYTES = 128;  // one k-block = one swizzle-128B row: 64 bf16 or 32 fp32 (tf32) elements
 constexpr int MMAS_PER_KB = 4; // 4 x (16 bf16 | 8 tf32) = 32 bytes of K per tcgen05.mma
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: two epilogue groups of four warps
 
 struct GemmEpilogue {
     const float* bias;
@@ -174,8 +174,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // epilogue.  TMEM gives every thread one ROW of the accumulator (32 consecutive columns per tcgen05.ld); storing
@@ -456,8 +456,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         mbar_init(&tmem_full[0], 1);
         mbar_init(&tmem_full[1], 1);
-        mbar_init(&tmem_empty[0], 4 * CL);
-        mbar_init(&tmem_empty[1], 4 * CL);
+        mbar_init(&tmem_empty[0], 8 * CL);
+        mbar_init(&tmem_empty[1], 8 * CL);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -541,7 +541,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else if (warp >= 4) {
-        const int ew = warp - 4;  // TMEM lane quarter this warp may touch = warp % 4
+        // Two epilogue groups (warps 4-7 and 8-11).  A warp may only touch the TMEM lane quarter warp % 4, so both groups
+        // cover all 128 rows and split the 32-column chunks between them (even / odd).  With a single group the
+        // epilogue's serial chain (TMEM load -> operand loads -> math -> stores, ~1 us per chunk) was longer than the
+        // MMA time of a tile and capped the tensor pipe at 55 % (ncu); two warps per scheduler also hide each other's
+        // latencies.
+        const int ew = (warp - 4) & 3;     // TMEM lane quarter = warp % 4
+        const int grp = (warp - 4) >> 2;   // 0 / 1
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
@@ -553,23 +559,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const bool direct = ep.vec256_ok && !ep.staged;
             const bool row_ok = row0 + lane < M;
             const bool extras = direct && row_ok && (ep.residual != nullptr || ep.act >= TVS_ACT_DQGELU);
-            EpiExtras ex0, ex1;
-            if (extras && n_blk * BN + 32 <= N) load_extras(ep, row0 + lane, n_blk * BN, ex0);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c += 2) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int col0 = n_blk * BN + (c + u) * 32;
-                    if (row0 >= M || col0 >= N) break;      // warp-uniform: nothing of this chunk is inside the matrix
+            for (int c = grp; c < BN / 32; c += 2) {
+                const int col0 = n_blk * BN + c * 32;
+                if (row0 >= M || col0 >= N) break;      // warp-uniform: nothing of this chunk is inside the matrix
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + c * 32, r);
+                if (direct && col0 + 32 <= N) {
+                    EpiExtras ex;
+                    if (extras) load_extras(ep, row0 + lane, col0, ex);     // in flight together with the TMEM load
+                    tmem_ld_wait();
+                    if (row_ok) epilogue_direct(ep, r, row0 + lane, col0, ex);
+                } else {
+                    tmem_ld_wait();
+                    // ragged / unaligned chunks go through the shared-memory stage, which exists once per lane quarter:
+                    // group 1 hands them to group 0 (tiny GEMMs only)
+                    if (grp == 0) epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
+                }
+            }
+            if (grp == 0 && !(direct && N % 32 == 0)) {
+                // pick up the odd chunks that group 1 skipped because they need the staged path
+#pragma unroll 1
+                for (int c = 1; c < BN / 32; c += 2) {
+                    const int col0 = n_blk * BN + c * 32;
+                    if (row0 >= M || col0 >= N) break;
+                    if (direct && col0 + 32 <= N) continue;
                     uint32_t r[32];
-                    tmem_ld_32x32(t_row + (c + u) * 32, r);
-                    if (direct && col0 + 32 <= N) {
-                        // fetch the NEXT chunk's operands before working on this one
-                        if (extras && c + u + 1 < BN / 32 && col0 + 64 <= N) load_extras(ep, row0 + lane, col0 + 32, u == 0 ? ex1 : ex0);
-                        if (row_ok) epilogue_direct(ep, r, row0 + lane, col0, u == 0 ? ex0 : ex1);
-                    } else {
-                        epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
-                    }
+                    tmem_ld_32x32(t_row + c * 32, r);
+                    tmem_ld_wait();
+                    epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
                 }
             }
             tc_fence_before();
