@@ -559,8 +559,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const bool direct = ep.vec256_ok && !ep.staged;
             const bool row_ok = row0 + lane < M;
             const bool extras = direct && row_ok && (ep.residual != nullptr || ep.act >= TVS_ACT_DQGELU);
+            // a group takes PAIRS of adjacent chunks (64 columns): for the bf16 arrays a thread then reads / writes whole
+            // 128-byte lines within a few hundred cycles instead of a quarter of a line per visit
 #pragma unroll 1
-            for (int c = grp; c < BN / 32; c += 2) {
+            for (int cc = grp * 2; cc < BN / 32; cc += (cc & 1) ? 3 : 1) {
+                const int c = cc;
                 const int col0 = n_blk * BN + c * 32;
                 if (row0 >= M || col0 >= N) break;      // warp-uniform: nothing of this chunk is inside the matrix
                 uint32_t r[32];
@@ -578,9 +581,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
             if (grp == 0 && !(direct && N % 32 == 0)) {
-                // pick up the odd chunks that group 1 skipped because they need the staged path
+                // pick up the chunks that group 1 skipped because they need the staged path
 #pragma unroll 1
-                for (int c = 1; c < BN / 32; c += 2) {
+                for (int c = 2; c < BN / 32; c += (c & 1) ? 3 : 1) {
                     const int col0 = n_blk * BN + c * 32;
                     if (row0 >= M || col0 >= N) break;
                     if (direct && col0 + 32 <= N) continue;
