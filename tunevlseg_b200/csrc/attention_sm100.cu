@@ -260,18 +260,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
                 const int k0 = it * TI;
-#pragma unroll 1
-                for (int c = 0; c < TI / 32; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(tl + C_S + 32 * c, r);
-                    tmem_ld_wait();
-                    if (k0 + 32 * c + 32 <= S) {
+                uint32_t r0[32], r1[32];                    // both 32-column chunks in flight, one wait
+                tmem_ld32(tl + C_S, r0);
+                tmem_ld32(tl + C_S + 32, r1);
+                tmem_ld_wait();
+                if (k0 + TI <= S) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
-                    } else {
+                    for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (k0 + 32 * c + i < S) m = fmaxf(m, __uint_as_float(r[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        if (k0 + i < S) m = fmaxf(m, __uint_as_float(r0[i]));
+                        if (k0 + 32 + i < S) m = fmaxf(m, __uint_as_float(r1[i]));
                     }
                 }
                 tc_fence_before();
@@ -283,17 +283,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
                 const int k0 = (it - n_in) * TI;
-#pragma unroll 1
-                for (int c = 0; c < TI / 32; ++c) {           // 32 score columns -> 16 packed bf16x2 columns, in place
+                uint32_t r0[32], r1[32];
+                tmem_ld32(tl + C_S, r0);
+                tmem_ld32(tl + C_S + 32, r1);
+                tmem_ld_wait();
+                const bool full = k0 + TI <= S;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {                 // 32 score columns -> 16 packed bf16x2 columns, in place
                     uint32_t pk[16];
-                    uint32_t r[32];
-                    tmem_ld32(tl + C_S + 32 * c, r);
-                    tmem_ld_wait();
-                    const bool full = k0 + 32 * c + 32 <= S;
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), L2E, -mL));
-                        float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), L2E, -mL));
+                        float p0 = fast_exp2(fmaf(__uint_as_float(c == 0 ? r0[i] : r1[i]), L2E, -mL));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(c == 0 ? r0[i + 1] : r1[i + 1]), L2E, -mL));
                         if (!full) {
                             if (k0 + 32 * c + i >= S) p0 = 0.f;
                             if (k0 + 32 * c + i + 1 >= S) p1 = 0.f;
@@ -342,32 +343,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 const int c0 = it * TI;                      // first inner row (key for DQ, query for DKV)
                 const float* v_lse = s_vec + (it & 1) * 2 * TI;
                 const float* v_del = v_lse + TI;
-#pragma unroll 1
-                for (int c = 0; c < TI / 32; ++c) {          // 32 score columns -> 16 packed bf16x2 columns
+                // software pipeline over the two 32-column chunks: chunk 1's TMEM loads fly while chunk 0 is processed
+                uint32_t sA[32], dA[32], sB[32], dB[32];
+                tmem_ld32(tl + C_S, sA);
+                tmem_ld32(tl + C_DP, dA);
+                tmem_ld_wait();
+                tmem_ld32(tl + C_S + 32, sB);
+                tmem_ld32(tl + C_DP + 32, dB);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {                // 32 score columns -> 16 packed bf16x2 columns
                     uint32_t pkp[16], pks[16];
-                    uint32_t s[32], dp[32];
-                    tmem_ld32(tl + C_S + 32 * c, s);
-                    tmem_ld32(tl + C_DP + 32 * c, dp);
-                    tmem_ld_wait();
+                    if (c == 1) tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
+                        const float s0 = __uint_as_float(c == 0 ? sA[i] : sB[i]), s1 = __uint_as_float(c == 0 ? sA[i + 1] : sB[i + 1]);
+                        const float g0 = __uint_as_float(c == 0 ? dA[i] : dB[i]), g1 = __uint_as_float(c == 0 ? dA[i + 1] : dB[i + 1]);
                         float p0, p1, d0, d1;
                         if (MODE == MODE_DQ) {
-                            p0 = (c0 + 32 * c + i < S) ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -my_lse)) : 0.f;
-                            p1 = (c0 + 32 * c + i + 1 < S) ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -my_lse)) : 0.f;
-                            d0 = p0 * (__uint_as_float(dp[i]) - my_del);
-                            d1 = p1 * (__uint_as_float(dp[i + 1]) - my_del);
+                            p0 = (c0 + 32 * c + i < S) ? fast_exp2(fmaf(s0, L2E, -my_lse)) : 0.f;
+                            p1 = (c0 + 32 * c + i + 1 < S) ? fast_exp2(fmaf(s1, L2E, -my_lse)) : 0.f;
+                            d0 = p0 * (g0 - my_del);
+                            d1 = p1 * (g1 - my_del);
                         } else {
                             const int q = 32 * c + i;      // lse = +inf for queries past the end -> p = 0
-                            p0 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i]), L2E, -v_lse[q])) : 0.f;
-                            p1 = row_ok ? fast_exp2(fmaf(__uint_as_float(s[i + 1]), L2E, -v_lse[q + 1])) : 0.f;
-                            d0 = p0 * (__uint_as_float(dp[i]) - v_del[q]);
-                            d1 = p1 * (__uint_as_float(dp[i + 1]) - v_del[q + 1]);
+                            p0 = row_ok ? fast_exp2(fmaf(s0, L2E, -v_lse[q])) : 0.f;
+                            p1 = row_ok ? fast_exp2(fmaf(s1, L2E, -v_lse[q + 1])) : 0.f;
+                            d0 = p0 * (g0 - v_del[q]);
+                            d1 = p1 * (g1 - v_del[q + 1]);
                         }
                         pks[i / 2] = pack_bf16x2(d0, d1);
                         if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
                     }
-                    // the packed values overwrite the first half of the columns just consumed (chunk c -> columns 16c..)
+                    // the packed values overwrite the first half of the columns just consumed (chunk c -> columns 16c..);
+                    // all four loads have completed before the first store (c == 0 stores touch columns 0..15 only, which
+                    // belong to chunk 0, already in registers)
                     if (MODE == MODE_DQ) {
                         tmem_st16(tl + C_S + 16 * c, pks);        // dS
                     } else {
