@@ -14,6 +14,13 @@ import sys
 
 __version__ = "0.1.0"
 
+try:  # the text tower runs on a side stream by design: its AccumulateGrad nodes legitimately see two streams
+    import torch as _torch
+
+    _torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+except Exception:  # noqa: BLE001 - older torch
+    pass
+
 
 def install_as_src() -> None:
     """Expose this package under the reference's module paths, so its Hydra configs resolve unchanged:

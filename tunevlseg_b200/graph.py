@@ -47,6 +47,32 @@ class GraphedTrainStep:
             if torch.is_tensor(v):
                 self.static[k].copy_(v, non_blocking=True)
 
+    # ---- input prefetch: the host->device copy of step k+1 runs on a copy stream while step k computes -------------
+    def prefetch(self, batch: dict) -> None:
+        """Start copying ``batch`` (pinned host tensors) into a staging buffer on a side stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = {k: torch.empty_like(v) for k, v in self.static.items() if torch.is_tensor(v)}
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)          # the previous staging contents have been consumed
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in batch.items():
+                if torch.is_tensor(v):
+                    self._staging[k].copy_(v, non_blocking=True)
+            self._staged.record()
+
+    def step_prefetched(self) -> torch.Tensor:
+        """Consume the staged batch (device-to-device copy into the graph's static inputs) and replay."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for k, v in self._staging.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self._consumed.record()
+        self.graph.replay()
+        return self.loss
+
     def __call__(self, batch: dict | None = None) -> torch.Tensor:
         if batch is not None:
             self.load(batch)
