@@ -362,9 +362,14 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out))
     if world > 1:
+        # The captured graph holds NCCL work on the communicator; tearing the process group down under it can block
+        # forever (observed).  All ranks are done and rank 0 has printed: synchronise, flush and leave without the
+        # communicator teardown.
         torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
