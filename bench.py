@@ -332,8 +332,14 @@ def main():
         fam = k.split(":")[0]
         fam_t = sum(v[0] for kk, v in agg.items() if kk.split(":")[0] == fam)
         achieved = f / (t * 1e-3) / 1e12
+        traffic = None      # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture, if it is this kernel
+        tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("kernel") == k:
+                traffic = tj["dram_bytes_per_launch"]
         roof = {"bound": "tensor", "kernel": k, "achieved": round(achieved, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["tf_sustained"], 4), "traffic": None, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                 "launches_per_step": c, "avg_launch_us": round(1e3 * t / c, 1), "share_of_step": round(t / total, 3),
                 "family_share_of_step": round(fam_t / total, 3)}
 
