@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from oracle import clipseg as OC
+from oracle import cris as OCR
 from oracle import learners as OL
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -43,3 +44,26 @@ def load_case(name):
 
 def learner_state(name, params):
     return OL.LearnerState(params=params, **CASES[name])
+
+
+# ---- CRIS (tests/golden/make_golden_cris.py) -----------------------------------------------------------------------
+CRIS_TINY = OCR.CrisSpec(image_size=64, input_resolution=96, rn_layers=(1, 2, 1, 1), rn_width=8, embed_dim=160,
+                         t_width=128, t_layers=3, context_length=77, vocab_size=600, fpn_out=(64, 128, 192),
+                         dec_layers=2, dec_heads=2, dec_ffn=256)
+
+CRIS_CASES = {
+    "cris_coop_d1_n4": dict(kind="coop", prompt_depth=1, num_context=4),
+    "cris_coop_d3_n4_nomask": dict(kind="coop", prompt_depth=3, num_context=4),
+    "cris_cocoop_d1_n4": dict(kind="cocoop", prompt_depth=1, num_context=4, proj_style="mlp", norm_image_features=False),
+    "cris_cocoop_d2_n4_long": dict(kind="cocoop", prompt_depth=2, num_context=4, proj_style="mlp", norm_image_features=True),
+}
+
+
+def load_cris_weights():
+    """The generator loads ``init_weights(CRIS_TINY, seed=2025)`` over the whole reference net (bit-exact fp32), so the
+    frozen weights are regenerated from the seed instead of being stored (12 MB)."""
+    return OCR.init_weights(CRIS_TINY, seed=2025)
+
+
+def cris_learner_state(name, params):
+    return OL.LearnerState(params=params, **CRIS_CASES[name])

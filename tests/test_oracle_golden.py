@@ -3,7 +3,9 @@ import pytest
 import torch
 
 from oracle import clipseg as OC
-from tests.golden_cases import CASES, TINY, learner_state, load_case, load_weights
+from oracle import cris as OCR
+from tests.golden_cases import (CASES, CRIS_CASES, CRIS_TINY, TINY, cris_learner_state, learner_state, load_case,
+                                load_cris_weights, load_weights)
 
 TOL = 1e-5
 
@@ -60,3 +62,43 @@ def test_known_quirks():
     d, _, _ = load_case("coop_d1_n4")
     assert not bool(d["head_hasgrad/additive_decoder_layer.1.weight"])
     assert not bool(d["head_hasgrad/residual_ratio"])
+
+
+@pytest.mark.parametrize("name", list(CRIS_CASES))
+def test_cris_oracle_matches_reference(name):
+    """oracle/cris.py against the reference's own COOPCRIS (fixtures from tests/golden/make_golden_cris.py)."""
+    w = load_cris_weights()
+    d, learner, head = load_case(name)
+    learner = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in learner.items()}
+    head = {k: v.clone().requires_grad_(True) for k, v in head.items()}
+    st = cris_learner_state(name, learner)
+    am = d["attention_mask"] if bool(d["has_mask"]) else None
+    logits = OCR.net_forward(w, CRIS_TINY, st, head, d["input_ids"], am, d["image"])
+    assert logits.shape == d["logits"].shape
+    err = (logits - d["logits"]).abs().max().item()
+    assert err <= 2e-5, f"logits max-abs {err}"
+    (logits * d["grad_weight"]).sum().backward()
+    checked = 0
+    for k, v in d.items():
+        for kind, store in (("learner_grad/", learner), ("head_grad/", head)):
+            if not k.startswith(kind):
+                continue
+            pk = k[len(kind):]
+            has = bool(d[f"{kind[:-6]}_hasgrad/{pk}"])
+            g = store[pk].grad
+            if not has:
+                assert g is None or g.abs().max() == 0, f"{pk}: reference gives no grad"
+                continue
+            scale = max(1.0, v.abs().max().item())
+            assert (g - v).abs().max().item() / scale <= 5e-5, f"{pk}: grad rel err {(g - v).abs().max().item() / scale}"
+            checked += 1
+    assert checked >= 5
+
+
+def test_cris_known_quirks():
+    # depth 1: the rows inserted from ctx[0] are re-written with the same ctx[0] after block 0 (0-based overwrite,
+    # coop_cris.py:129-141), so ctx[0] gets gradient through both uses; every additive-layer tensor is live.
+    d, _, _ = load_case("cris_coop_d1_n4")
+    assert bool(d["learner_hasgrad/context_vectors"]) and d["learner_grad/context_vectors"].abs().max() > 0
+    for k in ("additive_decoder_layer.0.weight", "additive_decoder_layer.2.weight", "additive_decoder_layer.2.bias", "residual_ratio"):
+        assert bool(d[f"head_hasgrad/{k}"])

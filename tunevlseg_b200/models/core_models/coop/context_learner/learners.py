@@ -162,6 +162,50 @@ class BaseProjectorLearner(CoOpContextLearner):
         return layers
 
 
+def _batched_projection(layers, x: torch.Tensor):
+    """Apply `len(layers)` structurally identical projectors to x[i] in a handful of batched launches.
+
+    Every depth has its own tiny projector (n x 512 -> 64 -> 768 rows); evaluating them one by one costs ~15 kernel
+    launches per depth in forward + backward, all on the step's critical path in front of the vision tower.  Stacking
+    the per-depth parameters (they stay separate nn.Parameters: state_dict / optimizer groups are unchanged) turns
+    them into two bmm's, one ReLU and one LayerNorm.  Returns None when the projectors are not of a batchable form
+    (Linear | Linear-ReLU-Linear, optionally followed by LayerNorm).
+    """
+    seqs = [list(l) if isinstance(l, nn.Sequential) else [l] for l in layers]
+    kinds = [tuple(type(m) for m in q) for q in seqs]
+    if len(set(kinds)) != 1:
+        return None
+    kind = kinds[0]
+    has_ln = kind and kind[-1] is nn.LayerNorm
+    core = kind[:-1] if has_ln else kind
+    if core not in ((nn.Linear,), (nn.Linear, nn.ReLU, nn.Linear)):
+        return None
+
+    def stk(ms, attr):
+        ts = [getattr(m, attr) for m in ms]
+        if any(t is None for t in ts):
+            return None
+        return torch.stack(ts)
+
+    def lin(ms, inp):
+        w, b = stk(ms, "weight"), stk(ms, "bias")
+        out = torch.bmm(inp, w.transpose(1, 2))
+        return out if b is None else out + b.unsqueeze(1)
+
+    h = lin([q[0] for q in seqs], x)
+    if len(core) == 3:
+        h = lin([q[2] for q in seqs], torch.relu(h))
+    if has_ln:
+        lns = [q[-1] for q in seqs]
+        if len({ln.eps for ln in lns}) != 1:
+            return None
+        h = torch.nn.functional.layer_norm(h, (h.shape[-1],), eps=lns[0].eps) * stk(lns, "weight").unsqueeze(1)
+        beta = stk(lns, "bias")
+        if beta is not None:
+            h = h + beta.unsqueeze(1)
+    return h
+
+
 def _layer_list(factory, depth: int, unified: bool, clone_first: bool = False) -> nn.ModuleList:
     """One shared module repeated `depth` times (unified) or `depth` independent ones."""
     if unified:
@@ -220,6 +264,15 @@ class MapleContextLearner(BaseProjectorLearner, BaseVisualLearner):
 
     def get_visual_context(self, *args, **kwargs) -> torch.Tensor:
         return self.get_transformed_context(*args, **kwargs)
+
+    def visual_stack(self, n_layers: int) -> torch.Tensor:
+        used = min(self.prompt_depth, n_layers + 1)
+        out = _batched_projection(list(self.projection_layers)[:used], self.context_vectors[:used])
+        if out is None:
+            return super().visual_stack(n_layers)
+        if used < self.prompt_depth:
+            out = torch.cat((out, out.new_zeros((self.prompt_depth - used, *out.shape[1:]))))
+        return out
 
 
 class VPTContextLearner(BaseVisualLearner):
@@ -322,3 +375,19 @@ class SharedSeparateLearner(BaseSharedLearner):
 
     def get_visual_context(self, in_context=None, index: int = 0) -> torch.Tensor:
         return self.visual_projection_layers[index](self.context_vectors[index] if in_context is None else in_context)
+
+    def visual_stack(self, n_layers: int) -> torch.Tensor:
+        used = min(self.prompt_depth, n_layers + 1)
+        out = _batched_projection(list(self.visual_projection_layers)[:used], self.context_vectors[:used])
+        if out is None:
+            return super().visual_stack(n_layers)
+        if used < self.prompt_depth:
+            out = torch.cat((out, out.new_zeros((self.prompt_depth - used, *out.shape[1:]))))
+        return out
+
+    def textual_deep_stack(self, n_layers: int, image_features=None):
+        last = min(self.prompt_depth, n_layers)
+        if last <= 1:
+            return None
+        out = _batched_projection(list(self.textual_projection_layers)[1:last], self.context_vectors[1:last])
+        return out if out is not None else super().textual_deep_stack(n_layers, image_features)
