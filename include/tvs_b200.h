@@ -44,12 +44,14 @@ int tvs_device_check(void);
  *     v  = act(v)                            act: TVS_ACT_*
  *     v += residual_f32[m,n]
  *     out_f32[m,n] = v ; out_bf16[m,n] = v
+ * TVS_ACT_RES_RELU applies the ReLU AFTER the residual add: relu(acc + bias + residual) - the tail of a ResNet
+ * bottleneck (cris_model/clip.py:66-75).
  * TVS_ACT_DQGELU / TVS_ACT_DRELU multiply v by act'(aux_bf16[m,n]) (aux = saved pre-activation, or the
  * post-ReLU activation for DRELU) - the dgrad-through-activation epilogue.
  * Requirements: K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, A and W 16-byte aligned.
  * ------------------------------------------------------------------------------------------------ */
 enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1 };
-enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4 };
+enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4, TVS_ACT_RES_RELU = 5 };
 
 typedef struct tvs_gemm_args {
     const void* A;  int64_t lda;           /* bf16 [M,K] */
@@ -78,7 +80,7 @@ int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);
  * fwd: y = (x - mean) * rstd * gamma + beta ; saves mean/rstd (f32 [M]) when non-NULL.
  * bwd: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma   (no dgamma/dbeta: frozen)
  *      dx_out_f32 = dx (+ dx_add_f32) ; dx_out_bf16 = same, rounded.  dy is bf16 (dy_bf16) or f32 (dy_f32).
- * D % 4 == 0, D <= 1024.
+ * D % 4 == 0, D <= 2048 (2048: the CRIS decoder FFN norm, layers.py:303-309).
  * ------------------------------------------------------------------------------------------------ */
 int tvs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int32_t D,
                       float* y_f32, void* y_bf16, float* mean, float* rstd, void* stream);
@@ -206,6 +208,63 @@ int tvs_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_a
                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                    const int32_t* step_dev, const float* lr_dev, void* stream);
 int tvs_counter_inc(int32_t* counter_dev, void* stream);
+
+/* ================================================================================================
+ * CRIS path (src/models/components/cris_model, src/models/core_models/coop/coop_cris.py).
+ * Activations are channels-last matrices [B*H*W, C]; a k x k convolution = tvs_im2col_nhwc + tvs_gemm_bf16
+ * (BatchNorm folded into the weight rows, ReLU / residual in the GEMM epilogue); its dgrad = GEMM with the
+ * transposed weight + tvs_col2im_nhwc.  Replaces nn.Conv2d / nn.BatchNorm2d / F.avg_pool2d / F.interpolate /
+ * nn.MultiheadAttention / F.conv2d(groups=B) at the cited lines.
+ * ================================================================================================ */
+/* col[(b,oy,ox), (ky,kx,c)] = x[b, oy*stride - pad + ky, ox*stride - pad + kx, c] (0 outside); columns
+ * [ksize*ksize*C, ldcol) are zero-filled (K padding for the GEMM).  elem_bytes 2 (bf16) or 4 (f32).
+ * clip.py:199-218 (stem), :26-27 (bottleneck conv2), layers.py:14-26 (conv_layer 3x3). */
+int tvs_im2col_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize,
+                    int32_t stride, int32_t pad, void* col, int64_t ldcol, void* stream);
+/* dgrad of a stride-1 'same' k x k conv from dcol = dy @ W: dx[b,y,x,c] = sum_taps dcol[...] for c < Cx <= Ccol,
+ * times (relu_mask > 0) when given (the ReLU of the layer that produced x). */
+int tvs_col2im_nhwc(const float* dcol, int64_t ldcol, int32_t B, int32_t H, int32_t W, int32_t Ccol, int32_t Cx,
+                    int32_t ksize, const float* relu_mask, int64_t ld_mask, float* dx, int64_t ld_dx, void* stream);
+/* out = y > 0 ? dy : 0 on [M, C] views with row strides (ReLU backward in front of a 1x1-conv dgrad GEMM) */
+int tvs_relu_mask(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int64_t M, int32_t C, float* out,
+                  int64_t ld_out, void* stream);
+/* 2x2 / stride-2 average pooling (clip.py:32,47,222 nn.AvgPool2d(2); layers.py:432 F.avg_pool2d) */
+int tvs_avgpool2_nhwc(const void* x, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* y,
+                      int64_t ld_out, void* stream);
+/* bilinear x2, align_corners=False (layers.py:85-88 nn.Upsample, :427,:441 F.interpolate); f32.
+ * fwd writes rows of ld_out floats (a column slice of a concat buffer); bwd reads dy rows of ld_dy floats. */
+int tvs_upsample2x_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, int64_t ld_out, void* stream);
+int tvs_upsample2x_bwd(const float* dy, int64_t ld_dy, int32_t B, int32_t H, int32_t W, int32_t C, float* dx, void* stream);
+/* Attention over a SHORT key set in fp32: Sq queries x Sk <= 80 keys, head dim 64.  Used for the decoder's cross
+ * attention (layers.py:341-349 multihead_attn with key_padding_mask) and, with causal != 0 (Sq == Sk, key j > query i
+ * masked), for the <= 77-token CLIP text encoder of CRIS (clip.py:291-343), whose output steers the dynamic
+ * convolution and needs more than bf16 operands.  q: [B*Sq, H*64] rows of ld_q (scale pre-folded), k / v: [B*Sk, H*64] rows of ld_kv,
+ * key_mask u8 [B,Sk] 1 = attend or NULL; out [B*Sq, H*64]; lse, delta f32 [B,H,Sq]. */
+int tvs_cross_attn_fwd(const float* q, int64_t ld_q, const float* k, const float* v, int64_t ld_kv,
+                       const uint8_t* key_mask, int32_t B, int32_t Sq, int32_t Sk, int32_t H, int32_t hd, int32_t causal,
+                       float* out, int64_t ld_o, float* lse, void* stream);
+int tvs_cross_attn_bwd(const float* q, int64_t ld_q, const float* k, const float* v, int64_t ld_kv,
+                       const uint8_t* key_mask, const float* out, const float* dout, int64_t ld_o, const float* lse,
+                       int32_t B, int32_t Sq, int32_t Sk, int32_t H, int32_t hd, int32_t causal, float* dq, int64_t ld_dq,
+                       float* dk, float* dv, int64_t ld_dkv, float* delta, void* stream);
+/* Projector tail (layers.py:96-119): out[b,p] = bias[b] + sum_{c,t} x[b, p+off_t, c] * w[b, c*9+t], 3x3, zero pad.
+ * x f32 [B*H*W, C]; w rows of ld_w floats (the txt Linear output), bias[b] at bias + b*ld_bias; taps f32 [B*H*W, 9]
+ * scratch kept for nothing (recomputed in bwd).  bwd: dx, and dw_part f32 [chunks, B, C*9] partial sums over
+ * pixel chunks (the caller adds them: deterministic). */
+int tvs_dynconv_fwd(const float* x, const float* w, int64_t ld_w, const float* bias, int64_t ld_bias, int32_t B,
+                    int32_t H, int32_t W, int32_t C, float* taps, float* out, void* stream);
+int tvs_dynconv_bwd(const float* dout, const float* x, const float* w, int64_t ld_w, int32_t B, int32_t H, int32_t W,
+                    int32_t C, float* dx, float* dw_part, int32_t chunks, void* stream);
+/* Separable table-driven resampling of single-channel maps (coop_cris.py:235 bicubic, align_corners=True).
+ * fwd: out[b,y,x] = sum_a sum_c wy[y,a] wx[x,c] in[b, iy[y,a], ix[x,c]]   (tables [Ho,ntaps] / [Wo,ntaps])
+ * bwd: din[b,y,x] = sum over the transposed tables ty/twy [Hi,max_taps] with counts cy [Hi] (same for x).
+ * tile > 0: the big map is stored in tvs_head_fwd's [B*(Ho/tile)*(Wo/tile), tile*tile] layout. */
+int tvs_resample2d_fwd(const float* in, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, const int32_t* iy,
+                       const float* wy, const int32_t* ix, const float* wx, int32_t ntaps, int32_t tile, float* out,
+                       void* stream);
+int tvs_resample2d_bwd(const void* dout, int32_t dout_is_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho,
+                       int32_t Wo, const int32_t* ty, const float* twy, const int32_t* cy, const int32_t* tx,
+                       const float* twx, const int32_t* cx, int32_t max_taps, int32_t tile, float* din, void* stream);
 
 #ifdef __cplusplus
 }

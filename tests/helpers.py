@@ -115,3 +115,94 @@ def make_batch(spec: OC.ClipSegSpec, B: int, L: int, seed: int, pad: bool = True
         am[b, eos + 1:] = 0
     mask = (torch.rand(B, 1, spec.image_size, spec.image_size, generator=g) < 0.3).float()
     return img, ids, am, mask
+
+
+# ---- CRIS ------------------------------------------------------------------------------------------------------------
+from types import SimpleNamespace  # noqa: E402
+
+from oracle import cris as OCR  # noqa: E402
+
+CRIS_SMALL = OCR.CrisSpec(image_size=64, input_resolution=96, rn_layers=(1, 2, 1, 1), rn_width=8, embed_dim=160,
+                          t_width=128, t_layers=3, context_length=77, vocab_size=600, fpn_out=(64, 128, 192),
+                          dec_layers=2, dec_heads=2, dec_ffn=256)
+CRIS_FULL = OCR.CrisSpec()        # CLIP-RN50 @ 416x416 (configs/model/coop/cris.yaml)
+
+CRIS_CASES = {
+    "coop": dict(learner="CoOpContextLearner", kw=dict(prompt_depth=1, num_context=4), oracle=dict(kind="coop")),
+    "coop_d3": dict(learner="CoOpContextLearner", kw=dict(prompt_depth=3, num_context=4), oracle=dict(kind="coop")),
+    "cocoop": dict(learner="CoCoOpContextLearner",
+                   kw=dict(prompt_depth=1, num_context=4, intermediate_dim=64, use_proj_norm=True, use_unified_projection=False,
+                           use_lora_proj=False, norm_image_features=False),
+                   oracle=dict(kind="cocoop", proj_style="mlp", norm_image_features=False)),
+    "cocoop_d2_norm": dict(learner="CoCoOpContextLearner",
+                           kw=dict(prompt_depth=2, num_context=4, intermediate_dim=8, use_proj_norm=True, use_unified_projection=False,
+                                   use_lora_proj=False, norm_image_features=True),
+                           oracle=dict(kind="cocoop", proj_style="mlp", norm_image_features=True)),
+}
+
+
+class StubTokenizer:
+    """'a photo of a' -> 4 fixed ids: stands in for the CLIP BPE tokenizer of configs/model/coop/cris.yaml:22-24."""
+
+    def __call__(self, text, **kw):
+        texts = [text] if isinstance(text, str) else list(text)
+        return SimpleNamespace(input_ids=torch.tensor([[320 + 7 * i + 13 * j for j, _ in enumerate(t.split())] for i, t in enumerate(texts)]))
+
+
+def cris_model_cfg(spec: OCR.CrisSpec, weights: dict):
+    backbone = {k[len("backbone."):]: v for k, v in weights.items() if k.startswith("backbone.")}
+    return dict(clip_pretrain=backbone, fpn_in=list(spec.fpn_in), fpn_out=list(spec.fpn_out), vis_dim=spec.vis_dim,
+                word_dim=spec.embed_dim, num_layers=spec.dec_layers, num_head=spec.dec_heads, dim_ffn=spec.dec_ffn, dropout=0.2,
+                return_intermediate=False, img_size=spec.image_size, freeze_encoder=True, cris_pretrain=None)
+
+
+def build_cris_net(case: str, spec: OCR.CrisSpec, weights: dict, seed: int = 0, residual_ratio: float = 0.35, new_last_layer: bool = True):
+    """Product COOPCRIS on CPU holding exactly ``weights`` (the oracle's dict) as frozen parameters."""
+    import tunevlseg_b200.models.core_models.coop as nets
+    import tunevlseg_b200.models.core_models.coop.context_learner as learners
+
+    c = CRIS_CASES[case]
+    torch.manual_seed(seed)
+    net = nets.COOPCRIS(model_cfg=cris_model_cfg(spec, weights),
+                        context_learner=partial(getattr(learners, c["learner"]), context_initializer="a photo of a",
+                                                tokenizer=StubTokenizer(), **c["kw"]),
+                        freeze_all=True, no_freeze_last_layer=False, use_new_last_layer=new_last_layer, new_last_layer_kernel_size=5,
+                        residual_ratio=residual_ratio)
+    res = net.load_state_dict(weights, strict=False)       # undo build_model's fp16 round trip: hold the oracle's exact values
+    assert not res.unexpected_keys, res.unexpected_keys
+    with torch.no_grad():
+        for p in net.context_learner.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    return net
+
+
+def cris_oracle_state(case: str, net) -> OL.LearnerState:
+    c = CRIS_CASES[case]
+    params = {k: v.detach().cpu().clone().float().requires_grad_(v.is_floating_point())
+              for k, v in net.context_learner.state_dict().items()}
+    return OL.LearnerState(params=params, prompt_depth=c["kw"]["prompt_depth"], num_context=c["kw"]["num_context"], **c["oracle"])
+
+
+CRIS_HEAD_KEYS = ("additive_decoder_layer.0.weight", "additive_decoder_layer.2.weight", "additive_decoder_layer.2.bias", "residual_ratio")
+
+
+def cris_oracle_head(net):
+    named = dict(net.named_parameters())
+    if "residual_ratio" not in named:
+        return None
+    return {k: named[k].detach().cpu().clone().float().requires_grad_(True) for k in CRIS_HEAD_KEYS}
+
+
+def make_cris_batch(spec: OCR.CrisSpec, B: int, L: int, seed: int, pad: bool = True):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(B, 3, spec.image_size, spec.image_size, generator=g)
+    ids = torch.randint(1, spec.vocab_size - 10, (B, L), generator=g)
+    ids[:, 0] = spec.vocab_size - 2
+    am = torch.ones(B, L, dtype=torch.long)
+    for b in range(B):
+        eos = L - 1 if not pad else max(2, L - 1 - 2 * b)
+        ids[b, eos] = spec.vocab_size - 1
+        ids[b, eos + 1:] = 0
+        am[b, eos + 1:] = 0
+    mask = (torch.rand(B, 1, spec.image_size, spec.image_size, generator=g) < 0.3).float()
+    return img, ids, am, mask

@@ -181,3 +181,101 @@ def test_install_as_src_resolves_reference_targets():
                    "src.models.components.hf_clipseg_wrapper.HFCLIPSegWrapper"):
         mod, _, attr = target.rpartition(".")
         assert hasattr(importlib.import_module(mod), attr), target
+
+
+# ---- CRIS host side ----------------------------------------------------------------------------------------------------
+def test_cris_state_dict_keys_match_reference():
+    """COOPCRIS holds its parameters under the reference's state_dict names: frozen keys == the oracle's weight dict
+    (whose key set the golden generator asserted against the real reference net), plus BN counters / logit_scale."""
+    from oracle import cris as OCR
+    from tests.helpers import CRIS_HEAD_KEYS, CRIS_SMALL, build_cris_net
+
+    w = OCR.init_weights(CRIS_SMALL, seed=3)
+    net = build_cris_net("cocoop", CRIS_SMALL, w)
+    sd = net.state_dict()
+    frozen = {k for k in sd if not k.startswith(("context_learner.", "additive_decoder_layer.", "residual_ratio"))
+              and not k.endswith("num_batches_tracked") and k != "backbone.logit_scale"}
+    assert frozen == set(w)
+    assert all(torch.equal(sd[k], w[k]) for k in w)
+    assert all(k in sd for k in CRIS_HEAD_KEYS) and "backbone.logit_scale" in sd
+    assert "context_learner.context_vectors" in sd and sd["context_learner.context_vectors"].shape == (1, 4, CRIS_SMALL.t_width)
+    trainable = {k for k, p in net.named_parameters() if p.requires_grad}
+    assert trainable == {k for k in sd if k.startswith(("context_learner.", "additive_decoder_layer."))
+                         and not k.endswith(("running_mean", "running_var", "num_batches_tracked"))} | {"residual_ratio"}
+    net.train()
+    assert not net.backbone.training and not net.decoder.training and not net.neck.training and not net.proj.training
+
+
+def test_cris_build_model_fp16_round_trip_and_errors():
+    from oracle import cris as OCR
+    from tests.helpers import CRIS_SMALL, cris_model_cfg
+    from tunevlseg_b200.models.components.cris_model import CRIS, build_model
+
+    w = OCR.init_weights(CRIS_SMALL, seed=4)
+    bb = {k[len("backbone."):]: v for k, v in w.items() if k.startswith("backbone.")}
+    m = build_model(dict(bb, input_resolution=torch.tensor(96), context_length=torch.tensor(77), vocab_size=torch.tensor(600)))
+    sd = m.state_dict()
+    # clip.py:556-575: conv / linear / attention tensors go through fp16, norms and embeddings do not
+    assert torch.equal(sd["visual.layer1.0.conv2.weight"], bb["visual.layer1.0.conv2.weight"].half().float())
+    assert torch.equal(sd["transformer.resblocks.0.attn.in_proj_weight"], bb["transformer.resblocks.0.attn.in_proj_weight"].half().float())
+    assert torch.equal(sd["text_projection"], bb["text_projection"].half().float())
+    assert torch.equal(sd["visual.bn1.weight"], bb["visual.bn1.weight"]) and torch.equal(sd["token_embedding.weight"], bb["token_embedding.weight"])
+    assert m.visual.layers == CRIS_SMALL.rn_layers and m.visual.input_resolution == 96 and not m.training
+    with pytest.raises(NotImplementedError):
+        build_model({"visual.proj": torch.zeros(1)})
+    net = CRIS(**cris_model_cfg(CRIS_SMALL, w))
+    with pytest.raises(NotImplementedError):
+        net(None, None)
+    with pytest.raises(ValueError):
+        from tunevlseg_b200.models.components.cris_model import FPN
+        FPN(in_channels=(1, 2), out_channels=(1, 2, 3))
+
+
+def test_cris_bicubic_tables_match_torch():
+    """The tap tables driving tvs_resample2d reproduce F.interpolate(bicubic, align_corners=True) and its adjoint."""
+    from tunevlseg_b200.engine_cris import _bicubic_tables
+
+    for n_in, n_out in ((16, 64), (104, 416), (5, 5)):
+        idx, wt, t_idx, t_w, cnt, mt = _bicubic_tables(n_in, n_out, "cpu")
+        R = torch.zeros(n_out, n_in)
+        for o in range(n_out):
+            for a in range(4):
+                R[o, idx[o, a]] += wt[o, a]
+        x = torch.randn(1, 1, n_in, n_in)
+        ref = torch.nn.functional.interpolate(x, (n_out, n_out), mode="bicubic", align_corners=True)[0, 0]
+        assert (R @ x[0, 0] @ R.t() - ref).abs().max() < 1e-4      # torch evaluates the source index in fp32
+        Rt = torch.zeros(n_in, n_out)
+        for i in range(n_in):
+            for j in range(int(cnt[i])):
+                Rt[i, t_idx[i, j]] += t_w[i, j]
+        assert torch.allclose(Rt, R.t(), atol=1e-7)
+
+
+@pytest.mark.parametrize("case", ["coop_d3", "cocoop"])
+def test_cris_engine_composition_against_oracle(case, monkeypatch):
+    """The host-side composition of the CRIS engine (operand packing with folded BatchNorm, layouts, strides, flags,
+    autograd wiring) run over a CPU emulation of the C ABI (tests/fake_abi.py) must reproduce the oracle to fp32
+    round-off - forward and every learner / additive-layer gradient."""
+    from oracle import cris as OCR
+    from tests import fake_abi
+    from tests.helpers import CRIS_SMALL, build_cris_net, cris_oracle_head, cris_oracle_state, make_cris_batch
+
+    fake_abi.install(monkeypatch)
+    w = OCR.init_weights(CRIS_SMALL, seed=7)
+    net = build_cris_net(case, CRIS_SMALL, w, seed=31)
+    st, head = cris_oracle_state(case, net), cris_oracle_head(net)
+    img, ids, am, mask = make_cris_batch(CRIS_SMALL, 2, 8, 32)
+    logits = net(text_input={"input_ids": ids, "attention_mask": am}, image_input=img)
+    ref = OCR.net_forward(w, CRIS_SMALL, st, head, ids, am, img)
+    # the emulation rounds GEMM operands to tf32 and the flash-attention operands to bf16, as the device does
+    assert (logits - ref).abs().max().item() < 2e-2, (logits - ref).abs().max().item()
+    gw = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    (logits * gw).sum().backward()
+    (ref * gw).sum().backward()
+    named = dict(net.named_parameters())
+    for k, p_ref in list(st.params.items()) + list(head.items()):
+        pk = k if k in head else f"context_learner.{k}"
+        g, g_ref = named[pk].grad, p_ref.grad
+        assert g is not None and g_ref is not None, pk
+        err = ((g - g_ref).norm() / g_ref.norm()).item()
+        assert err < 5e-2, f"{pk}: {err}"

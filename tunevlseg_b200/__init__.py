@@ -26,7 +26,7 @@ def install_as_src() -> None:
     """Expose this package under the reference's module paths, so its Hydra configs resolve unchanged:
     ``_target_: src.models.core_models.coop.MapleCLIPSeg`` -> ``tunevlseg_b200.models.core_models.coop.MapleCLIPSeg``;
     ``monai.losses.DiceCELoss`` -> the fused loss when monai is absent."""
-    names = ["models", "models.image_text_mask_module", "models.components", "models.components.hf_clipseg_wrapper",
+    names = ["models", "models.image_text_mask_module", "models.components", "models.components.hf_clipseg_wrapper", "models.components.cris_model",
              "models.core_models", "models.core_models.coop", "models.core_models.coop.context_learner"]
     if "src" not in sys.modules:
         import types

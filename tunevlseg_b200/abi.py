@@ -15,7 +15,7 @@ import torch
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtvs_b200.so")
 
-ACT_NONE, ACT_QGELU, ACT_RELU, ACT_DQGELU, ACT_DRELU = range(5)
+ACT_NONE, ACT_QGELU, ACT_RELU, ACT_DQGELU, ACT_DRELU, ACT_RES_RELU = range(6)
 BLEND_NONE, BLEND_RATIO, BLEND_ADD = range(3)
 
 
@@ -86,6 +86,18 @@ def load():
         "tvs_metrics_from_probs": [P, P, I32, I64, F, P, P, P, P],
         "tvs_adamw_flat": [P, P, P, P, I64, F, F, F, F, F, I32, F, P, P, P],
         "tvs_counter_inc": [P, P],
+        "tvs_im2col_nhwc": [P, I32, I32, I32, I32, I32, I32, I32, I32, P, I64, P],
+        "tvs_col2im_nhwc": [P, I64, I32, I32, I32, I32, I32, I32, P, I64, P, I64, P],
+        "tvs_relu_mask": [P, I64, P, I64, I64, I32, P, I64, P],
+        "tvs_avgpool2_nhwc": [P, I32, I32, I32, I32, I32, P, I64, P],
+        "tvs_upsample2x_fwd": [P, I32, I32, I32, I32, P, I64, P],
+        "tvs_upsample2x_bwd": [P, I64, I32, I32, I32, I32, P, P],
+        "tvs_cross_attn_fwd": [P, I64, P, P, I64, P, I32, I32, I32, I32, I32, I32, P, I64, P, P],
+        "tvs_cross_attn_bwd": [P, I64, P, P, I64, P, P, P, I64, P, I32, I32, I32, I32, I32, I32, P, I64, P, P, I64, P, P],
+        "tvs_dynconv_fwd": [P, P, I64, P, I64, I32, I32, I32, I32, P, P, P],
+        "tvs_dynconv_bwd": [P, P, P, I64, I32, I32, I32, I32, P, P, I32, P],
+        "tvs_resample2d_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, I32, P, P],
+        "tvs_resample2d_bwd": [P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, I32, I32, P, P],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -110,6 +122,11 @@ def require_device() -> None:
     if lib.tvs_device_check() != 0:
         raise TvsError(lib.tvs_last_error().decode())
     _device_ok = True
+
+
+def check_cuda_input(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise TvsError("tunevlseg_b200 runs on a CUDA (sm_100a) device only; inputs must be CUDA tensors")
 
 
 def launch_count() -> int:
@@ -426,3 +443,124 @@ for _n in ("gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "im
            "film_bwd", "head_fwd", "head_bwd", "dicebce_metrics_fwd", "dicebce_bwd", "metrics_from_probs", "adamw_flat",
            "counter_inc"):
     globals()[_n] = _wrap(globals()[_n], _n)
+
+
+# ---- CRIS path (conv_ops.cu) -----------------------------------------------------------------------------------------
+def _chk2(t, name, dtypes=(torch.float32,)):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise TvsError(f"{name} must be a CUDA tensor")
+    if t.dtype not in dtypes:
+        raise TvsError(f"{name} must be one of {dtypes}, got {t.dtype}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise TvsError(f"{name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+
+
+def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col):
+    """x: contiguous [B*H*W, C] (bf16 or f32) -> col [B*Ho*Wo, ld >= k*k*C] of the same dtype (tail zero-filled)."""
+    require_device()
+    _chk2(x, "x", (torch.float32, torch.bfloat16)); _chk2(col, "col", (x.dtype,))
+    if not x.is_contiguous() or tuple(x.shape) != (B * H * W, C):
+        raise TvsError(f"im2col: x must be contiguous {(B * H * W, C)}, got {tuple(x.shape)}")
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    if col.shape[0] != B * Ho * Wo or col.stride(0) != col.shape[1]:
+        raise TvsError("im2col: col must be a dense [B*Ho*Wo, ld] matrix")
+    _ck(load().tvs_im2col_nhwc(x.data_ptr(), x.element_size(), B, H, W, C, ksize, stride, pad, col.data_ptr(), col.shape[1],
+                               _stream()), "tvs_im2col_nhwc")
+
+
+def col2im_nhwc(dcol, B, H, W, Ccol, Cx, ksize, dx, relu_mask=None):
+    require_device()
+    _chk2(dcol, "dcol"); _chk2(dx, "dx"); _chk2(relu_mask, "relu_mask")
+    _ck(load().tvs_col2im_nhwc(dcol.data_ptr(), dcol.stride(0), B, H, W, Ccol, Cx, ksize, _p(relu_mask),
+                               relu_mask.stride(0) if relu_mask is not None else 0, dx.data_ptr(), dx.stride(0), _stream()),
+        "tvs_col2im_nhwc")
+
+
+def relu_mask(dy, y, out):
+    require_device()
+    _chk2(dy, "dy"); _chk2(y, "y"); _chk2(out, "out")
+    if dy.shape != y.shape or dy.shape != out.shape:
+        raise TvsError("relu_mask: shape mismatch")
+    _ck(load().tvs_relu_mask(dy.data_ptr(), dy.stride(0), y.data_ptr(), y.stride(0), dy.shape[0], dy.shape[1], out.data_ptr(),
+                             out.stride(0), _stream()), "tvs_relu_mask")
+
+
+def avgpool2_nhwc(x, B, H, W, C, y):
+    require_device()
+    _chk2(x, "x", (torch.float32, torch.bfloat16)); _chk2(y, "y", (x.dtype,))
+    if not x.is_contiguous():
+        raise TvsError("avgpool2: x must be contiguous")
+    _ck(load().tvs_avgpool2_nhwc(x.data_ptr(), int(x.dtype == torch.bfloat16), B, H, W, C, y.data_ptr(), y.stride(0), _stream()),
+        "tvs_avgpool2_nhwc")
+
+
+def upsample2x_fwd(x, B, H, W, C, y):
+    require_device()
+    _chk2(x, "x"); _chk2(y, "y")
+    if not x.is_contiguous():
+        raise TvsError("upsample2x: x must be contiguous")
+    _ck(load().tvs_upsample2x_fwd(x.data_ptr(), B, H, W, C, y.data_ptr(), y.stride(0), _stream()), "tvs_upsample2x_fwd")
+
+
+def upsample2x_bwd(dy, B, H, W, C, dx):
+    require_device()
+    _chk2(dy, "dy"); _chk2(dx, "dx")
+    if not dx.is_contiguous():
+        raise TvsError("upsample2x_bwd: dx must be contiguous")
+    _ck(load().tvs_upsample2x_bwd(dy.data_ptr(), dy.stride(0), B, H, W, C, dx.data_ptr(), _stream()), "tvs_upsample2x_bwd")
+
+
+def cross_attn_fwd(q, k, v, key_mask, B, Sq, Sk, H, hd, out, lse, causal=False):
+    require_device()
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _chk2(t, n)
+    if k.stride(0) != v.stride(0):
+        raise TvsError("cross_attn: k and v must share a row stride")
+    _chk(lse, torch.float32, "lse"); _chk(key_mask, torch.uint8, "key_mask")
+    _ck(load().tvs_cross_attn_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), _p(key_mask), B, Sq, Sk, H, hd,
+                                  int(causal), out.data_ptr(), out.stride(0), lse.data_ptr(), _stream()), "tvs_cross_attn_fwd")
+
+
+def cross_attn_bwd(q, k, v, key_mask, out, dout, lse, B, Sq, Sk, H, hd, dq, dk, dv, delta, causal=False):
+    require_device()
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out), ("dout", dout), ("dq", dq), ("dk", dk), ("dv", dv)):
+        _chk2(t, n)
+    if k.stride(0) != v.stride(0) or out.stride(0) != dout.stride(0) or dk.stride(0) != dv.stride(0):
+        raise TvsError("cross_attn_bwd: paired operands must share row strides")
+    _ck(load().tvs_cross_attn_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), _p(key_mask), out.data_ptr(),
+                                  dout.data_ptr(), out.stride(0), lse.data_ptr(), B, Sq, Sk, H, hd, int(causal), dq.data_ptr(), dq.stride(0),
+                                  dk.data_ptr(), dv.data_ptr(), dk.stride(0), delta.data_ptr(), _stream()), "tvs_cross_attn_bwd")
+
+
+def dynconv_fwd(x, w, bias, B, H, W, C, taps, out):
+    """w: [B, >= C*9] rows (channel-major, tap-minor); bias: a column view [B, 1] of the same matrix."""
+    require_device()
+    _chk2(x, "x"); _chk2(w, "w"); _chk(taps, torch.float32, "taps"); _chk(out, torch.float32, "out")
+    _ck(load().tvs_dynconv_fwd(x.data_ptr(), w.data_ptr(), w.stride(0), bias.data_ptr(), bias.stride(0), B, H, W, C, taps.data_ptr(),
+                               out.data_ptr(), _stream()), "tvs_dynconv_fwd")
+
+
+def dynconv_bwd(dout, x, w, B, H, W, C, dx, dw_part):
+    require_device()
+    _chk(dout, torch.float32, "dout"); _chk2(x, "x"); _chk2(w, "w"); _chk(dx, torch.float32, "dx"); _chk(dw_part, torch.float32, "dw_part")
+    _ck(load().tvs_dynconv_bwd(dout.data_ptr(), x.data_ptr(), w.data_ptr(), w.stride(0), B, H, W, C, dx.data_ptr(), dw_part.data_ptr(),
+                               dw_part.shape[0], _stream()), "tvs_dynconv_bwd")
+
+
+def resample2d_fwd(inp, B, Hi, Wi, Ho, Wo, tab, tile, out):
+    require_device()
+    _chk(inp, torch.float32, "in"); _chk(out, torch.float32, "out")
+    _ck(load().tvs_resample2d_fwd(inp.data_ptr(), B, Hi, Wi, Ho, Wo, tab["iy"].data_ptr(), tab["wy"].data_ptr(), tab["ix"].data_ptr(),
+                                  tab["wx"].data_ptr(), tab["ntaps"], tile, out.data_ptr(), _stream()), "tvs_resample2d_fwd")
+
+
+def resample2d_bwd(dout, B, Hi, Wi, Ho, Wo, tab, tile, din):
+    require_device()
+    if dout.dtype not in (torch.float32, torch.bfloat16) or not dout.is_contiguous():
+        raise TvsError("resample2d_bwd: dout must be contiguous f32 or bf16")
+    _chk(din, torch.float32, "din")
+    _ck(load().tvs_resample2d_bwd(dout.data_ptr(), int(dout.dtype == torch.bfloat16), B, Hi, Wi, Ho, Wo, tab["ty"].data_ptr(),
+                                  tab["twy"].data_ptr(), tab["cy"].data_ptr(), tab["tx"].data_ptr(), tab["twx"].data_ptr(),
+                                  tab["cx"].data_ptr(), tab["max_taps"], tile, din.data_ptr(), _stream()), "tvs_resample2d_bwd")

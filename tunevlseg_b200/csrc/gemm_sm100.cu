@@ -188,6 +188,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr int EPI_LD = 36;                       // floats per staged row
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;     // 4608 bytes per epilogue warp
 
+__device__ __forceinline__ bool is_dact(int act) { return act == TVS_ACT_DQGELU || act == TVS_ACT_DRELU; }
+
 __device__ __forceinline__ float epi_act(const GemmEpilogue& ep, float v, float aux) {
     if (ep.act == TVS_ACT_QGELU) return quick_gelu(v);
     if (ep.act == TVS_ACT_RELU) return fmaxf(v, 0.0f);
@@ -202,7 +204,7 @@ __device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, 
     if (ep.pre_bf16) *reinterpret_cast<uint2*>(ep.pre_bf16 + row * ep.ldpre + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     if (ep.act != TVS_ACT_NONE) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.act >= TVS_ACT_DQGELU) {
+        if (is_dact(ep.act)) {
             const uint2 q = __ldg(reinterpret_cast<const uint2*>(ep.aux_bf16 + row * ep.ldaux + col));
             const float2 lo = unpack_bf16x2(q.x), hi = unpack_bf16x2(q.y);
             a = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -213,6 +215,7 @@ __device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, 
         const float4 r = *reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col);
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
+    if (ep.act == TVS_ACT_RES_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + row * ep.ldo32 + col) = v;
     if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + row * ep.ldo16 + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
@@ -221,8 +224,9 @@ __device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, 
 __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& ep, float x, long long row, int c) {
     if (ep.bias) x += __ldg(ep.bias + c);
     if (ep.pre_bf16) ep.pre_bf16[row * ep.ldpre + c] = __float2bfloat16(x);
-    if (ep.act != TVS_ACT_NONE) x = epi_act(ep, x, ep.act >= TVS_ACT_DQGELU ? __bfloat162float(ep.aux_bf16[row * ep.ldaux + c]) : 0.f);
+    if (ep.act != TVS_ACT_NONE) x = epi_act(ep, x, is_dact(ep.act) ? __bfloat162float(ep.aux_bf16[row * ep.ldaux + c]) : 0.f);
     if (ep.residual) x += ep.residual[row * ep.ldr + c];
+    if (ep.act == TVS_ACT_RES_RELU) x = fmaxf(x, 0.f);
     if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = x;
     if (ep.out_bf16) ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
 }
@@ -258,7 +262,7 @@ struct EpiExtras {
     uint32_t res[32];
 };
 __device__ __forceinline__ void load_extras(const GemmEpilogue& ep, long long row, int col0, EpiExtras& e) {
-    if (ep.act >= TVS_ACT_DQGELU) {
+    if (is_dact(ep.act)) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             uint32_t a[8];
@@ -299,7 +303,7 @@ __device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const ui
     } else if (ep.act == TVS_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-    } else if (ep.act >= TVS_ACT_DQGELU) {
+    } else if (is_dact(ep.act)) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float2 u = unpack_bf16x2(ex.aux[i]);
@@ -310,6 +314,10 @@ __device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const ui
     if (ep.residual) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(ex.res[i]);
+    }
+    if (ep.act == TVS_ACT_RES_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
     }
     if (ep.out_f32) {
 #pragma unroll
@@ -558,7 +566,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + ew * EPI_WARP_FLOATS;
             const bool direct = ep.vec256_ok && !ep.staged;
             const bool row_ok = row0 + lane < M;
-            const bool extras = direct && row_ok && (ep.residual != nullptr || ep.act >= TVS_ACT_DQGELU);
+            const bool extras = direct && row_ok && (ep.residual != nullptr || is_dact(ep.act));
             // a group takes PAIRS of adjacent chunks (64 columns): for the bf16 arrays a thread then reads / writes whole
             // 128-byte lines within a few hundred cycles instead of a quarter of a line per visit
 #pragma unroll 1

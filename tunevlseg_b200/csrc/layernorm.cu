@@ -6,9 +6,10 @@
 
 namespace tvs {
 
-constexpr int LN_MAXC = 8;  // float4 chunks per lane -> D <= 1024
+constexpr int LN_MAXC = 16;  // float4 chunks per lane: the kernels are instantiated for 8 (D <= 1024) and 16 (D <= 2048)
 constexpr int LN_WARPS = 4;
 
+template <int MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M,
                      int D, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
@@ -17,10 +18,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     const int lane = threadIdx.x & 31;
     const int nch = D >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
-    float4 v[LN_MAXC];
+    float4 v[MAXC];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
+    for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
         if (c < nch) {
             v[i] = xr[c];
@@ -30,7 +31,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     const float mean = warp_sum(sum) / static_cast<float>(D);
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
+    for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
         if (c < nch) {
             const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -45,7 +46,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
+    for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
         if (c < nch) {
             const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
@@ -60,6 +61,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     }
 }
 
+template <int MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add,
@@ -71,10 +73,10 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
-    float4 gg[LN_MAXC], xh[LN_MAXC];
+    float4 gg[MAXC], xh[MAXC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
+    for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
         if (c < nch) {
             float4 d;
@@ -96,7 +98,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     const float c1 = warp_sum(s1) / static_cast<float>(D);
     const float c2 = warp_sum(s2) / static_cast<float>(D);
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
+    for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
         if (c < nch) {
             float4 o;
@@ -122,8 +124,12 @@ extern "C" __attribute__((visibility("default"))) int tvs_layernorm_fwd(const fl
     TVS_REQUIRE(x && gamma && beta && (y_f32 || y_bf16), "tvs_layernorm_fwd: null pointer");
     TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_fwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
     const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
-    layernorm_fwd_kernel<<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
-                                                                                        static_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
+    if (D <= 1024)
+        layernorm_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
+                                                                                               static_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
+    else
+        layernorm_fwd_kernel<16><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
+                                                                                                static_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
     return check_launch("layernorm_fwd_kernel");
 }
 
@@ -135,8 +141,13 @@ extern "C" __attribute__((visibility("default"))) int tvs_layernorm_bwd(const vo
     TVS_REQUIRE(x && gamma && mean && rstd && (dx_out_f32 || dx_out_bf16), "tvs_layernorm_bwd: null pointer");
     TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_bwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
     const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
-    layernorm_bwd_kernel<<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, M, D, dx_out_f32,
-        static_cast<__nv_bfloat16*>(dx_out_bf16));
+    if (D <= 1024)
+        layernorm_bwd_kernel<8><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, M, D, dx_out_f32,
+            static_cast<__nv_bfloat16*>(dx_out_bf16));
+    else
+        layernorm_bwd_kernel<16><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, M, D, dx_out_f32,
+            static_cast<__nv_bfloat16*>(dx_out_bf16));
     return check_launch("layernorm_bwd_kernel");
 }

@@ -49,9 +49,11 @@ def _f(w: torch.Tensor) -> torch.Tensor:
 class PackedLayer:
     """bf16 operands of one transformer block (pre- or post-LN), forward and transposed (dgrad) copies."""
 
-    def __init__(self, layer, heads: int, tf32: bool = False):
+    def __init__(self, layer, heads: int, tf32: bool = False, attn32: bool = False):
         """``tf32``: also keep fp32 forward operands; the block's forward GEMMs then run kind::tf32 on fp32
-        activations (text tower and decoder: <3 % of the FLOPs but most of the logit rounding error)."""
+        activations (text tower and decoder: <3 % of the FLOPs but most of the logit rounding error).
+        ``attn32`` (needs tf32, head dim 64, S <= 80): q / k / v stay fp32 and the attention runs in the short-key fp32
+        kernel (tvs_cross_attn_*) - the CRIS text encoder, whose output steers a dynamic convolution."""
         sa, mlp = layer.self_attn, layer.mlp
         D = sa.q_proj.weight.shape[0]
         hd = D // heads
@@ -70,7 +72,9 @@ class PackedLayer:
         self.w2_t = _bf(mlp.fc2.weight.t())                     # [F, D]
         self.g1, self.be1 = _f(layer.layer_norm1.weight), _f(layer.layer_norm1.bias)
         self.g2, self.be2 = _f(layer.layer_norm2.weight), _f(layer.layer_norm2.bias)
-        self.tf32 = tf32
+        self.tf32, self.attn32 = tf32, attn32 and tf32
+        if attn32 and tf32:
+            self.wqkv_t32 = _f(wqkv.t())
         if tf32:
             self.wqkv32, self.wo32 = _f(wqkv), _f(sa.out_proj.weight)
             self.w1_32, self.w2_32 = _f(mlp.fc1.weight), _f(mlp.fc2.weight)
@@ -170,12 +174,18 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     ln = _e((M, D), adt, x)
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
     abi.layernorm_fwd(x, pk.g1, pk.be1, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean1, rstd=rstd1)
-    qkv = _e((M, 3 * D), BF16, x)
-    abi.gemm(ln, pk.wqkv32 if hi else pk.wqkv, bias=pk.bqkv, out_bf16=qkv)
-    att = _e((M, D), BF16, x)
-    att32 = _e((M, D), F32, x) if hi else None
     lse = _e((B, pk.heads, S), F32, x)
-    abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, causal, key_mask, att, lse, out_f32=att32)
+    if pk.attn32:
+        qkv = _e((M, 3 * D), F32, x)
+        abi.gemm(ln, pk.wqkv32, bias=pk.bqkv, out_f32=qkv)
+        att = att32 = _e((M, D), F32, x)
+        abi.cross_attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], key_mask, B, S, S, pk.heads, pk.hd, att32, lse, causal=causal)
+    else:
+        qkv = _e((M, 3 * D), BF16, x)
+        abi.gemm(ln, pk.wqkv32 if hi else pk.wqkv, bias=pk.bqkv, out_bf16=qkv)
+        att = _e((M, D), BF16, x)
+        att32 = _e((M, D), F32, x) if hi else None
+        abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, causal, key_mask, att, lse, out_f32=att32)
     x1 = _e((M, D), F32, x)
     abi.gemm(att32 if hi else att, pk.wo32 if hi else pk.wo, bias=pk.bo, residual=x, out_f32=x1)
     mean2, rstd2 = _e((M,), F32, x), _e((M,), F32, x)
@@ -202,8 +212,8 @@ def encoder_layer_bwd(pk: PackedLayer, sv: Saved, g, g16, B, S, causal, key_mask
         abi.gemm(du, pk.w1_t32, out_f32=dln)
         g1 = _e((M, D), F32, g)
         abi.layernorm_bwd(dln, sv.x1, pk.g2, sv.mean2, sv.rstd2, dx_add=g, dx_f32=g1)
-        datt = _e((M, D), BF16, g)
-        abi.gemm(g1, pk.wo_t32, out_bf16=datt)
+        datt = _e((M, D), F32 if pk.attn32 else BF16, g)
+        abi.gemm(g1, pk.wo_t32, out_f32=datt if pk.attn32 else None, out_bf16=None if pk.attn32 else datt)
     else:
         du = _e((M, F), BF16, g)
         abi.gemm(g16, pk.w2_t, aux_bf16=sv.u, out_bf16=du, act=abi.ACT_DQGELU)
@@ -213,13 +223,19 @@ def encoder_layer_bwd(pk: PackedLayer, sv: Saved, g, g16, B, S, causal, key_mask
         abi.layernorm_bwd(dln, sv.x1, pk.g2, sv.mean2, sv.rstd2, dx_add=g, dx_f32=g1, dx_bf16=g1_16)
         datt = dln
         abi.gemm(g1_16, pk.wo_t, out_bf16=datt)
-    dqkv = _e((M, 3 * D), BF16, g)
     delta = _e((B, pk.heads, S), F32, g)
-    abi.attn_bwd(sv.qkv, sv.att, datt, sv.lse, B, S, pk.heads, pk.hd, causal, key_mask, delta, dqkv)
+    if pk.attn32:
+        dqkv = _e((M, 3 * D), F32, g)
+        q, k, v = sv.qkv[:, :D], sv.qkv[:, D:2 * D], sv.qkv[:, 2 * D:]
+        abi.cross_attn_bwd(q, k, v, key_mask, sv.att, datt, sv.lse, B, S, S, pk.heads, pk.hd, dqkv[:, :D], dqkv[:, D:2 * D],
+                           dqkv[:, 2 * D:], delta, causal=causal)
+    else:
+        dqkv = _e((M, 3 * D), BF16, g)
+        abi.attn_bwd(sv.qkv, sv.att, datt, sv.lse, B, S, pk.heads, pk.hd, causal, key_mask, delta, dqkv)
     g0 = _e((M, D), F32, g)
     if hi:
         dln1 = _e((M, D), F32, g)
-        abi.gemm(dqkv, pk.wqkv_t, out_f32=dln1)
+        abi.gemm(dqkv, pk.wqkv_t32 if pk.attn32 else pk.wqkv_t, out_f32=dln1)
         abi.layernorm_bwd(dln1, sv.x, pk.g1, sv.mean1, sv.rstd1, dx_add=g1, dx_f32=g0)
         return g0, None
     dln1 = _e((M, D), BF16, g)

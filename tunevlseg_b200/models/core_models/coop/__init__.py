@@ -1,5 +1,4 @@
-"""Prompt-tuned CLIPSeg nets with the reference's names (src/models/core_models/coop/__init__.py:1-8).
-COOPCRIS (CRIS / CLIP-RN50) is not built yet - see DESIGN.md "out of scope this round"."""
+"""Prompt-tuned CLIPSeg / CRIS nets with the reference's names (src/models/core_models/coop/__init__.py:1-8)."""
 from .clipseg import (  # noqa: F401
     BaseCLIPSeg,
     BaseMultimodalCLIPSeg,
@@ -9,3 +8,4 @@ from .clipseg import (  # noqa: F401
     SharedSeparateCLIPSeg,
     VPTCLIPSeg,
 )
+from .coop_cris import COOPCRIS  # noqa: F401,E402
