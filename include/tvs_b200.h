@@ -220,7 +220,11 @@ int tvs_counter_inc(int32_t* counter_dev, void* stream);
  * [ksize*ksize*C, ldcol) are zero-filled (K padding for the GEMM).  elem_bytes 2 (bf16) or 4 (f32).
  * clip.py:199-218 (stem), :26-27 (bottleneck conv2), layers.py:14-26 (conv_layer 3x3). */
 int tvs_im2col_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize,
-                    int32_t stride, int32_t pad, void* col, int64_t ldcol, void* stream);
+                    int32_t stride, int32_t pad, void* col, int64_t ldcol, int32_t round_tf32, void* stream);
+/* y = x rounded to nearest tf32 (cvt.rna), [M, C] f32 views.  The kind::tf32 MMA truncates its operands (a
+ * systematic -3.4e-4 relative bias per GEMM that compounds over the ~60 layers of CLIP-RN50), so forward operands are
+ * rounded on their way into tvs_gemm_bf16: here, or inside tvs_im2col_nhwc (round_tf32 != 0) for k x k convolutions. */
+int tvs_round_tf32(const float* x, int64_t ld_x, int64_t M, int32_t C, float* y, int64_t ld_y, void* stream);
 /* dgrad of a stride-1 'same' k x k conv from dcol = dy @ W: dx[b,y,x,c] = sum_taps dcol[...] for c < Cx <= Ccol,
  * times (relu_mask > 0) when given (the ReLU of the layer that produced x). */
 int tvs_col2im_nhwc(const float* dcol, int64_t ldcol, int32_t B, int32_t H, int32_t W, int32_t Ccol, int32_t Cx,

@@ -25,9 +25,17 @@ def _qg_grad(x):
 
 
 def _tf32(x):
-    """Round fp32 to the 10-bit mantissa the kind::tf32 MMA reads (round to nearest, ties away - as cvt.rna.tf32)."""
-    i = x.contiguous().view(torch.int32)
-    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    """What the kind::tf32 MMA does to an fp32 operand: the low 13 mantissa bits are TRUNCATED (measured on B200)."""
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _tf32_rn(x):
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) on the 10-bit mantissa."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def round_tf32(x, y):
+    y.copy_(_tf32_rn(x))
 
 
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0):
@@ -137,14 +145,14 @@ def cast_bf16(x, y):
     y.copy_(x)
 
 
-def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col):
+def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col, round_tf32=False):
     assert x.is_contiguous() and x.shape == (B * H * W, C) and col.dtype == x.dtype and col.is_contiguous()
     cols = F.unfold(x.float().view(B, H, W, C).permute(0, 3, 1, 2), ksize, padding=pad, stride=stride)      # (B, C*k*k, L), (c,ky,kx)
     L = cols.shape[-1]
     cols = cols.view(B, C, ksize, ksize, L).permute(0, 4, 2, 3, 1).reshape(B * L, ksize * ksize * C)
     assert col.shape[0] == B * L and col.shape[1] >= cols.shape[1]
     col.zero_()
-    col[:, : cols.shape[1]] = cols
+    col[:, : cols.shape[1]] = _tf32_rn(cols) if round_tf32 else cols
 
 
 def col2im_nhwc(dcol, B, H, W, Ccol, Cx, ksize, dx, relu_mask=None):
@@ -304,7 +312,7 @@ def head_bwd(dlogits, tconv, add_out, bias_t, ratio, blend, B, G, P, ksize, dtco
 
 def install(monkeypatch):
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "prompt_overwrite", "prompt_grad", "wgrad_small",
-                 "cast_bf16", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd",
+                 "cast_bf16", "round_tf32", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd",
                  "cross_attn_fwd", "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd", "head_fwd",
                  "head_bwd"):
         monkeypatch.setattr(abi, name, globals()[name])

@@ -22,6 +22,16 @@ GRAD_TOL = 8e-2
 GRAD_L2_TOL = 4e-2
 
 
+@pytest.fixture(autouse=True)
+def _fp32_torch_reference():
+    """The torch references below must be true fp32: cuDNN / cuBLAS default to TF32 for convolutions."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
@@ -50,11 +60,14 @@ def test_conv_fwd_dgrad_tf32(cin, cout, k, hw):
     x2 = _nhwc(x).requires_grad_(True)
     y2 = E.conv(x2, op, B, hw, hw)
     xr = x.clone().requires_grad_(True)
-    ref = F.relu(F.batch_norm(F.conv2d(xr, sd["c.0.weight"], padding=k // 2), sd["c.1.running_mean"], sd["c.1.running_var"],
-                              sd["c.1.weight"], sd["c.1.bias"], False, 0.0, 1e-5))
+    pre = F.batch_norm(F.conv2d(xr, sd["c.0.weight"], padding=k // 2), sd["c.1.running_mean"], sd["c.1.running_var"],
+                       sd["c.1.weight"], sd["c.1.bias"], False, 0.0, 1e-5)
+    ref = F.relu(pre)
     assert _rel(_nchw(y2, B, hw, hw), ref) < 2e-3                 # tf32 operands
     gy = torch.randn(ref.shape, device="cuda", generator=g)
-    ref.backward(gy)
+    # ReLU mask taken from OUR output: pre-activations within tf32 round-off of zero may legitimately flip, and one
+    # flipped tap moves dx by ~1/sqrt(cin k^2) of its scale
+    (pre * (_nchw(y2, B, hw, hw).detach() > 0)).backward(gy)
     y2.backward(_nhwc(gy))
     cx = cin // 4 * 4
     assert _rel(_nchw(x2.grad, B, hw, hw)[:, :cx], xr.grad[:, :cx]) < 3e-3
@@ -222,7 +235,7 @@ def _run_cris(case, spec, B, L, seed, pad=True, use_mask=True, new_last_layer=Tr
         l2 = ((g.detach().cpu() - g_ref).norm() / g_ref.norm()).item()
         assert gerr <= GRAD_TOL and l2 <= GRAD_L2_TOL, f"{case}: grad {pk} max rel {gerr:.4f} l2 rel {l2:.4f}"
         checked += 1
-    assert checked >= 2
+    assert checked >= (2 if head else 1)
     return err
 
 

@@ -129,6 +129,7 @@ def test_eval_step_no_grad_matches_train_forward():
     assert not out_eval.requires_grad and out_train.requires_grad
     assert torch.equal(out_eval, out_train.detach())
     module.eval()
+    module.setup("test")
     with torch.no_grad():
         module.validation_step(batch, 0)
         module.test_step(batch, 0)

@@ -86,7 +86,8 @@ def load():
         "tvs_metrics_from_probs": [P, P, I32, I64, F, P, P, P, P],
         "tvs_adamw_flat": [P, P, P, P, I64, F, F, F, F, F, I32, F, P, P, P],
         "tvs_counter_inc": [P, P],
-        "tvs_im2col_nhwc": [P, I32, I32, I32, I32, I32, I32, I32, I32, P, I64, P],
+        "tvs_im2col_nhwc": [P, I32, I32, I32, I32, I32, I32, I32, I32, P, I64, I32, P],
+        "tvs_round_tf32": [P, I64, I64, I32, P, I64, P],
         "tvs_col2im_nhwc": [P, I64, I32, I32, I32, I32, I32, I32, P, I64, P, I64, P],
         "tvs_relu_mask": [P, I64, P, I64, I64, I32, P, I64, P],
         "tvs_avgpool2_nhwc": [P, I32, I32, I32, I32, I32, P, I64, P],
@@ -457,7 +458,16 @@ def _chk2(t, name, dtypes=(torch.float32,)):
         raise TvsError(f"{name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
 
 
-def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col):
+def round_tf32(x, y):
+    """y = x rounded to nearest tf32 (the tf32 MMA itself truncates); 2-D f32 views, row strides allowed."""
+    require_device()
+    _chk2(x, "x"); _chk2(y, "y")
+    if x.shape != y.shape:
+        raise TvsError("round_tf32: shape mismatch")
+    _ck(load().tvs_round_tf32(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], y.data_ptr(), y.stride(0), _stream()), "tvs_round_tf32")
+
+
+def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col, round_tf32=False):
     """x: contiguous [B*H*W, C] (bf16 or f32) -> col [B*Ho*Wo, ld >= k*k*C] of the same dtype (tail zero-filled)."""
     require_device()
     _chk2(x, "x", (torch.float32, torch.bfloat16)); _chk2(col, "col", (x.dtype,))
@@ -467,7 +477,7 @@ def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col):
     if col.shape[0] != B * Ho * Wo or col.stride(0) != col.shape[1]:
         raise TvsError("im2col: col must be a dense [B*Ho*Wo, ld] matrix")
     _ck(load().tvs_im2col_nhwc(x.data_ptr(), x.element_size(), B, H, W, C, ksize, stride, pad, col.data_ptr(), col.shape[1],
-                               _stream()), "tvs_im2col_nhwc")
+                               int(round_tf32), _stream()), "tvs_im2col_nhwc")
 
 
 def col2im_nhwc(dcol, B, H, W, Ccol, Cx, ksize, dx, relu_mask=None):

@@ -26,7 +26,19 @@ static inline unsigned grid_for(long long total, int threads, int cap_blocks = 1
 // im2col: col[(b,oy,ox), (ky,kx,c)] = x[b, oy*s - p + ky, ox*s - p + kx, c]  (0 outside), tail columns zero.
 // Elements are moved as opaque V-sized vectors (V = 16/8/4/2 bytes), so one kernel serves bf16 and f32 operands.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename V>
+// kind::tf32 MMAs TRUNCATE their fp32 operands to 10 mantissa bits (measured: a systematic -3.4e-4 relative bias per
+// GEMM, which compounds through ~60 layers); operands are therefore rounded to nearest on their way into a GEMM.
+__device__ __forceinline__ uint32_t rn_tf32(uint32_t bits) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__uint_as_float(bits)));
+    return r;
+}
+__device__ __forceinline__ void round_words(uint4& v) { v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w); }
+__device__ __forceinline__ void round_words(uint2& v) { v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); }
+__device__ __forceinline__ void round_words(uint32_t& v) { v = rn_tf32(v); }
+__device__ __forceinline__ void round_words(uint16_t&) {}
+
+template <typename V, bool ROUND>
 __global__ void __launch_bounds__(256) im2col_kernel(const V* __restrict__ x, V* __restrict__ col, int H, int W, int Cv, int Ho, int Wo, int ks,
                                                      int stride, int pad, long long ldcol_v, int Kv, long long total) {
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -44,6 +56,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const V* __restrict__ x, V*
             const int oy = r / Wo, ox = r - oy * Wo;
             const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
             if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((b * H + iy) * W + ix) * Cv + cv];
+            if (ROUND) round_words(v);
         }
         col[idx] = v;
     }
@@ -82,6 +95,19 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
             acc.z = m.z > 0.f ? acc.z : 0.f; acc.w = m.w > 0.f ? acc.w : 0.f;
         }
         *reinterpret_cast<float4*>(dx + pix * ld_dx + c) = acc;
+    }
+}
+
+// y = round-to-nearest tf32 of x, [M, C] views with row strides
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float* __restrict__ x, long long ld_x, float* __restrict__ y, long long ld_y, int C4,
+                                                         long long total) {
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = idx / C4;
+        const int c = static_cast<int>(idx - m * C4) * 4;
+        uint4 v = *reinterpret_cast<const uint4*>(x + m * ld_x + c);
+        round_words(v);
+        *reinterpret_cast<uint4*>(y + m * ld_y + c) = v;
     }
 }
 
@@ -619,8 +645,9 @@ using namespace tvs;
 #define TVS_API extern "C" __attribute__((visibility("default")))
 
 TVS_API int tvs_im2col_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t stride,
-                            int32_t pad, void* col, int64_t ldcol, void* stream) {
+                            int32_t pad, void* col, int64_t ldcol, int32_t round_tf32, void* stream) {
     TVS_REQUIRE(x && col && (elem_bytes == 2 || elem_bytes == 4), "tvs_im2col_nhwc: bad pointers / elem_bytes");
+    TVS_REQUIRE(!round_tf32 || elem_bytes == 4, "tvs_im2col_nhwc: round_tf32 needs f32 elements");
     TVS_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && ksize >= 1 && stride >= 1 && pad >= 0, "tvs_im2col_nhwc: bad geometry");
     const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
     const long long K = static_cast<long long>(ksize) * ksize * C;
@@ -635,9 +662,14 @@ TVS_API int tvs_im2col_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_
     {                                                                                                                        \
         const int vb = static_cast<int>(sizeof(V));                                                                          \
         const long long total = rows * (lb / vb);                                                                            \
-        im2col_kernel<V><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const V*>(x), static_cast<V*>(col), H, W,          \
-                                                               static_cast<int>(cb / vb), Ho, Wo, ksize, stride, pad, lb / vb, \
-                                                               static_cast<int>(K * elem_bytes / vb), total);                 \
+        if (round_tf32)                                                                                                      \
+            im2col_kernel<V, true><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const V*>(x), static_cast<V*>(col), H, W, \
+                                                                         static_cast<int>(cb / vb), Ho, Wo, ksize, stride, pad, \
+                                                                         lb / vb, static_cast<int>(K * elem_bytes / vb), total); \
+        else                                                                                                                 \
+            im2col_kernel<V, false><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const V*>(x), static_cast<V*>(col), H, W, \
+                                                                          static_cast<int>(cb / vb), Ho, Wo, ksize, stride, pad, \
+                                                                          lb / vb, static_cast<int>(K * elem_bytes / vb), total); \
     }
     if (al(16)) TVS_IM2COL(uint4)
     else if (al(8)) TVS_IM2COL(uint2)
@@ -656,6 +688,13 @@ TVS_API int tvs_col2im_nhwc(const float* dcol, int64_t ldcol, int32_t B, int32_t
     col2im_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, ldcol, H, W, Ccol, Cx, ksize, relu_mask, ld_mask, dx,
                                                                                        ld_dx, total);
     return check_launch("col2im_kernel");
+}
+
+TVS_API int tvs_round_tf32(const float* x, int64_t ld_x, int64_t M, int32_t C, float* y, int64_t ld_y, void* stream) {
+    TVS_REQUIRE(x && y && C % 4 == 0 && ld_x % 4 == 0 && ld_y % 4 == 0, "tvs_round_tf32: C and strides must be multiples of 4");
+    const long long total = M * (C / 4);
+    round_tf32_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld_x, y, ld_y, C / 4, total);
+    return check_launch("round_tf32_kernel");
 }
 
 TVS_API int tvs_relu_mask(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int64_t M, int32_t C, float* out, int64_t ld_out,

@@ -43,6 +43,21 @@ def _f(w: torch.Tensor) -> torch.Tensor:
     return w.detach().to(F32).contiguous()
 
 
+def tf32_rn(w: torch.Tensor) -> torch.Tensor:
+    """fp32 rounded to NEAREST tf32 (10-bit mantissa, ties away).  The kind::tf32 MMA truncates its operands, which is
+    a systematic relative bias of about -3.4e-4 per GEMM; frozen weights are rounded once here, activations by
+    ``rn_act`` / the im2col kernel."""
+    w = w.detach().to(F32).contiguous()
+    return ((w.view(torch.int32) + 0x1000) & ~0x1FFF).view(F32)
+
+
+def rn_act(a: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest-tf32 copy of a 2-D fp32 GEMM operand (tvs_round_tf32)."""
+    out = torch.empty(tuple(a.shape), dtype=F32, device=a.device)
+    abi.round_tf32(a, out)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # weight packing
 # ------------------------------------------------------------------------------------------------------------------
@@ -76,8 +91,9 @@ class PackedLayer:
         if attn32 and tf32:
             self.wqkv_t32 = _f(wqkv.t())
         if tf32:
-            self.wqkv32, self.wo32 = _f(wqkv), _f(sa.out_proj.weight)
-            self.w1_32, self.w2_32 = _f(mlp.fc1.weight), _f(mlp.fc2.weight)
+            pack = tf32_rn if self.attn32 else _f      # attn32 (CRIS) layers round every forward operand to nearest
+            self.wqkv32, self.wo32 = pack(wqkv), pack(sa.out_proj.weight)
+            self.w1_32, self.w2_32 = pack(mlp.fc1.weight), pack(mlp.fc2.weight)
             self.wo_t32 = _f(sa.out_proj.weight.t())
             self.w1_t32, self.w2_t32 = _f(mlp.fc1.weight.t()), _f(mlp.fc2.weight.t())
 
@@ -175,9 +191,10 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
     abi.layernorm_fwd(x, pk.g1, pk.be1, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean1, rstd=rstd1)
     lse = _e((B, pk.heads, S), F32, x)
+    rn = rn_act if pk.attn32 else (lambda t: t)
     if pk.attn32:
         qkv = _e((M, 3 * D), F32, x)
-        abi.gemm(ln, pk.wqkv32, bias=pk.bqkv, out_f32=qkv)
+        abi.gemm(rn(ln), pk.wqkv32, bias=pk.bqkv, out_f32=qkv)
         att = att32 = _e((M, D), F32, x)
         abi.cross_attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], key_mask, B, S, S, pk.heads, pk.hd, att32, lse, causal=causal)
     else:
@@ -187,15 +204,15 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
         att32 = _e((M, D), F32, x) if hi else None
         abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, causal, key_mask, att, lse, out_f32=att32)
     x1 = _e((M, D), F32, x)
-    abi.gemm(att32 if hi else att, pk.wo32 if hi else pk.wo, bias=pk.bo, residual=x, out_f32=x1)
+    abi.gemm(rn(att32) if hi else att, pk.wo32 if hi else pk.wo, bias=pk.bo, residual=x, out_f32=x1)
     mean2, rstd2 = _e((M,), F32, x), _e((M,), F32, x)
     abi.layernorm_fwd(x1, pk.g2, pk.be2, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean2, rstd=rstd2)
     u = _e((M, F), BF16, x)
     a = _e((M, F), adt, x)
-    abi.gemm(ln, pk.w1_32 if hi else pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_f32=a if hi else None,
+    abi.gemm(rn(ln), pk.w1_32 if hi else pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_f32=a if hi else None,
              out_bf16=None if hi else a, act=abi.ACT_QGELU)
     x2 = _e((M, D), F32, x)
-    abi.gemm(a, pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2)
+    abi.gemm(rn(a), pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2)
     sv = Saved(x, mean1, rstd1, qkv, att, lse, x1, mean2, rstd2, u) if save else None
     return x2, sv
 

@@ -21,7 +21,7 @@ from types import SimpleNamespace
 import torch
 
 from . import abi
-from .engine import BF16, F32, PackedLayer, _e, encoder_layer_bwd, encoder_layer_fwd
+from .engine import BF16, F32, PackedLayer, _e, encoder_layer_bwd, encoder_layer_fwd, rn_act, tf32_rn
 
 BN_EPS = 1e-5
 LN_EPS = 1e-5
@@ -57,9 +57,9 @@ class ConvOp:
         self.K, self.Kp = k * k * cin, _up8(k * k * cin)
         wp = torch.zeros((cout, self.Kp), dtype=F32, device=w.device)
         wp[:, : self.K] = w2
-        self.w = wp.to(dtype).contiguous()
+        self.w = tf32_rn(wp) if dtype == F32 else wp.to(dtype).contiguous()     # forward operand: rounded to nearest tf32
         self.bias = b.contiguous()
-        self.w_t = wp.t().contiguous() if dgrad else None      # dgrad runs in fp32 / tf32
+        self.w_t = wp.t().contiguous() if dgrad else None      # dgrad: tf32 truncation is far inside the gradient tolerance
 
 
 class LinearOp:
@@ -74,7 +74,7 @@ class LinearOp:
             w = torch.cat((w, w.new_zeros((self.n_pad - self.n, w.shape[1]))))
             if b is not None:
                 b = torch.cat((b.detach().to(F32), w.new_zeros(self.n_pad - self.n)))
-        self.w = w.to(dtype).contiguous()
+        self.w = tf32_rn(w) if dtype == F32 else w.to(dtype).contiguous()
         self.bias = None if b is None else b.detach().to(F32).contiguous()
         self.w_t = w.t().contiguous() if dgrad else None
 
@@ -292,12 +292,13 @@ class PackedCris:
 # ------------------------------------------------------------------------------------------------------------------
 def _conv_nograd(op: ConvOp, x, B, H, W, *, residual=None, act=None):
     """x: [B*H*W, Cin] in op.w.dtype -> ([B*Ho*Wo, Cout] same dtype, Ho, Wo)."""
+    f32 = x.dtype == F32
     if op.k == 1 and op.stride == 1:
-        A, Ho, Wo = x, H, W
+        A, Ho, Wo = (rn_act(x) if f32 else x), H, W
     else:
         Ho, Wo = (H + 2 * op.pad - op.k) // op.stride + 1, (W + 2 * op.pad - op.k) // op.stride + 1
         A = _e((B * Ho * Wo, op.Kp), x.dtype, x)
-        abi.im2col_nhwc(x, B, H, W, op.cin, op.k, op.stride, op.pad, A)
+        abi.im2col_nhwc(x, B, H, W, op.cin, op.k, op.stride, op.pad, A, round_tf32=f32)
     y = _e((B * Ho * Wo, op.cout), x.dtype, x)
     if act is None:
         act = abi.ACT_RELU if op.relu else abi.ACT_NONE
@@ -341,12 +342,12 @@ def encode_image(pk: PackedCris, image):
     res, _, _ = _conv_nograd(pk.ap_connect, x, B, H4, W4)
     t = (x4.view(B, S, Ce) + pk.attnpool_pos(H4, W4)).to(dt).view(B * S, Ce)
     qkv = _e((B * S, 3 * Ce), BF16, t)
-    abi.gemm(t, pk.ap_qkv.w, bias=pk.ap_qkv.bias, out_bf16=qkv)
+    abi.gemm(rn_act(t) if dt == F32 else t, pk.ap_qkv.w, bias=pk.ap_qkv.bias, out_bf16=qkv)
     att, att32 = _e((B * S, Ce), BF16, t), _e((B * S, Ce), F32, t)
     lse = _e((B, pk.rn_heads, S), F32, t)
     abi.attn_fwd(qkv, B, S, pk.rn_heads, Ce // pk.rn_heads, False, None, att, lse, out_f32=att32)
     v5 = _e((B * S, pk.embed_dim), F32, t)
-    abi.gemm(att32 if dt == F32 else att, pk.ap_c.w, bias=pk.ap_c.bias, residual=res.to(F32), out_f32=v5, act=abi.ACT_RES_RELU)
+    abi.gemm(rn_act(att32) if dt == F32 else att, pk.ap_c.w, bias=pk.ap_c.bias, residual=res.to(F32), out_f32=v5, act=abi.ACT_RES_RELU)
     return outs[2], outs[3], (v5, H4, W4)
 
 
@@ -360,10 +361,10 @@ class ConvFn(torch.autograd.Function):
     def forward(ctx, x, op: ConvOp, B, H, W):
         x = x.contiguous()
         if op.k == 1:
-            A = x
+            A = rn_act(x)
         else:
             A = _e((B * H * W, op.Kp), F32, x)
-            abi.im2col_nhwc(x, B, H, W, op.cin, op.k, 1, op.pad, A)
+            abi.im2col_nhwc(x, B, H, W, op.cin, op.k, 1, op.pad, A, round_tf32=True)
         y = _e((B * H * W, op.cout), F32, x)
         abi.gemm(A, op.w, bias=op.bias, out_f32=y, act=abi.ACT_RELU if op.relu else abi.ACT_NONE)
         ctx.op, ctx.geom = op, (B, H, W)
@@ -406,7 +407,7 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, op: LinearOp, relu: bool):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         y = _e((x2.shape[0], op.n_pad), F32, x)
-        abi.gemm(x2, op.w, bias=op.bias, out_f32=y, act=abi.ACT_RELU if relu else abi.ACT_NONE)
+        abi.gemm(rn_act(x2), op.w, bias=op.bias, out_f32=y, act=abi.ACT_RELU if relu else abi.ACT_NONE)
         ctx.op, ctx.relu, ctx.shape = op, relu, x.shape
         ctx.save_for_backward(y if relu else None)
         return y[:, : op.n].view(*x.shape[:-1], op.n) if op.n == op.n_pad else y[:, : op.n].reshape(*x.shape[:-1], op.n)
@@ -487,7 +488,7 @@ class SelfAttnFn(torch.autograd.Function):
     def forward(ctx, xqk, xv, m, B, S):
         M, D = B * S, m.D
         ctx.shapes = (xqk.shape, xv.shape)
-        xqk, xv = xqk.reshape(M, D).contiguous(), xv.reshape(M, D).contiguous()
+        xqk, xv = rn_act(xqk.reshape(M, D).contiguous()), rn_act(xv.reshape(M, D).contiguous())
         qkv = _e((M, 3 * D), BF16, xqk)
         abi.gemm(xqk, m.qk.w, bias=m.qk.bias, out_bf16=qkv[:, : 2 * D])
         abi.gemm(xv, m.v.w, bias=m.v.bias, out_bf16=qkv[:, 2 * D:])
@@ -495,7 +496,7 @@ class SelfAttnFn(torch.autograd.Function):
         lse = _e((B, m.heads, S), F32, xqk)
         abi.attn_fwd(qkv, B, S, m.heads, m.hd, False, None, att, lse, out_f32=att32)
         out = _e((M, D), F32, xqk)
-        abi.gemm(att32, m.o.w, bias=m.o.bias, out_f32=out)
+        abi.gemm(rn_act(att32), m.o.w, bias=m.o.bias, out_f32=out)
         ctx.m, ctx.geom = m, (B, S)
         ctx.save_for_backward(qkv, att, lse)
         return out
@@ -524,7 +525,7 @@ class CrossAttnFn(torch.autograd.Function):
     def forward(ctx, xq, xk, xv, key_mask, m, B, Sq, Sk):
         D = m.D
         ctx.shapes = (xq.shape, xk.shape, xv.shape)
-        xq, xk, xv = xq.reshape(B * Sq, D).contiguous(), xk.reshape(B * Sk, D).contiguous(), xv.reshape(B * Sk, D).contiguous()
+        xq, xk, xv = (rn_act(t.reshape(-1, D).contiguous()) for t in (xq, xk, xv))
         q, kv = _e((B * Sq, D), F32, xq), _e((B * Sk, 2 * D), F32, xq)
         abi.gemm(xq, m.q.w, bias=m.q.bias, out_f32=q)
         abi.gemm(xk, m.k.w, bias=m.k.bias, out_f32=kv[:, :D])
@@ -533,7 +534,7 @@ class CrossAttnFn(torch.autograd.Function):
         lse = _e((B, m.heads, Sq), F32, xq)
         abi.cross_attn_fwd(q, kv[:, :D], kv[:, D:], key_mask, B, Sq, Sk, m.heads, m.hd, att, lse)
         out = _e((B * Sq, D), F32, xq)
-        abi.gemm(att, m.o.w, bias=m.o.bias, out_f32=out)
+        abi.gemm(rn_act(att), m.o.w, bias=m.o.bias, out_f32=out)
         ctx.m, ctx.geom, ctx.key_mask = m, (B, Sq, Sk), key_mask
         ctx.save_for_backward(q, kv, att, lse)
         return out
@@ -611,10 +612,10 @@ class TailFn(torch.autograd.Function):
         fq = fq.contiguous()
         w0m = w0.detach().to(F32).reshape(mid, C).contiguous()
         midf = _e((B * G * G, mid), F32, pred)
-        abi.gemm(fq, w0m, out_f32=midf)
+        abi.gemm(rn_act(fq), tf32_rn(w0m), out_f32=midf)
         wa = w2.detach().to(F32).reshape(mid, KK).t().contiguous()        # [KK, mid]
         addmap = torch.zeros((B * G * G, _up8(KK)), dtype=F32, device=pred.device)
-        abi.gemm(midf, wa, out_f32=addmap[:, :KK])
+        abi.gemm(rn_act(midf), tf32_rn(wa), out_f32=addmap[:, :KK])
         add_out = _e((B, img, img), F32, pred)
         r = ratio.detach().to(F32).reshape(1).contiguous()
         abi.head_fwd(big, addmap[:, :KK], zero_b, b2.detach().to(F32).contiguous(), r, abi.BLEND_RATIO, B, G, P, ks, logits, add_out)
@@ -685,7 +686,7 @@ class CrisTextFn(torch.autograd.Function):
         rows = torch.arange(B, device=x.device) * S + pool_pos.to(x.device)
         pooled = words.index_select(0, rows)
         state = _e((B, pk.t_proj.w.shape[0]), F32, x)
-        abi.gemm(pooled, pk.t_proj.w, out_f32=state)
+        abi.gemm(rn_act(pooled), pk.t_proj.w, out_f32=state)
         ctx.pk, ctx.saved, ctx.km = pk, saved, key_mask
         ctx.fin = (x, mean_f, rstd_f, rows)
         ctx.dims = (B, S, D, depth, n_ctx, tuple(co.shape))
