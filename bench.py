@@ -97,6 +97,46 @@ def build_module(device, seed=0):
     return module, opt
 
 
+CRIS_WORKLOAD = "CRIS CLIP-RN50 + CoCoOp (per-image meta-net context, depth 1, 4 ctx), 416x416, batch {B}/GPU, 1 binary class, text L=8"
+
+
+def build_module_cris(device, seed=0):
+    """Random-init CRIS (CLIP-RN50 geometry of RN50.pt, configs/model/cocoop/cris.yaml) + CoCoOp learner."""
+    from functools import partial
+    from types import SimpleNamespace
+
+    from tunevlseg_b200.losses import DiceCELoss
+    from tunevlseg_b200.models.components.cris_model import CLIP
+    from tunevlseg_b200.models.core_models.coop import COOPCRIS
+    from tunevlseg_b200.models.core_models.coop.context_learner import CoCoOpContextLearner
+    from tunevlseg_b200.models.image_text_mask_module import ImageTextMaskModule
+    from tunevlseg_b200.optim import FusedAdamW
+
+    torch.manual_seed(seed)
+    clip = CLIP(1024, 224, (3, 4, 6, 3), 64, 77, 49408, 512, 8, 12)
+    with torch.no_grad():                      # default BN statistics are (0, 1): make every folded term non-trivial
+        for name, buf in clip.named_buffers():
+            if name.endswith("running_mean"):
+                buf.normal_(0, 0.1)
+            elif name.endswith("running_var"):
+                buf.uniform_(0.8, 1.2)
+    tok = lambda text, **kw: SimpleNamespace(input_ids=torch.tensor([[320, 1125, 539, 320]]))      # "a photo of a"  # noqa: E731
+    net = COOPCRIS(
+        model_cfg=dict(clip_pretrain=clip.state_dict(), fpn_in=[512, 1024, 1024], fpn_out=[256, 512, 1024], vis_dim=512, word_dim=1024,
+                       num_layers=3, num_head=8, dim_ffn=2048, dropout=0.2, return_intermediate=False, img_size=416, freeze_encoder=True,
+                       cris_pretrain=None),
+        context_learner=partial(CoCoOpContextLearner, norm_image_features=False, prompt_depth=1, use_unified_projection=False,
+                                intermediate_dim=64, use_proj_norm=True, use_lora_proj=False, num_context=4,
+                                context_initializer="a photo of a", tokenizer=tok),
+        freeze_all=True, no_freeze_last_layer=False, use_new_last_layer=True, new_last_layer_kernel_size=5, residual_ratio=0.5)
+    module = ImageTextMaskModule(net=net, loss_fn=DiceCELoss(sigmoid=True, lambda_dice=1, lambda_ce=0.2),
+                                 optimizer=partial(FusedAdamW, lr=2e-5, weight_decay=0.0), scheduler=None, compile=False,
+                                 task="binary", threshold=0.5, weight_decay=0.0)
+    module = module.to(device)
+    module.setup("fit")
+    return module, module.configure_optimizers()["optimizer"]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -134,6 +174,36 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU oracle step (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------------------------
+def oracle_step_factory_cris(B):
+    from oracle import cris as OCR
+    from oracle import learners as OL
+    from oracle import loss_metrics as OLM
+
+    spec = OCR.CrisSpec()
+    w = OCR.init_weights(spec, seed=0)
+    g = torch.Generator().manual_seed(1)
+    params = {"context_vectors": (torch.randn(1, 4, 512, generator=g) * 0.02).requires_grad_(True),
+              "projection_layers.0.0.weight": (torch.randn(64, 1024, generator=g) * 0.04).requires_grad_(True),
+              "projection_layers.0.0.bias": torch.zeros(64, requires_grad=True),
+              "projection_layers.0.2.weight": (torch.randn(512, 64, generator=g) * 0.1).requires_grad_(True),
+              "projection_layers.0.3.weight": torch.ones(512, requires_grad=True), "projection_layers.0.3.bias": torch.zeros(512, requires_grad=True)}
+    st = OL.LearnerState(kind="cocoop", prompt_depth=1, num_context=4, params=params, proj_style="mlp")
+    head = {k: v.requires_grad_(True) for k, v in OCR.init_head(spec).items()}
+    opt = torch.optim.AdamW(list(params.values()) + list(head.values()), lr=2e-5, weight_decay=0.0)
+    batch = synth_batch(B, size=416)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        logits = OCR.net_forward(w, spec, st, head, batch["input_ids"], batch["attention_mask"], batch["image"])
+        loss = OLM.dice_ce_loss(logits, batch["mask"])
+        OLM.metric_counts(torch.sigmoid(logits.detach()), batch["mask"])
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step
+
+
 def oracle_step_factory(B):
     from oracle import clipseg as OC
     from oracle import learners as OL
@@ -167,9 +237,9 @@ def oracle_step_factory(B):
     return step
 
 
-def time_oracle(B, steps, warmup):
+def time_oracle(B, steps, warmup, workload="maple"):
     torch.set_num_threads(os.cpu_count() or 1)
-    step = oracle_step_factory(B)
+    step = oracle_step_factory_cris(B) if workload == "cris_cocoop" else oracle_step_factory(B)
     for _ in range(warmup):
         step()
     ts = []
@@ -186,12 +256,13 @@ def run_reference(args, rank):
     if rank != 0:
         return
     B = args.ref_batch
-    v, ms, cores = time_oracle(B, max(1, args.steps), min(args.warmup, 1))
+    cris = args.workload == "cris_cocoop"
+    v, ms, cores = time_oracle(B, max(1, args.steps), min(args.warmup, 1), args.workload)
     print(json.dumps({
-        "impl": "reference", "metric": "train img/s CLIPSeg+MaPLe 352x352", "value": round(v, 3), "unit": "img/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "train img/s CRIS+CoCoOp 416x416" if cris else "train img/s CLIPSeg+MaPLe 352x352", "value": round(v, 3), "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (seed 12345), random-init weights",
-        "config": {"workload": WORKLOAD.format(B=B), "note": "bounded sample: batch %d per step on the host cores" % B},
+        "config": {"workload": (CRIS_WORKLOAD if cris else WORKLOAD).format(B=B), "note": "bounded sample: batch %d per step on the host cores" % B},
         "cpu_baseline": {"value": round(v, 3), "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full train steps (fwd+loss+metrics+bwd+AdamW) at batch {B}"},
         "e2e": {"value": round(v, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,6 +281,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="also print the per-kernel share table to stderr")
     ap.add_argument("--no-graph", action="store_true", help="drive every kernel launch from Python instead of one CUDA graph")
+    ap.add_argument("--workload", default="maple", choices=["maple", "cris_cocoop"],
+                    help="maple = BASELINE.json's metric (default); cris_cocoop = configs[3], an extra line for the CRIS path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -230,9 +303,10 @@ def main():
         dist.init_process_group("nccl", device_id=device, timeout=timedelta(seconds=180))
     abi.require_device()
     B = args.batch
-    module, opt = build_module(device, seed=0)
+    cris = args.workload == "cris_cocoop"
+    module, opt = build_module_cris(device, seed=0) if cris else build_module(device, seed=0)
     module.train()
-    host = synth_batch(B, seed=12345 + rank, pinned=True)
+    host = synth_batch(B, seed=12345 + rank, pinned=True, size=416 if cris else 352)
     resident = {k: v.to(device) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -345,7 +419,7 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        v, ms, cores = time_oracle(args.ref_batch, 3, 1)
+        v, ms, cores = time_oracle(args.ref_batch, 3, 1, args.workload)
         cpu = {"value": round(v, 3), "unit": "img/s", "cores": cores, "kind": "port",
                "sample": f"3 full train steps of the fp32 CPU oracle at batch {args.ref_batch} (median {ms:.0f} ms/step)"}
 
@@ -354,15 +428,17 @@ def main():
         e2e = world * B / (ms_e2e * 1e-3)
         pk = peaks()
         out = {
-            "metric": "train img/s CLIPSeg+MaPLe 352x352", "value": round(value, 1), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "metric": "train img/s CRIS+CoCoOp 416x416" if cris else "train img/s CLIPSeg+MaPLe 352x352", "value": round(value, 1),
+            "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic (seed 12345), random-init weights",
-            "config": {"workload": WORKLOAD.format(B=B), "global_batch": world * B, "parallelism": f"dp{world}",
+            "dtype": "tf32" if cris else "bf16", "data": "synthetic (seed 12345), random-init weights",
+            "config": {"workload": (CRIS_WORKLOAD if cris else WORKLOAD).format(B=B), "global_batch": world * B, "parallelism": f"dp{world}",
                        "cuda_graph": use_graph,
                        "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                       "precision": "bf16 tcgen05 GEMMs + fp32 residual stream in the vision tower; tf32 GEMMs in text tower/decoder"},
-            "model_tflops_per_gpu": round(value / world * GFLOP_PER_IMG / 1e3, 1),
-            "model_flops_frac_of_peak": round(value / world * GFLOP_PER_IMG / 1e3 / pk["tf_sustained"], 4),
+                       "precision": ("fp32 activations, kind::tf32 tcgen05 GEMMs with round-to-nearest operands, fp32 text attention" if cris else
+                                     "bf16 tcgen05 GEMMs + fp32 residual stream in the vision tower; tf32 GEMMs in text tower/decoder")},
+            "model_tflops_per_gpu": None if cris else round(value / world * GFLOP_PER_IMG / 1e3, 1),
+            "model_flops_frac_of_peak": None if cris else round(value / world * GFLOP_PER_IMG / 1e3 / pk["tf_sustained"], 4),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": round(e2e, 1), "unit": "img/s", "ms_per_step": round(ms_e2e, 3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks}

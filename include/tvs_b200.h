@@ -68,7 +68,8 @@ typedef struct tvs_gemm_args {
     int32_t ab_dtype;                      /* TVS_AB_BF16: A, W are bf16 (kind::f16).  TVS_AB_TF32: A, W are f32 and the
                                               MMA runs kind::tf32 (10-bit mantissa) - used for the small text tower and
                                               decoder, whose rounding dominates the logit error; K, lda, ldw % 4 == 0 */
-    int32_t reserved;
+    int32_t reserved;                      /* flags; bit 0: round out_f32 to nearest tf32 (cvt.rna) - for outputs that only
+                                              feed further TVS_AB_TF32 GEMMs, whose MMA truncates its operands */
 } tvs_gemm_args;
 
 int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);
@@ -233,6 +234,7 @@ int tvs_col2im_nhwc(const float* dcol, int64_t ldcol, int32_t B, int32_t H, int3
 int tvs_relu_mask(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int64_t M, int32_t C, float* out,
                   int64_t ld_out, void* stream);
 /* 2x2 / stride-2 average pooling (clip.py:32,47,222 nn.AvgPool2d(2); layers.py:432 F.avg_pool2d) */
+/* is_bf16: bit 0 = bf16 elements (else f32); bit 1 = round the f32 result to nearest tf32 (feeds a tf32 GEMM) */
 int tvs_avgpool2_nhwc(const void* x, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* y,
                       int64_t ld_out, void* stream);
 /* bilinear x2, align_corners=False (layers.py:85-88 nn.Upsample, :427,:441 F.interpolate); f32.

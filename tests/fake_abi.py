@@ -38,7 +38,7 @@ def round_tf32(x, y):
     y.copy_(_tf32_rn(x))
 
 
-def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0):
+def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False):
     assert A.dtype == W.dtype and A.dim() == 2 and W.dim() == 2 and A.shape[1] == W.shape[1], (A.shape, W.shape, A.dtype, W.dtype)
     assert A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] % (8 if A.dtype == BF16 else 4) == 0
     v = A.float() @ W.float().t() if A.dtype == BF16 else _tf32(A) @ _tf32(W).t()
@@ -63,7 +63,7 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     for o in (out_f32, out_bf16):
         if o is not None:
             assert o.shape == v.shape and o.stride(1) == 1
-            o.copy_(v)
+            o.copy_(_tf32_rn(v) if (round_out and o is out_f32) else v)
 
 
 def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None):
@@ -170,9 +170,9 @@ def relu_mask(dy, y, out):
     out.copy_(dy * (y > 0))
 
 
-def avgpool2_nhwc(x, B, H, W, C, y):
-    p = F.avg_pool2d(x.float().view(B, H, W, C).permute(0, 3, 1, 2), 2)
-    y.copy_(p.permute(0, 2, 3, 1).reshape(-1, C))
+def avgpool2_nhwc(x, B, H, W, C, y, round_tf32=False):
+    p = F.avg_pool2d(x.float().view(B, H, W, C).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).reshape(-1, C)
+    y.copy_(_tf32_rn(p) if round_tf32 else p)
 
 
 def upsample2x_fwd(x, B, H, W, C, y):

@@ -253,3 +253,43 @@ def test_cris_small_no_mask_long_prompt_and_plain_head():
 def test_cris_full_geometry(case):
     """CLIP-RN50 @ 416x416 (configs/model/coop/cris.yaml, cocoop/cris.yaml), batch 2."""
     _run_cris(case, CRIS_FULL, B=2, L=10, seed=41)
+
+
+def test_cris_train_step_graph_matches_eager():
+    """COOPCRIS inside the reference-shaped LightningModule: five AdamW steps lower the loss, and the whole-step CUDA
+    graph replays to the same parameters as the eagerly driven step."""
+    from functools import partial
+
+    from tunevlseg_b200.graph import GraphedTrainStep
+    from tunevlseg_b200.losses import DiceCELoss
+    from tunevlseg_b200.models.image_text_mask_module import ImageTextMaskModule
+    from tunevlseg_b200.optim import FusedAdamW
+
+    def make():
+        net = build_cris_net("cocoop", CRIS_SMALL, OCR.init_weights(CRIS_SMALL, seed=7), seed=3)
+        m = ImageTextMaskModule(net=net, loss_fn=DiceCELoss(sigmoid=True, lambda_dice=1, lambda_ce=0.2),
+                                optimizer=partial(FusedAdamW, lr=2e-3, weight_decay=0.0), scheduler=None, compile=False,
+                                task="binary", threshold=0.5, weight_decay=0.0).to("cuda")
+        m.setup("fit")
+        m.train()
+        return m, m.configure_optimizers()["optimizer"]
+
+    img, ids, am, mask = make_cris_batch(CRIS_SMALL, 4, 8, 12)
+    batch = {"image": img.cuda(), "mask": mask.cuda(), "input_ids": ids.cuda(), "attention_mask": am.cuda()}
+    m_e, o_e = make()
+    losses = []
+    for _ in range(5):
+        o_e.zero_grad()
+        loss = m_e.training_step(batch, 0)
+        loss.backward()
+        o_e.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    m_g, o_g = make()
+    step = GraphedTrainStep(m_g, o_g, batch, warmup=3)
+    l4, l5 = step(batch).item(), step(batch).item()
+    assert abs(l4 - losses[3]) <= 1e-4 and abs(l5 - losses[4]) <= 1e-4, (l4, l5, losses)
+    pe, pg = dict(m_e.named_parameters()), dict(m_g.named_parameters())
+    for k, p in pe.items():
+        if p.requires_grad:
+            assert torch.allclose(p, pg[k], rtol=1e-4, atol=1e-5), k

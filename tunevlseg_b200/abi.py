@@ -163,9 +163,9 @@ def _chk(t: torch.Tensor | None, dtype, name: str, dim2: bool = False) -> None:
 
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=ACT_NONE,
-         tile_n=0):
+         tile_n=0, round_out=False):
     """C[M,N] = epilogue(A[M,K] @ W[N,K]^T); see tvs_gemm_bf16 in include/tvs_b200.h.  2-D views with a row stride
-    are accepted (ld = stride(0))."""
+    are accepted (ld = stride(0)).  ``round_out``: out_f32 is rounded to nearest tf32 (it only feeds further tf32 GEMMs)."""
     require_device()
     if A.dtype != W.dtype or A.dtype not in (torch.bfloat16, torch.float32):
         raise TvsError(f"gemm: A and W must both be bf16 or both f32 (tf32 MMA), got {A.dtype} / {W.dtype}")
@@ -194,6 +194,7 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.aux_bf16, g.ldaux = _p(aux_bf16), (aux_bf16.stride(0) if aux_bf16 is not None else 0)
     g.act, g.tile_n = act, tile_n
     g.ab_dtype = 1 if A.dtype == torch.float32 else 0
+    g.reserved = 1 if round_out else 0
     _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
 
 
@@ -420,6 +421,13 @@ def _flops(name, args, kwargs) -> tuple[str, float]:
     if name == "attn_bwd":
         B, S, H, hd = args[4:8]
         return f"B{B}S{S}H{H}d{hd}", 10.0 * B * H * S * S * hd
+    if name in ("cross_attn_fwd", "cross_attn_bwd"):
+        i = 4 if name == "cross_attn_fwd" else 7
+        B, Sq, Sk, H = args[i:i + 4]
+        return f"B{B}Sq{Sq}Sk{Sk}H{H}", 0.0
+    if name in ("im2col_nhwc", "col2im_nhwc", "round_tf32", "relu_mask"):
+        t = args[-1] if name == "im2col_nhwc" else args[0]
+        return "x".join(str(d) for d in t.shape), 0.0
     return "", 0.0
 
 
@@ -497,13 +505,13 @@ def relu_mask(dy, y, out):
                              out.stride(0), _stream()), "tvs_relu_mask")
 
 
-def avgpool2_nhwc(x, B, H, W, C, y):
+def avgpool2_nhwc(x, B, H, W, C, y, round_tf32=False):
     require_device()
     _chk2(x, "x", (torch.float32, torch.bfloat16)); _chk2(y, "y", (x.dtype,))
     if not x.is_contiguous():
         raise TvsError("avgpool2: x must be contiguous")
-    _ck(load().tvs_avgpool2_nhwc(x.data_ptr(), int(x.dtype == torch.bfloat16), B, H, W, C, y.data_ptr(), y.stride(0), _stream()),
-        "tvs_avgpool2_nhwc")
+    _ck(load().tvs_avgpool2_nhwc(x.data_ptr(), int(x.dtype == torch.bfloat16) | (2 if round_tf32 else 0), B, H, W, C, y.data_ptr(),
+                                 y.stride(0), _stream()), "tvs_avgpool2_nhwc")
 
 
 def upsample2x_fwd(x, B, H, W, C, y):
@@ -574,3 +582,8 @@ def resample2d_bwd(dout, B, Hi, Wi, Ho, Wo, tab, tile, din):
     _ck(load().tvs_resample2d_bwd(dout.data_ptr(), int(dout.dtype == torch.bfloat16), B, Hi, Wi, Ho, Wo, tab["ty"].data_ptr(),
                                   tab["twy"].data_ptr(), tab["cy"].data_ptr(), tab["tx"].data_ptr(), tab["twx"].data_ptr(),
                                   tab["cx"].data_ptr(), tab["max_taps"], tile, din.data_ptr(), _stream()), "tvs_resample2d_bwd")
+
+
+for _n in ("round_tf32", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd", "cross_attn_fwd",
+           "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd"):
+    globals()[_n] = _wrap(globals()[_n], _n)

@@ -38,27 +38,39 @@ __device__ __forceinline__ void round_words(uint2& v) { v.x = rn_tf32(v.x); v.y 
 __device__ __forceinline__ void round_words(uint32_t& v) { v = rn_tf32(v); }
 __device__ __forceinline__ void round_words(uint16_t&) {}
 
+// Thread layout: 2^tpr_shift threads walk one output row (consecutive lanes -> consecutive 16-byte vectors, so both the
+// tap reads and the row writes are coalesced); the (tap, channel) position advances incrementally - no division in the
+// inner loop (the first version divided five times per vector and was instruction-bound at 1/3 of HBM speed).
 template <typename V, bool ROUND>
 __global__ void __launch_bounds__(256) im2col_kernel(const V* __restrict__ x, V* __restrict__ col, int H, int W, int Cv, int Ho, int Wo, int ks,
-                                                     int stride, int pad, long long ldcol_v, int Kv, long long total) {
-    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long row = idx / ldcol_v;
-        const int kv = static_cast<int>(idx - row * ldcol_v);
-        V v;
-        memset(&v, 0, sizeof(V));
-        if (kv < Kv) {
-            const int tap = kv / Cv, cv = kv - tap * Cv;
-            const int ky = tap / ks, kx = tap - ky * ks;
-            const int hw = Ho * Wo;
-            const long long b = row / hw;
-            const int r = static_cast<int>(row - b * hw);
-            const int oy = r / Wo, ox = r - oy * Wo;
-            const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((b * H + iy) * W + ix) * Cv + cv];
-            if (ROUND) round_words(v);
+                                                     int stride, int pad, int ldcol_v, int Kv, long long rows, int tpr_shift) {
+    const int tpr = 1 << tpr_shift, rpb = blockDim.x >> tpr_shift;
+    const int lane = threadIdx.x & (tpr - 1), rl = threadIdx.x >> tpr_shift;
+    const int hw = Ho * Wo;
+    const int tap0 = lane / Cv, cv0 = lane - tap0 * Cv, ky0 = tap0 / ks, kx0 = tap0 - ky0 * ks;
+    for (long long row = static_cast<long long>(blockIdx.x) * rpb + rl; row < rows; row += static_cast<long long>(gridDim.x) * rpb) {
+        const long long b = row / hw;
+        const int r = static_cast<int>(row - b * hw);
+        const int oy = r / Wo, ox = r - oy * Wo;
+        const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+        const V* xb = x + b * H * W * Cv;
+        V* crow = col + row * ldcol_v;
+        int cv = cv0, ky = ky0, kx = kx0;
+        for (int kv = lane; kv < ldcol_v; kv += tpr) {
+            V v;
+            memset(&v, 0, sizeof(V));
+            if (kv < Kv) {
+                const int iy = iy0 + ky, ix = ix0 + kx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = xb[(static_cast<long long>(iy) * W + ix) * Cv + cv];
+                if (ROUND) round_words(v);
+            }
+            crow[kv] = v;
+            cv += tpr;
+            while (cv >= Cv) {
+                cv -= Cv;
+                if (++kx == ks) { kx = 0; ++ky; }
+            }
         }
-        col[idx] = v;
     }
 }
 
@@ -128,7 +140,7 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const float* __restrict_
 // 2x2 / stride-2 average pooling, NHWC.  T = float (4 channels / thread) or bf16 (8 channels / thread).
 template <bool BF16>
 __global__ void __launch_bounds__(256) avgpool2_kernel(const void* __restrict__ xin, void* __restrict__ yout, int H, int W, int C, long long ld_out,
-                                                       long long total) {
+                                                       long long total, int round_out) {
     constexpr int VEC = BF16 ? 8 : 4;
     const int cvn = C / VEC, Ho = H >> 1, Wo = W >> 1;
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -162,8 +174,10 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(const void* __restrict__ 
             o.z = pack_bf16x2(acc[4 % VEC] * 0.25f, acc[5 % VEC] * 0.25f); o.w = pack_bf16x2(acc[6 % VEC] * 0.25f, acc[7 % VEC] * 0.25f);
             *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(yout) + opix * ld_out + c) = o;
         } else {
-            *reinterpret_cast<float4*>(static_cast<float*>(yout) + opix * ld_out + c) =
-                make_float4(acc[0] * 0.25f, acc[1] * 0.25f, acc[2] * 0.25f, acc[3] * 0.25f);
+            uint4 o = make_uint4(__float_as_uint(acc[0] * 0.25f), __float_as_uint(acc[1] * 0.25f), __float_as_uint(acc[2] * 0.25f),
+                                 __float_as_uint(acc[3] * 0.25f));
+            if (round_out) round_words(o);
+            *reinterpret_cast<uint4*>(static_cast<float*>(yout) + opix * ld_out + c) = o;
         }
     }
 }
@@ -272,6 +286,15 @@ __device__ __forceinline__ void xa_load_kv(const float* __restrict__ k, const fl
     }
 }
 
+// Four lanes (a quad) share one query row, 16 of the 64 head dims each: 48 live registers instead of 192 (the
+// one-thread-per-row version spilled), dot products finish with two quad shuffles.
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+constexpr int XA_QPB = XA_THREADS / 4;      // query rows per block
+
 __global__ void __launch_bounds__(XA_THREADS) cross_attn_fwd_kernel(const float* __restrict__ q, long long ld_q, const float* __restrict__ k,
                                                                     const float* __restrict__ v, long long ld_kv, const uint8_t* __restrict__ key_mask,
                                                                     int Sq, int Sk, int causal, float* __restrict__ out, long long ld_o,
@@ -283,35 +306,39 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attn_fwd_kernel(const float*
     xa_load_kv(k, v, ld_kv, Sk, b, h, sk, sv);
     for (int j = threadIdx.x; j < Sk; j += blockDim.x) sm[j] = key_mask ? key_mask[b * Sk + j] : 1;
     __syncthreads();
-    const int i = blockIdx.x * XA_THREADS + threadIdx.x;
-    if (i >= Sq) return;
-    const long long row = static_cast<long long>(b) * Sq + i;
-    float qr[XA_HD], acc[XA_HD];
+    const int part = threadIdx.x & 3;
+    const int i = blockIdx.x * XA_QPB + (threadIdx.x >> 2);
+    const bool live = i < Sq;                      // dead quads still take part in the shuffles
+    const long long row = static_cast<long long>(b) * Sq + (live ? i : 0);
+    float qr[16], acc[16];
 #pragma unroll
-    for (int d = 0; d < XA_HD; d += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(q + row * ld_q + h * XA_HD + d);
+    for (int d = 0; d < 16; d += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(q + row * ld_q + h * XA_HD + part * 16 + d);
         qr[d] = t.x; qr[d + 1] = t.y; qr[d + 2] = t.z; qr[d + 3] = t.w;
         acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
     }
     float mx = -INFINITY, sum = 0.f;
     const int jend = causal ? min(Sk, i + 1) : Sk;
-    for (int j = 0; j < jend; ++j) {
-        if (!sm[j]) continue;
+    for (int j = 0; j < Sk; ++j) {
         float s = 0.f;
 #pragma unroll
-        for (int d = 0; d < XA_HD; ++d) s = fmaf(qr[d], sk[j][d], s);
+        for (int d = 0; d < 16; ++d) s = fmaf(qr[d], sk[j][part * 16 + d], s);
+        s = quad_sum(s);
+        if (j >= jend || !sm[j]) continue;          // uniform within the quad
         const float nm = fmaxf(mx, s);
         const float corr = __expf(mx - nm), p = __expf(s - nm);
         sum = sum * corr + p;
 #pragma unroll
-        for (int d = 0; d < XA_HD; ++d) acc[d] = fmaf(acc[d], corr, p * sv[j][d]);
+        for (int d = 0; d < 16; ++d) acc[d] = fmaf(acc[d], corr, p * sv[j][part * 16 + d]);
         mx = nm;
     }
+    if (!live) return;
     const float inv = 1.f / sum;
 #pragma unroll
-    for (int d = 0; d < XA_HD; d += 4)
-        *reinterpret_cast<float4*>(out + row * ld_o + h * XA_HD + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
-    lse[(static_cast<long long>(b) * H + h) * Sq + i] = mx + __logf(sum);
+    for (int d = 0; d < 16; d += 4)
+        *reinterpret_cast<float4*>(out + row * ld_o + h * XA_HD + part * 16 + d) =
+            make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+    if (part == 0) lse[(static_cast<long long>(b) * H + h) * Sq + i] = mx + __logf(sum);
 }
 
 // dq[i] = sum_j ds_ij k_j,  ds_ij = p_ij (dO_i . v_j - delta_i),  delta_i = dO_i . O_i ; also stores delta
@@ -328,40 +355,46 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attn_bwd_dq_kernel(const flo
     xa_load_kv(k, v, ld_kv, Sk, b, h, sk, sv);
     for (int j = threadIdx.x; j < Sk; j += blockDim.x) sm[j] = key_mask ? key_mask[b * Sk + j] : 1;
     __syncthreads();
-    const int i = blockIdx.x * XA_THREADS + threadIdx.x;
-    if (i >= Sq) return;
-    const long long row = static_cast<long long>(b) * Sq + i;
-    float qr[XA_HD], gr[XA_HD], acc[XA_HD];
+    const int part = threadIdx.x & 3;
+    const int i = blockIdx.x * XA_QPB + (threadIdx.x >> 2);
+    const bool live = i < Sq;
+    const long long row = static_cast<long long>(b) * Sq + (live ? i : 0);
+    float qr[16], gr[16], acc[16];
     float dl = 0.f;
 #pragma unroll
-    for (int d = 0; d < XA_HD; d += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(q + row * ld_q + h * XA_HD + d);
-        const float4 g = *reinterpret_cast<const float4*>(dO + row * ld_o + h * XA_HD + d);
-        const float4 oo = *reinterpret_cast<const float4*>(o + row * ld_o + h * XA_HD + d);
+    for (int d = 0; d < 16; d += 4) {
+        const long long off = h * XA_HD + part * 16 + d;
+        const float4 t = *reinterpret_cast<const float4*>(q + row * ld_q + off);
+        const float4 g = *reinterpret_cast<const float4*>(dO + row * ld_o + off);
+        const float4 oo = *reinterpret_cast<const float4*>(o + row * ld_o + off);
         qr[d] = t.x; qr[d + 1] = t.y; qr[d + 2] = t.z; qr[d + 3] = t.w;
         gr[d] = g.x; gr[d + 1] = g.y; gr[d + 2] = g.z; gr[d + 3] = g.w;
         dl += g.x * oo.x + g.y * oo.y + g.z * oo.z + g.w * oo.w;
         acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
     }
-    const long long li = (static_cast<long long>(b) * H + h) * Sq + i;
+    dl = quad_sum(dl);
+    const long long li = (static_cast<long long>(b) * H + h) * Sq + (live ? i : 0);
     const float l = lse[li];
     const int jend = causal ? min(Sk, i + 1) : Sk;
-    for (int j = 0; j < jend; ++j) {
-        if (!sm[j]) continue;
+    for (int j = 0; j < Sk; ++j) {
         float s = 0.f, dp = 0.f;
 #pragma unroll
-        for (int d = 0; d < XA_HD; ++d) {
-            s = fmaf(qr[d], sk[j][d], s);
-            dp = fmaf(gr[d], sv[j][d], dp);
+        for (int d = 0; d < 16; ++d) {
+            s = fmaf(qr[d], sk[j][part * 16 + d], s);
+            dp = fmaf(gr[d], sv[j][part * 16 + d], dp);
         }
+        s = quad_sum(s);
+        dp = quad_sum(dp);
+        if (j >= jend || !sm[j]) continue;
         const float ds = __expf(s - l) * (dp - dl);
 #pragma unroll
-        for (int d = 0; d < XA_HD; ++d) acc[d] = fmaf(ds, sk[j][d], acc[d]);
+        for (int d = 0; d < 16; ++d) acc[d] = fmaf(ds, sk[j][part * 16 + d], acc[d]);
     }
+    if (!live) return;
 #pragma unroll
-    for (int d = 0; d < XA_HD; d += 4)
-        *reinterpret_cast<float4*>(dq + row * ld_dq + h * XA_HD + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
-    delta[li] = dl;
+    for (int d = 0; d < 16; d += 4)
+        *reinterpret_cast<float4*>(dq + row * ld_dq + h * XA_HD + part * 16 + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
+    if (part == 0) delta[li] = dl;
 }
 
 // dk_j = sum_i ds_ij q_i ; dv_j = sum_i p_ij dO_i.  One block per (b, h); thread (j, part) owns 16 of the 64 dims of
@@ -410,11 +443,21 @@ __global__ void __launch_bounds__(XA_MAXK * 4) cross_attn_bwd_dkv_kernel(const f
         }
         __syncthreads();
         for (int ii = 0; ii < XA_QT; ++ii) {
+            // this lane's 16 dims of q_i / dO_i: four 128-bit broadcast reads each (scalar reads made the kernel
+            // shared-memory-wavefront bound: 64 wavefronts per warp and query)
+            float qv[16], gv[16];
+#pragma unroll
+            for (int d = 0; d < 16; d += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(&sq[ii][part * 16 + d]);
+                const float4 g = *reinterpret_cast<const float4*>(&sg[ii][part * 16 + d]);
+                qv[d] = a.x; qv[d + 1] = a.y; qv[d + 2] = a.z; qv[d + 3] = a.w;
+                gv[d] = g.x; gv[d + 1] = g.y; gv[d + 2] = g.z; gv[d + 3] = g.w;
+            }
             float s = 0.f, dp = 0.f;
 #pragma unroll
             for (int d = 0; d < 16; ++d) {
-                s = fmaf(sq[ii][part * 16 + d], kr[d], s);
-                dp = fmaf(sg[ii][part * 16 + d], vr[d], dp);
+                s = fmaf(qv[d], kr[d], s);
+                dp = fmaf(gv[d], vr[d], dp);
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -424,8 +467,8 @@ __global__ void __launch_bounds__(XA_MAXK * 4) cross_attn_bwd_dkv_kernel(const f
             const float ds = p * (dp - sd[ii]);
 #pragma unroll
             for (int d = 0; d < 16; ++d) {
-                ak[d] = fmaf(ds, sq[ii][part * 16 + d], ak[d]);
-                av[d] = fmaf(p, sg[ii][part * 16 + d], av[d]);
+                ak[d] = fmaf(ds, qv[d], ak[d]);
+                av[d] = fmaf(p, gv[d], av[d]);
             }
         }
     }
@@ -658,18 +701,20 @@ TVS_API int tvs_im2col_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_
     };
     const long long rows = static_cast<long long>(B) * Ho * Wo;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define TVS_IM2COL(V)                                                                                                        \
-    {                                                                                                                        \
-        const int vb = static_cast<int>(sizeof(V));                                                                          \
-        const long long total = rows * (lb / vb);                                                                            \
-        if (round_tf32)                                                                                                      \
-            im2col_kernel<V, true><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const V*>(x), static_cast<V*>(col), H, W, \
-                                                                         static_cast<int>(cb / vb), Ho, Wo, ksize, stride, pad, \
-                                                                         lb / vb, static_cast<int>(K * elem_bytes / vb), total); \
-        else                                                                                                                 \
-            im2col_kernel<V, false><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const V*>(x), static_cast<V*>(col), H, W, \
-                                                                          static_cast<int>(cb / vb), Ho, Wo, ksize, stride, pad, \
-                                                                          lb / vb, static_cast<int>(K * elem_bytes / vb), total); \
+#define TVS_IM2COL(V)                                                                                                          \
+    {                                                                                                                          \
+        const int vb = static_cast<int>(sizeof(V));                                                                            \
+        const int cv = static_cast<int>(cb / vb), ldv = static_cast<int>(lb / vb), kvn = static_cast<int>(K * elem_bytes / vb); \
+        int shift = 5;                                                                                                         \
+        while (shift < 8 && (1 << (shift + 1)) <= std::max(32, std::min(cv, ldv))) ++shift;                                    \
+        const int rpb = 256 >> shift;                                                                                          \
+        const unsigned grid = grid_for((rows + rpb - 1) / rpb, 1, 148 * 16);                                                   \
+        if (round_tf32)                                                                                                        \
+            im2col_kernel<V, true><<<grid, 256, 0, st>>>(static_cast<const V*>(x), static_cast<V*>(col), H, W, cv, Ho, Wo, ksize, \
+                                                         stride, pad, ldv, kvn, rows, shift);                                  \
+        else                                                                                                                   \
+            im2col_kernel<V, false><<<grid, 256, 0, st>>>(static_cast<const V*>(x), static_cast<V*>(col), H, W, cv, Ho, Wo, ksize, \
+                                                          stride, pad, ldv, kvn, rows, shift);                                 \
     }
     if (al(16)) TVS_IM2COL(uint4)
     else if (al(8)) TVS_IM2COL(uint2)
@@ -707,14 +752,17 @@ TVS_API int tvs_relu_mask(const float* dy, int64_t ld_dy, const float* y, int64_
 
 TVS_API int tvs_avgpool2_nhwc(const void* x, int32_t is_bf16, int32_t B, int32_t H, int32_t W, int32_t C, void* y, int64_t ld_out, void* stream) {
     TVS_REQUIRE(x && y && H % 2 == 0 && W % 2 == 0, "tvs_avgpool2_nhwc: H and W must be even");
+    const int round_out = (is_bf16 >> 1) & 1;
+    is_bf16 &= 1;
+    TVS_REQUIRE(!(round_out && is_bf16), "tvs_avgpool2_nhwc: tf32 rounding applies to f32 elements");
     const int vec = is_bf16 ? 8 : 4;
     TVS_REQUIRE(C % vec == 0 && ld_out % vec == 0, "tvs_avgpool2_nhwc: C and ld_out must be multiples of %d", vec);
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / vec);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (is_bf16)
-        avgpool2_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(x, y, H, W, C, ld_out, total);
+        avgpool2_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(x, y, H, W, C, ld_out, total, 0);
     else
-        avgpool2_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(x, y, H, W, C, ld_out, total);
+        avgpool2_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(x, y, H, W, C, ld_out, total, round_out);
     return check_launch("avgpool2_kernel");
 }
 
@@ -739,7 +787,7 @@ TVS_API int tvs_cross_attn_fwd(const float* q, int64_t ld_q, const float* k, con
     TVS_REQUIRE(q && k && v && out && lse, "tvs_cross_attn_fwd: null pointer");
     TVS_REQUIRE(hd == XA_HD && Sk >= 1 && Sk <= XA_MAXK, "tvs_cross_attn_fwd: head dim must be %d and 1 <= Sk <= %d (got %d, %d)", XA_HD, XA_MAXK, hd, Sk);
     TVS_REQUIRE(ld_q % 4 == 0 && ld_kv % 4 == 0 && ld_o % 4 == 0, "tvs_cross_attn_fwd: strides must be multiples of 4");
-    cross_attn_fwd_kernel<<<dim3((Sq + XA_THREADS - 1) / XA_THREADS, H, B), XA_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    cross_attn_fwd_kernel<<<dim3((Sq + XA_QPB - 1) / XA_QPB, H, B), XA_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         q, ld_q, k, v, ld_kv, key_mask, Sq, Sk, causal, out, ld_o, lse);
     return check_launch("cross_attn_fwd_kernel");
 }
@@ -752,10 +800,11 @@ TVS_API int tvs_cross_attn_bwd(const float* q, int64_t ld_q, const float* k, con
     TVS_REQUIRE(hd == XA_HD && Sk >= 1 && Sk <= XA_MAXK, "tvs_cross_attn_bwd: head dim must be %d and 1 <= Sk <= %d", XA_HD, XA_MAXK);
     TVS_REQUIRE(ld_q % 4 == 0 && ld_kv % 4 == 0 && ld_o % 4 == 0 && ld_dq % 4 == 0, "tvs_cross_attn_bwd: strides must be multiples of 4");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cross_attn_bwd_dq_kernel<<<dim3((Sq + XA_THREADS - 1) / XA_THREADS, H, B), XA_THREADS, 0, st>>>(q, ld_q, k, v, ld_kv, key_mask, out, dout, ld_o,
+    cross_attn_bwd_dq_kernel<<<dim3((Sq + XA_QPB - 1) / XA_QPB, H, B), XA_THREADS, 0, st>>>(q, ld_q, k, v, ld_kv, key_mask, out, dout, ld_o,
                                                                                                      lse, Sq, Sk, causal, dq, ld_dq, delta);
     if (check_launch("cross_attn_bwd_dq_kernel")) return -3;
-    cross_attn_bwd_dkv_kernel<<<dim3(H, B), XA_MAXK * 4, 0, st>>>(q, ld_q, k, v, ld_kv, key_mask, dout, ld_o, lse, delta, Sq, Sk, causal, dk, dv, ld_dkv);
+    const int dkv_threads = std::max(128, (Sk * 4 + 31) / 32 * 32);       // 4 lanes per key; idle warps only burn issue slots
+    cross_attn_bwd_dkv_kernel<<<dim3(H, B), dkv_threads, 0, st>>>(q, ld_q, k, v, ld_kv, key_mask, dout, ld_o, lse, delta, Sq, Sk, causal, dk, dv, ld_dkv);
     return check_launch("cross_attn_bwd_dkv_kernel");
 }
 

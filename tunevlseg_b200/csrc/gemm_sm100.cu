@@ -41,6 +41,7 @@ struct GemmEpilogue {
     int vec_ok;      // every leading dimension % 4 == 0 and every pointer 16-byte aligned -> 128-bit staged epilogue
     int vec256_ok;   // 32-byte aligned rows for every operand -> direct 256-bit epilogue (the default)
     int staged;      // force the shared-memory staged (coalesced) epilogue
+    int round_out;   // out_f32 is rounded to nearest tf32 (cvt.rna): it only feeds further kind::tf32 MMAs, which truncate
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -188,6 +189,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr int EPI_LD = 36;                       // floats per staged row
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;     // 4608 bytes per epilogue warp
 
+__device__ __forceinline__ float rn_tf32f(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ bool is_dact(int act) { return act == TVS_ACT_DQGELU || act == TVS_ACT_DRELU; }
 
 __device__ __forceinline__ float epi_act(const GemmEpilogue& ep, float v, float aux) {
@@ -216,7 +222,9 @@ __device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, 
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     if (ep.act == TVS_ACT_RES_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + row * ep.ldo32 + col) = v;
+    if (ep.out_f32)
+        *reinterpret_cast<float4*>(ep.out_f32 + row * ep.ldo32 + col) =
+            ep.round_out ? make_float4(rn_tf32f(v.x), rn_tf32f(v.y), rn_tf32f(v.z), rn_tf32f(v.w)) : v;
     if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + row * ep.ldo16 + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
@@ -227,7 +235,7 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& ep, float x,
     if (ep.act != TVS_ACT_NONE) x = epi_act(ep, x, is_dact(ep.act) ? __bfloat162float(ep.aux_bf16[row * ep.ldaux + c]) : 0.f);
     if (ep.residual) x += ep.residual[row * ep.ldr + c];
     if (ep.act == TVS_ACT_RES_RELU) x = fmaxf(x, 0.f);
-    if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = x;
+    if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = ep.round_out ? rn_tf32f(x) : x;
     if (ep.out_bf16) ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
 }
 
@@ -324,7 +332,7 @@ __device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const ui
         for (int q = 0; q < 4; ++q) {
             uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(v[8 * q + i]);
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(ep.round_out ? rn_tf32f(v[8 * q + i]) : v[8 * q + i]);
             st256(ep.out_f32 + row * ep.ldo32 + col0 + 8 * q, o);
         }
     }
@@ -756,6 +764,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.aux_bf16 = static_cast<const __nv_bfloat16*>(a.aux_bf16);
     ep.ldaux = a.ldaux;
     ep.act = a.act;
+    ep.round_out = a.reserved & 1;
     ep.vec_ok = vec_ok ? 1 : 0;
     auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
     ep.vec256_ok = ((!a.out_f32 || (a.ldo32 % 8 == 0 && al32(a.out_f32))) && (!a.out_bf16 || (a.ldo16 % 16 == 0 && al32(a.out_bf16))) &&

@@ -290,64 +290,71 @@ class PackedCris:
 # ------------------------------------------------------------------------------------------------------------------
 # forward-only image encoder (clip.py:18-274), bf16 GEMM operands + fp32 residual stream
 # ------------------------------------------------------------------------------------------------------------------
-def _conv_nograd(op: ConvOp, x, B, H, W, *, residual=None, act=None):
-    """x: [B*H*W, Cin] in op.w.dtype -> ([B*Ho*Wo, Cout] same dtype, Ho, Wo)."""
+def _conv_nograd(op: ConvOp, x, B, H, W, *, residual=None, act=None, x_rounded=False, round_out=False):
+    """x: [B*H*W, Cin] in op.w.dtype -> ([B*Ho*Wo, Cout] same dtype, Ho, Wo).  tf32 operands are rounded to nearest:
+    by the producer (``x_rounded``), inside im2col, or by an explicit pass; ``round_out`` rounds this conv's output in the
+    GEMM epilogue for its consumers."""
     f32 = x.dtype == F32
     if op.k == 1 and op.stride == 1:
-        A, Ho, Wo = (rn_act(x) if f32 else x), H, W
+        A, Ho, Wo = (rn_act(x) if (f32 and not x_rounded) else x), H, W
     else:
         Ho, Wo = (H + 2 * op.pad - op.k) // op.stride + 1, (W + 2 * op.pad - op.k) // op.stride + 1
         A = _e((B * Ho * Wo, op.Kp), x.dtype, x)
-        abi.im2col_nhwc(x, B, H, W, op.cin, op.k, op.stride, op.pad, A, round_tf32=f32)
+        abi.im2col_nhwc(x, B, H, W, op.cin, op.k, op.stride, op.pad, A, round_tf32=f32 and not x_rounded)
     y = _e((B * Ho * Wo, op.cout), x.dtype, x)
     if act is None:
         act = abi.ACT_RELU if op.relu else abi.ACT_NONE
     res32 = None if residual is None else residual.to(F32)
-    abi.gemm(A, op.w, bias=op.bias, residual=res32, out_f32=y if y.dtype == F32 else None, out_bf16=y if y.dtype == BF16 else None, act=act)
+    abi.gemm(A, op.w, bias=op.bias, residual=res32, out_f32=y if f32 else None, out_bf16=None if f32 else y, act=act,
+             round_out=round_out and f32)
     return y, Ho, Wo
 
 
 @torch.no_grad()
 def encode_image(pk: PackedCris, image):
-    """image (B,3,H,W) f32 -> (v3, v4, v5) as f32 [B*h*w, C] matrices with their (h, w)."""
+    """image (B,3,H,W) f32 -> (v3, v4, v5) as f32 [B*h*w, C] matrices with their (h, w).
+
+    Every activation of the frozen encoder only ever feeds tf32 GEMMs (and the residual adds), so each producer rounds
+    its output to nearest tf32 once (GEMM epilogue / pooling kernel) instead of a separate rounding pass per consumer."""
     B, _, H, W = image.shape
     dt = pk.stem[0].w.dtype
+    f32 = dt == F32
     x = image.permute(0, 2, 3, 1).contiguous().to(dt).view(B * H * W, 3)
-    for op in pk.stem:
-        x, H, W = _conv_nograd(op, x, B, H, W)
+    for i, op in enumerate(pk.stem):
+        x, H, W = _conv_nograd(op, x, B, H, W, x_rounded=i > 0, round_out=True)
     C = pk.stem[-1].cout
     y = _e((B * (H // 2) * (W // 2), C), dt, x)
-    abi.avgpool2_nhwc(x, B, H, W, C, y)
+    abi.avgpool2_nhwc(x, B, H, W, C, y, round_tf32=f32)
     x, H, W = y, H // 2, W // 2
     outs = {}
     for blk in pk.blocks:
-        o1, _, _ = _conv_nograd(blk.c1, x, B, H, W)
-        o2, _, _ = _conv_nograd(blk.c2, o1, B, H, W)
+        o1, _, _ = _conv_nograd(blk.c1, x, B, H, W, x_rounded=True, round_out=True)
+        o2, _, _ = _conv_nograd(blk.c2, o1, B, H, W, x_rounded=True, round_out=True)
         Ho, Wo, xin = H, W, x
         if blk.stride > 1:                      # anti-aliased stride: AvgPool after conv2 and in front of the shortcut conv
             Ho, Wo = H // 2, W // 2
             p2 = _e((B * Ho * Wo, blk.c2.cout), dt, x)
-            abi.avgpool2_nhwc(o2, B, H, W, blk.c2.cout, p2)
+            abi.avgpool2_nhwc(o2, B, H, W, blk.c2.cout, p2, round_tf32=f32)
             o2 = p2
             xin = _e((B * Ho * Wo, blk.c1.cin), dt, x)
-            abi.avgpool2_nhwc(x, B, H, W, blk.c1.cin, xin)
-        ident = xin if blk.ds is None else _conv_nograd(blk.ds, xin, B, Ho, Wo)[0]
-        x, _, _ = _conv_nograd(blk.c3, o2, B, Ho, Wo, residual=ident, act=abi.ACT_RES_RELU)
+            abi.avgpool2_nhwc(x, B, H, W, blk.c1.cin, xin, round_tf32=f32)
+        ident = xin if blk.ds is None else _conv_nograd(blk.ds, xin, B, Ho, Wo, x_rounded=True)[0]
+        x, _, _ = _conv_nograd(blk.c3, o2, B, Ho, Wo, residual=ident, act=abi.ACT_RES_RELU, x_rounded=True, round_out=True)
         H, W = Ho, Wo
         if blk.last:
             outs[blk.stage] = (x.to(F32), H, W)
     # attention pool (clip.py:78-182): tokens + resized positions -> MHA -> c_proj, + connect(x) residual, ReLU
     x4, H4, W4 = outs[4]
     S, Ce = H4 * W4, x4.shape[1]
-    res, _, _ = _conv_nograd(pk.ap_connect, x, B, H4, W4)
+    res, _, _ = _conv_nograd(pk.ap_connect, x, B, H4, W4, x_rounded=True)
     t = (x4.view(B, S, Ce) + pk.attnpool_pos(H4, W4)).to(dt).view(B * S, Ce)
     qkv = _e((B * S, 3 * Ce), BF16, t)
-    abi.gemm(rn_act(t) if dt == F32 else t, pk.ap_qkv.w, bias=pk.ap_qkv.bias, out_bf16=qkv)
+    abi.gemm(rn_act(t) if f32 else t, pk.ap_qkv.w, bias=pk.ap_qkv.bias, out_bf16=qkv)
     att, att32 = _e((B * S, Ce), BF16, t), _e((B * S, Ce), F32, t)
     lse = _e((B, pk.rn_heads, S), F32, t)
     abi.attn_fwd(qkv, B, S, pk.rn_heads, Ce // pk.rn_heads, False, None, att, lse, out_f32=att32)
     v5 = _e((B * S, pk.embed_dim), F32, t)
-    abi.gemm(rn_act(att32) if dt == F32 else att, pk.ap_c.w, bias=pk.ap_c.bias, residual=res.to(F32), out_f32=v5, act=abi.ACT_RES_RELU)
+    abi.gemm(rn_act(att32) if f32 else att, pk.ap_c.w, bias=pk.ap_c.bias, residual=res.to(F32), out_f32=v5, act=abi.ACT_RES_RELU)
     return outs[2], outs[3], (v5, H4, W4)
 
 
