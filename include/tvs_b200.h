@@ -84,7 +84,9 @@ int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);
  * D % 4 == 0, D <= 2048 (2048: the CRIS decoder FFN norm, layers.py:303-309).
  * ------------------------------------------------------------------------------------------------ */
 int tvs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int32_t D,
-                      float* y_f32, void* y_bf16, float* mean, float* rstd, void* stream);
+                      float* y_f32, void* y_bf16, float* mean, float* rstd, int32_t round_tf32, void* stream);
+/* round_tf32 != 0: y_f32 is rounded to nearest tf32 - it feeds a TVS_AB_TF32 GEMM, whose MMA truncates its operands.
+ * (tvs_attn_fwd's out_f32 and tvs_cross_attn_fwd's out are always rounded that way: they only feed such GEMMs.) */
 int tvs_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dx_add_f32, int64_t M, int32_t D,
                       float* dx_out_f32, void* dx_out_bf16, void* stream);

@@ -66,7 +66,7 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
             o.copy_(_tf32_rn(v) if (round_out and o is out_f32) else v)
 
 
-def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None, round_tf32=False):
     D = x.shape[-1]
     x2 = x.reshape(-1, D)
     mu = x2.mean(1)
@@ -75,7 +75,7 @@ def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rs
     y = (x2 - mu[:, None]) * rs[:, None] * gamma + beta
     for o in (y_f32, y_bf16):
         if o is not None:
-            o.view(-1, D).copy_(y)
+            o.view(-1, D).copy_(_tf32_rn(y) if (round_tf32 and o is y_f32) else y)
     if mean is not None:
         mean.copy_(mu)
     if rstd is not None:
@@ -111,7 +111,7 @@ def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse, out_f32=None):
     out.copy_(o)
     lse.copy_(l)
     if out_f32 is not None:
-        out_f32.copy_(o)
+        out_f32.copy_(_tf32_rn(o))
 
 
 def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv):
@@ -201,7 +201,7 @@ def _xattn_ref(q, k, v, key_mask, B, Sq, Sk, H, hd, causal=False):
 def cross_attn_fwd(q, k, v, key_mask, B, Sq, Sk, H, hd, out, lse, causal=False):
     assert hd == 64 and Sk <= 80
     o, l = _xattn_ref(q, k, v, key_mask, B, Sq, Sk, H, hd, causal)
-    out.copy_(o)
+    out.copy_(_tf32_rn(o))
     lse.copy_(l)
 
 

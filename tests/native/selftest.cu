@@ -407,7 +407,7 @@ static void ln_case(int M, int D) {
     float *dmean = dev_zero<float>(M), *drstd = dev_zero<float>(M);
     float* ddx = dev_zero<float>((size_t)M * D);
     __nv_bfloat16* ddx16 = dev_zero<__nv_bfloat16>((size_t)M * D);
-    TV(tvs_layernorm_fwd(dx, dg, db, 1e-5f, M, D, dy32, dy16, dmean, drstd, nullptr));
+    TV(tvs_layernorm_fwd(dx, dg, db, 1e-5f, M, D, dy32, dy16, dmean, drstd, 0, nullptr));
     TV(tvs_layernorm_bwd(nullptr, ddy, dx, dg, dmean, drstd, dadd, M, D, ddx, ddx16, nullptr));
     CK(cudaDeviceSynchronize());
     auto y = host(dy32, (size_t)M * D);

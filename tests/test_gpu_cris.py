@@ -119,14 +119,14 @@ def test_short_key_attention(Sq, Sk, H, causal):
     if causal:
         s = s.masked_fill(torch.triu(torch.ones(Sq, Sk, dtype=torch.bool, device="cuda"), 1), float("-inf"))
     ref = (torch.softmax(s, -1) @ vr.view(B, Sk, H, hd).transpose(1, 2)).transpose(1, 2).reshape(B * Sq, D)
-    assert _rel(out, ref) < 2e-5
+    assert _rel(out, ref) < 6e-4                       # the output is rounded to nearest tf32 (it feeds a tf32 GEMM)
     assert _rel(lse, torch.logsumexp(s, -1)) < 1e-5
     go = torch.randn(B * Sq, D, device="cuda", generator=g)
     ref.backward(go)
     dq, dkv = torch.empty_like(q), torch.empty_like(kv)
     delta = torch.empty_like(lse)
     abi.cross_attn_bwd(q, kv[:, :D], kv[:, D:], km, out, go, lse, B, Sq, Sk, H, hd, dq, dkv[:, :D], dkv[:, D:], delta, causal=causal)
-    assert _rel(dq, qr.grad) < 5e-5 and _rel(dkv[:, :D], kr.grad) < 5e-5 and _rel(dkv[:, D:], vr.grad) < 5e-5
+    assert _rel(dq, qr.grad) < 1e-3 and _rel(dkv[:, :D], kr.grad) < 1e-3 and _rel(dkv[:, D:], vr.grad) < 1e-3
     assert dkv[Sk + Sk // 2:, :].abs().max() == 0        # padded keys of sample 1 get exactly no gradient
 
 
@@ -219,6 +219,7 @@ def _run_cris(case, spec, B, L, seed, pad=True, use_mask=True, new_last_layer=Tr
     err = (logits.detach().cpu() - ref.detach()).abs().max().item()
     ref_max = ref.detach().abs().max().item()
     tol = max(LOGIT_TOL, 2.0 ** (math.floor(math.log2(ref_max)) - 7))
+    print(f"PARITY cris {case} B={B} {spec.image_size}px: logits max-abs err {err:.5f} (tol {tol:.4f}, |logit|max {ref_max:.2f})")
     assert err <= tol, f"{case}: logits max-abs err {err:.4f} > {tol} (|logit|max {ref_max:.2f})"
     assert abs(loss.item() - ref_loss.item()) <= 5e-3
     _, c_counts, c_conf = OLM.c_dicebce_metrics(logits.detach().cpu(), mask)

@@ -64,7 +64,7 @@ def load():
     lib.tvs_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
     sig = {
-        "tvs_layernorm_fwd": [P, P, P, F, I64, I32, P, P, P, P, P],
+        "tvs_layernorm_fwd": [P, P, P, F, I64, I32, P, P, P, P, I32, P],
         "tvs_layernorm_bwd": [P, P, P, P, P, P, P, I64, I32, P, P, P],
         "tvs_attn_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, P],
         "tvs_attn_bwd": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, P],
@@ -198,14 +198,14 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
 
 
-def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None, round_tf32=False):
     require_device()
     _chk(x, torch.float32, "x"); _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
     _chk(y_f32, torch.float32, "y_f32"); _chk(y_bf16, torch.bfloat16, "y_bf16")
     D = x.shape[-1]
     M = x.numel() // D
     _ck(load().tvs_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, D, _p(y_f32), _p(y_bf16),
-                                 _p(mean), _p(rstd), _stream()), "tvs_layernorm_fwd")
+                                 _p(mean), _p(rstd), int(round_tf32), _stream()), "tvs_layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_add=None, dx_f32=None, dx_bf16=None):

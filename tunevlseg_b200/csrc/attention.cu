@@ -231,7 +231,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int H, int causal,
                 float* frow = out32 + (static_cast<long long>(b) * S + q) * E + h * HD;
 #pragma unroll
                 for (int nb = 0; nb < HD / 8; ++nb)
-                    *reinterpret_cast<float2*>(frow + nb * 8 + 2 * tq) = make_float2(o[nb][2 * r] * inv, o[nb][2 * r + 1] * inv);
+                    *reinterpret_cast<float2*>(frow + nb * 8 + 2 * tq) =
+                        make_float2(round_tf32_rn(o[nb][2 * r] * inv), round_tf32_rn(o[nb][2 * r + 1] * inv));      // feeds a tf32 GEMM
             }
             if (tq == 0) lse[(static_cast<long long>(b) * H + h) * S + q] = (m_run[r] == -INFINITY ? 0.f : m_run[r]) + logf(fmaxf(l_run[r], 1e-30f));
         }

@@ -326,7 +326,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int e = 8 * q + i;
-                            w[i] = __float_as_uint(__uint_as_float(e < 32 ? o0[e] : o1[e - 32]) * inv);
+                            w[i] = __float_as_uint(round_tf32_rn(__uint_as_float(e < 32 ? o0[e] : o1[e - 32]) * inv));     // feeds a tf32 GEMM
                         }
                         st_global_256(f + 8 * q, w);
                     }
@@ -613,7 +613,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int e = 8 * q + i;
-                        w[i] = __float_as_uint(__uint_as_float(e < 32 ? o0[e] : o1[e - 32]) * inv);
+                        w[i] = __float_as_uint(round_tf32_rn(__uint_as_float(e < 32 ? o0[e] : o1[e - 32]) * inv));     // feeds a tf32 GEMM
                     }
                     st_global_256(f + 8 * q, w);
                 }

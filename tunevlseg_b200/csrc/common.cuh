@@ -50,6 +50,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
     __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
     return __bfloat1622float2(t);
 }
+// fp32 -> nearest tf32 (10-bit mantissa, ties away).  The kind::tf32 MMA TRUNCATES its fp32 operands (a systematic
+// -3.4e-4 relative bias per GEMM), so every producer of a tf32 GEMM operand rounds with this on the way out.
+__device__ __forceinline__ float round_tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
 // sigmoid through ONE special-function op: sigma(z) = 0.5 * tanh(z / 2) + 0.5 (MUFU.TANH, ~2^-11 relative error).
 // An IEEE division in a GEMM epilogue costs a slow-path subroutine per element (measured: 3x the whole GEMM time).

@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(XA_THREADS) cross_attn_fwd_kernel(const float*
 #pragma unroll
     for (int d = 0; d < 16; d += 4)
         *reinterpret_cast<float4*>(out + row * ld_o + h * XA_HD + part * 16 + d) =
-            make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+            make_float4(round_tf32_rn(acc[d] * inv), round_tf32_rn(acc[d + 1] * inv), round_tf32_rn(acc[d + 2] * inv),
+                        round_tf32_rn(acc[d + 3] * inv));                  // the output only feeds the out-proj tf32 GEMM
     if (part == 0) lse[(static_cast<long long>(b) * H + h) * Sq + i] = mx + __logf(sum);
 }
 

@@ -12,7 +12,8 @@ constexpr int LN_WARPS = 4;
 template <int MAXC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M,
-                     int D, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                     int D, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     int round_out) {
     const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -55,7 +56,9 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
             o.y = (v[i].y - mean) * rstd * g.y + b.y;
             o.z = (v[i].z - mean) * rstd * g.z + b.z;
             o.w = (v[i].w - mean) * rstd * g.w + b.w;
-            if (y32) reinterpret_cast<float4*>(y32 + row * D)[c] = o;
+            if (y32)
+                reinterpret_cast<float4*>(y32 + row * D)[c] =
+                    round_out ? make_float4(round_tf32_rn(o.x), round_tf32_rn(o.y), round_tf32_rn(o.z), round_tf32_rn(o.w)) : o;
             if (y16) reinterpret_cast<uint2*>(y16 + row * D)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         }
     }
@@ -119,17 +122,17 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
 }  // namespace tvs
 
 extern "C" __attribute__((visibility("default"))) int tvs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int32_t D, float* y_f32,
-                                 void* y_bf16, float* mean, float* rstd, void* stream) {
+                                 void* y_bf16, float* mean, float* rstd, int32_t round_tf32, void* stream) {
     using namespace tvs;
     TVS_REQUIRE(x && gamma && beta && (y_f32 || y_bf16), "tvs_layernorm_fwd: null pointer");
     TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_fwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
     const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
     if (D <= 1024)
         layernorm_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
-                                                                                               static_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
+                                                                                               static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32);
     else
         layernorm_fwd_kernel<16><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
-                                                                                                static_cast<__nv_bfloat16*>(y_bf16), mean, rstd);
+                                                                                                static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32);
     return check_launch("layernorm_fwd_kernel");
 }
 

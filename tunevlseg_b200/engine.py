@@ -91,7 +91,7 @@ class PackedLayer:
         if attn32 and tf32:
             self.wqkv_t32 = _f(wqkv.t())
         if tf32:
-            pack = tf32_rn if self.attn32 else _f      # attn32 (CRIS) layers round every forward operand to nearest
+            pack = tf32_rn                                # forward tf32 operands are rounded to nearest (the MMA truncates)
             self.wqkv32, self.wo32 = pack(wqkv), pack(sa.out_proj.weight)
             self.w1_32, self.w2_32 = pack(mlp.fc1.weight), pack(mlp.fc2.weight)
             self.wo_t32 = _f(sa.out_proj.weight.t())
@@ -131,18 +131,18 @@ class PackedClipSeg:
         # text
         self.t_layers = [PackedLayer(l, self.t_heads, tf32=True) for l in tm.encoder.layers]
         self.fin_g, self.fin_b = _f(tm.final_layer_norm.weight), _f(tm.final_layer_norm.bias)
-        self.w_tproj = _f(model.clip.text_projection.weight)                         # [proj, Dt] f32 (tf32 MMA)
+        self.w_tproj = tf32_rn(model.clip.text_projection.weight)                    # [proj, Dt] f32 (tf32 MMA)
         self.w_tproj_t = _f(model.clip.text_projection.weight.t())
         # decoder
         self.d_layers = [PackedLayer(l, self.d_heads, tf32=True) for l in dec.layers]
-        self.w_red = [_f(r.weight) for r in dec.reduces]                             # [Dr, Dv] f32 (tf32 MMA)
+        self.w_red = [tf32_rn(r.weight) for r in dec.reduces]                        # [Dr, Dv] f32 (tf32 MMA, rounded to nearest)
         self.b_red = [_f(r.bias) for r in dec.reduces]
         self.w_red_t = [_bf(r.weight.t()) for r in dec.reduces]                      # [Dv, Dr]
-        self.w_film = _f(torch.cat((dec.film_mul.weight, dec.film_add.weight), dim=0))       # [2Dr, proj] f32
+        self.w_film = tf32_rn(torch.cat((dec.film_mul.weight, dec.film_add.weight), dim=0))  # [2Dr, proj] f32
         self.b_film = _f(torch.cat((dec.film_mul.bias, dec.film_add.bias)))
         self.w_film_t = _bf(torch.cat((dec.film_mul.weight, dec.film_add.weight), dim=0).t())  # [proj, 2Dr]
         tw = dec.transposed_convolution.weight.detach()                              # [Dr, 1, P, P]
-        self.w_tconv = _f(tw.reshape(self.Dr, -1).t())                               # [P*P, Dr] f32 (tf32 MMA)
+        self.w_tconv = tf32_rn(tw.reshape(self.Dr, -1).t())                          # [P*P, Dr] f32 (tf32 MMA)
         self.w_tconv_t = _bf(tw.reshape(self.Dr, -1))                                # [Dr, P*P]
         self.b_tconv = _f(dec.transposed_convolution.bias)
 
@@ -189,12 +189,13 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     adt = F32 if hi else BF16
     ln = _e((M, D), adt, x)
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
-    abi.layernorm_fwd(x, pk.g1, pk.be1, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean1, rstd=rstd1)
+    abi.layernorm_fwd(x, pk.g1, pk.be1, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean1, rstd=rstd1, round_tf32=hi)
     lse = _e((B, pk.heads, S), F32, x)
-    rn = rn_act if pk.attn32 else (lambda t: t)
+    # tf32 operands are rounded to nearest by their producers: LayerNorm (flag), the attention kernels (always), the
+    # fc1 epilogue (round_out)
     if pk.attn32:
         qkv = _e((M, 3 * D), F32, x)
-        abi.gemm(rn(ln), pk.wqkv32, bias=pk.bqkv, out_f32=qkv)
+        abi.gemm(ln, pk.wqkv32, bias=pk.bqkv, out_f32=qkv)
         att = att32 = _e((M, D), F32, x)
         abi.cross_attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], key_mask, B, S, S, pk.heads, pk.hd, att32, lse, causal=causal)
     else:
@@ -204,15 +205,15 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
         att32 = _e((M, D), F32, x) if hi else None
         abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, causal, key_mask, att, lse, out_f32=att32)
     x1 = _e((M, D), F32, x)
-    abi.gemm(rn(att32) if hi else att, pk.wo32 if hi else pk.wo, bias=pk.bo, residual=x, out_f32=x1)
+    abi.gemm(att32 if hi else att, pk.wo32 if hi else pk.wo, bias=pk.bo, residual=x, out_f32=x1)
     mean2, rstd2 = _e((M,), F32, x), _e((M,), F32, x)
-    abi.layernorm_fwd(x1, pk.g2, pk.be2, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean2, rstd=rstd2)
+    abi.layernorm_fwd(x1, pk.g2, pk.be2, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean2, rstd=rstd2, round_tf32=hi)
     u = _e((M, F), BF16, x)
     a = _e((M, F), adt, x)
-    abi.gemm(rn(ln), pk.w1_32 if hi else pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_f32=a if hi else None,
-             out_bf16=None if hi else a, act=abi.ACT_QGELU)
+    abi.gemm(ln, pk.w1_32 if hi else pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_f32=a if hi else None,
+             out_bf16=None if hi else a, act=abi.ACT_QGELU, round_out=hi)
     x2 = _e((M, D), F32, x)
-    abi.gemm(rn(a), pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2)
+    abi.gemm(a, pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2)
     sv = Saved(x, mean1, rstd1, qkv, att, lse, x1, mean2, rstd2, u) if save else None
     return x2, sv
 
@@ -281,17 +282,17 @@ def decoder_layer_fwd(pk: PackedLayer, x, B, S, eps):
     Returns (y f32, saved)."""
     M, D, F = B * S, pk.D, pk.F
     qkv = _e((M, 3 * D), BF16, x)
-    abi.gemm(x, pk.wqkv32, bias=pk.bqkv, out_bf16=qkv)
+    abi.gemm(rn_act(x), pk.wqkv32, bias=pk.bqkv, out_bf16=qkv)
     att, att32 = _e((M, D), BF16, x), _e((M, D), F32, x)
     lse = _e((B, pk.heads, S), F32, x)
     abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, False, None, att, lse, out_f32=att32)
     s1 = _e((M, D), F32, x)
-    abi.gemm(att32, pk.wo32, bias=pk.bo, residual=x, out_f32=s1)
+    abi.gemm(att32, pk.wo32, bias=pk.bo, residual=x, out_f32=s1)       # att32 leaves the attention kernel rounded to tf32
     y1 = _e((M, D), F32, x)
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
     abi.layernorm_fwd(s1, pk.g1, pk.be1, eps, y_f32=y1, mean=mean1, rstd=rstd1)
     a32, a16 = _e((M, F), F32, x), _e((M, F), BF16, x)
-    abi.gemm(y1, pk.w1_32, bias=pk.b1, out_f32=a32, out_bf16=a16, act=abi.ACT_RELU)
+    abi.gemm(rn_act(y1), pk.w1_32, bias=pk.b1, out_f32=a32, out_bf16=a16, act=abi.ACT_RELU, round_out=True)
     s2 = _e((M, D), F32, x)
     abi.gemm(a32, pk.w2_32, bias=pk.b2, residual=y1, out_f32=s2)
     y2 = _e((M, D), F32, x)
@@ -461,7 +462,7 @@ class TextTowerFn(torch.autograd.Function):
         rows = torch.arange(B, device=x.device) * S + pool_pos.to(x.device)
         pooled = xf.index_select(0, rows)
         cond = _e((B, pk.w_tproj.shape[0]), F32, x)
-        abi.gemm(pooled, pk.w_tproj, out_f32=cond)
+        abi.gemm(rn_act(pooled), pk.w_tproj, out_f32=cond)
         ctx.pk, ctx.saved, ctx.km = pk, saved, km
         ctx.fin = (x, mean_f, rstd_f, rows)
         ctx.dims = (B, S, D, depth, n_ctx, None if cd is None else tuple(cd.shape))
@@ -516,10 +517,10 @@ class DecoderFn(torch.autograd.Function):
         saved_layers, film_saved = [], None
         for i, act in enumerate(acts):
             r = _e((M, Dr), F32, act)
-            abi.gemm(act.detach().contiguous().view(M, Dv), pk.w_red[i], bias=pk.b_red[i], residual=out, out_f32=r)
+            abi.gemm(rn_act(act.detach().contiguous().view(M, Dv)), pk.w_red[i], bias=pk.b_red[i], residual=out, out_f32=r)
             if i == pk.conditional_layer:
                 film = _e((B, 2 * Dr), F32, act)
-                abi.gemm(cond_d, pk.w_film, bias=pk.b_film, out_f32=film)
+                abi.gemm(rn_act(cond_d), pk.w_film, bias=pk.b_film, out_f32=film)
                 mul, add = film[:, :Dr].contiguous(), film[:, Dr:].contiguous()
                 y = _e((M, Dr), F32, act)
                 abi.film_fwd(r.view(B, S, Dr), mul, add, y.view(B, S, Dr), None)
@@ -533,7 +534,8 @@ class DecoderFn(torch.autograd.Function):
         feat32 = _e((B, G2, Dr), F32, out)
         abi.slice_rows(out.view(B, S, Dr), 1, G2, y_f32=feat32)
         tconv = _e((B * G2, P * P), F32, out)
-        abi.gemm(feat32.view(B * G2, Dr), pk.w_tconv, out_f32=tconv)
+        feat_rn = rn_act(feat32.view(B * G2, Dr))
+        abi.gemm(feat_rn, pk.w_tconv, out_f32=tconv)
         H = G * P
         logits = _e((B, 1, H, H), F32, out)
         addmap = add_out = wa16 = ratio_d = add_b_d = None
@@ -546,7 +548,7 @@ class DecoderFn(torch.autograd.Function):
             wa16 = torch.zeros((32 * ((KK + 31) // 32), Dr), dtype=BF16, device=out.device)   # padded bf16 copy for the dgrad
             wa16[:KK] = wa.to(BF16)
             addmap = torch.zeros((B * G2, wa16.shape[0]), dtype=F32, device=out.device)
-            abi.gemm(feat32.view(B * G2, Dr), wa, out_f32=addmap[:, :KK])
+            abi.gemm(feat_rn, tf32_rn(wa), out_f32=addmap[:, :KK])
             add_out = _e((B, H, H), F32, out) if blend == abi.BLEND_RATIO else None
             ratio_d = None if ratio is None else ratio.detach().to(F32).reshape(1).contiguous()
             add_b_d = add_b.detach().to(F32).contiguous()

@@ -354,7 +354,7 @@ def encode_image(pk: PackedCris, image):
     lse = _e((B, pk.rn_heads, S), F32, t)
     abi.attn_fwd(qkv, B, S, pk.rn_heads, Ce // pk.rn_heads, False, None, att, lse, out_f32=att32)
     v5 = _e((B * S, pk.embed_dim), F32, t)
-    abi.gemm(rn_act(att32) if f32 else att, pk.ap_c.w, bias=pk.ap_c.bias, residual=res.to(F32), out_f32=v5, act=abi.ACT_RES_RELU)
+    abi.gemm(att32 if f32 else att, pk.ap_c.w, bias=pk.ap_c.bias, residual=res.to(F32), out_f32=v5, act=abi.ACT_RES_RELU)
     return outs[2], outs[3], (v5, H4, W4)
 
 
@@ -503,7 +503,7 @@ class SelfAttnFn(torch.autograd.Function):
         lse = _e((B, m.heads, S), F32, xqk)
         abi.attn_fwd(qkv, B, S, m.heads, m.hd, False, None, att, lse, out_f32=att32)
         out = _e((M, D), F32, xqk)
-        abi.gemm(rn_act(att32), m.o.w, bias=m.o.bias, out_f32=out)
+        abi.gemm(att32, m.o.w, bias=m.o.bias, out_f32=out)              # att32 leaves the attention kernel rounded to tf32
         ctx.m, ctx.geom = m, (B, S)
         ctx.save_for_backward(qkv, att, lse)
         return out
@@ -541,7 +541,7 @@ class CrossAttnFn(torch.autograd.Function):
         lse = _e((B, m.heads, Sq), F32, xq)
         abi.cross_attn_fwd(q, kv[:, :D], kv[:, D:], key_mask, B, Sq, Sk, m.heads, m.hd, att, lse)
         out = _e((B * Sq, D), F32, xq)
-        abi.gemm(rn_act(att), m.o.w, bias=m.o.bias, out_f32=out)
+        abi.gemm(att, m.o.w, bias=m.o.bias, out_f32=out)                # rounded to tf32 by the attention kernel
         ctx.m, ctx.geom, ctx.key_mask = m, (B, Sq, Sk), key_mask
         ctx.save_for_backward(q, kv, att, lse)
         return out
