@@ -270,6 +270,10 @@ int tvs_dynconv_bwd(const float* dout, const float* x, const float* w, int64_t l
 int tvs_resample2d_fwd(const float* in, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, const int32_t* iy,
                        const float* wy, const int32_t* ix, const float* wx, int32_t ntaps, int32_t tile, float* out,
                        void* stream);
+/* Predict tail (src/utils/save_utils.py:96-104): TF.resize(pred, mask_shape, BICUBIC, antialias=False) fused with
+ * torchvision.utils.save_image's quantisation u8 = clamp(v * 255 + 0.5, 0, 255); tables as above (align_corners=False). */
+int tvs_resample2d_u8(const float* in, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, const int32_t* iy,
+                      const float* wy, const int32_t* ix, const float* wx, int32_t ntaps, uint8_t* out, void* stream);
 int tvs_resample2d_bwd(const void* dout, int32_t dout_is_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho,
                        int32_t Wo, const int32_t* ty, const float* twy, const int32_t* cy, const int32_t* tx,
                        const float* twx, const int32_t* cx, int32_t max_taps, int32_t tile, float* din, void* stream);

@@ -243,7 +243,7 @@ def test_cris_bicubic_tables_match_torch():
                 R[o, idx[o, a]] += wt[o, a]
         x = torch.randn(1, 1, n_in, n_in)
         ref = torch.nn.functional.interpolate(x, (n_out, n_out), mode="bicubic", align_corners=True)[0, 0]
-        assert (R @ x[0, 0] @ R.t() - ref).abs().max() < 1e-4      # torch evaluates the source index in fp32
+        assert (R @ x[0, 0] @ R.t() - ref).abs().max() < 2e-5
         Rt = torch.zeros(n_in, n_out)
         for i in range(n_in):
             for j in range(int(cnt[i])):
@@ -279,3 +279,23 @@ def test_cris_engine_composition_against_oracle(case, monkeypatch):
         assert g is not None and g_ref is not None, pk
         err = ((g - g_ref).norm() / g_ref.norm()).item()
         assert err < 5e-2, f"{pk}: {err}"
+
+
+def test_predict_tail_tables_and_metric_formulas():
+    """align_corners=False bicubic tap tables == F.interpolate / TF.resize(antialias=False); eval-script formulas."""
+    from tunevlseg_b200.engine_cris import _bicubic_tables
+    from tunevlseg_b200.scripts.eval_metrics import metrics_from_counts
+
+    for n_in, n_out in ((64, 301), (352, 200), (9, 9), (352, 480)):
+        idx, wt, *_ = _bicubic_tables(n_in, n_out, "cpu", align_corners=False)
+        R = torch.zeros(n_out, n_in)
+        for o in range(n_out):
+            for a in range(4):
+                R[o, idx[o, a]] += wt[o, a]
+        x = torch.randn(1, 1, n_in, n_in)
+        ref = torch.nn.functional.interpolate(x, (n_out, n_out), mode="bicubic", align_corners=False)[0, 0]
+        assert (R @ x[0, 0] @ R.t() - ref).abs().max() < 1e-4
+    m = metrics_from_counts(tp=30, fp=10, fn=20, n_pos_gt=50, n=200)
+    assert abs(m["dice"] - 100 * 60 / 90) < 1e-9 and abs(m["iou"] - 50.0) < 1e-9
+    assert abs(m["ones_dice_diff"] - (100 * 60 / 90 - 100 * 100 / 250)) < 1e-9
+    assert metrics_from_counts(0, 0, 0, 0, 100)["dice"] == 100.0 and metrics_from_counts(0, 5, 0, 0, 100)["iou"] == 0.0

@@ -98,6 +98,7 @@ def load():
         "tvs_dynconv_fwd": [P, P, I64, P, I64, I32, I32, I32, I32, P, P, P],
         "tvs_dynconv_bwd": [P, P, P, I64, I32, I32, I32, I32, P, P, I32, P],
         "tvs_resample2d_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, I32, P, P],
+        "tvs_resample2d_u8": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, P, P],
         "tvs_resample2d_bwd": [P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, I32, I32, P, P],
     }
     for name, argtypes in sig.items():
@@ -574,6 +575,14 @@ def resample2d_fwd(inp, B, Hi, Wi, Ho, Wo, tab, tile, out):
                                   tab["wx"].data_ptr(), tab["ntaps"], tile, out.data_ptr(), _stream()), "tvs_resample2d_fwd")
 
 
+def resample2d_u8(inp, B, Hi, Wi, Ho, Wo, tab, out):
+    """Bicubic resize fused with save_image's quantisation: f32 (B,Hi,Wi) -> u8 (B,Ho,Wo)."""
+    require_device()
+    _chk(inp, torch.float32, "in"); _chk(out, torch.uint8, "out")
+    _ck(load().tvs_resample2d_u8(inp.data_ptr(), B, Hi, Wi, Ho, Wo, tab["iy"].data_ptr(), tab["wy"].data_ptr(), tab["ix"].data_ptr(),
+                                 tab["wx"].data_ptr(), tab["ntaps"], out.data_ptr(), _stream()), "tvs_resample2d_u8")
+
+
 def resample2d_bwd(dout, B, Hi, Wi, Ho, Wo, tab, tile, din):
     require_device()
     if dout.dtype not in (torch.float32, torch.bfloat16) or not dout.is_contiguous():
@@ -585,5 +594,5 @@ def resample2d_bwd(dout, B, Hi, Wi, Ho, Wo, tab, tile, din):
 
 
 for _n in ("round_tf32", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd", "cross_attn_fwd",
-           "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd"):
+           "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd", "resample2d_u8"):
     globals()[_n] = _wrap(globals()[_n], _n)

@@ -636,9 +636,10 @@ __device__ __forceinline__ long long tiled_index(long long b, int y, int x, int 
     return ((b * (Ho / tile) + gy) * (Wo / tile) + gx) * (static_cast<long long>(tile) * tile) + py * tile + px;
 }
 
+template <bool U8>
 __global__ void __launch_bounds__(256) resample2d_fwd_kernel(const float* __restrict__ in, int Hi, int Wi, int Ho, int Wo, const int* __restrict__ iy,
                                                              const float* __restrict__ wy, const int* __restrict__ ix, const float* __restrict__ wx,
-                                                             int NT, int tile, float* __restrict__ out, long long total) {
+                                                             int NT, int tile, void* __restrict__ out, long long total) {
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long b = idx / (static_cast<long long>(Ho) * Wo);
@@ -651,7 +652,12 @@ __global__ void __launch_bounds__(256) resample2d_fwd_kernel(const float* __rest
             for (int c = 0; c < NT; ++c) s = fmaf(wx[x * NT + c], row[ix[x * NT + c]], s);
             acc = fmaf(wy[y * NT + a], s, acc);
         }
-        out[tiled_index(b, y, x, Ho, Wo, tile)] = acc;
+        if (U8) {
+            // torchvision.utils.save_image: mul(255).add(0.5).clamp(0, 255).to(uint8)
+            static_cast<uint8_t*>(out)[idx] = static_cast<uint8_t>(fminf(fmaxf(fmaf(acc, 255.f, 0.5f), 0.f), 255.f));
+        } else {
+            static_cast<float*>(out)[tiled_index(b, y, x, Ho, Wo, tile)] = acc;
+        }
     }
 }
 
@@ -841,8 +847,18 @@ TVS_API int tvs_resample2d_fwd(const float* in, int32_t B, int32_t Hi, int32_t W
     TVS_REQUIRE(in && out && iy && wy && ix && wx && ntaps >= 1, "tvs_resample2d_fwd: null pointer");
     TVS_REQUIRE(tile == 0 || (Ho % tile == 0 && Wo % tile == 0), "tvs_resample2d_fwd: tile must divide the output size");
     const long long total = static_cast<long long>(B) * Ho * Wo;
-    resample2d_fwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, Hi, Wi, Ho, Wo, iy, wy, ix, wx, ntaps, tile, out, total);
+    resample2d_fwd_kernel<false><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, Hi, Wi, Ho, Wo, iy, wy, ix, wx, ntaps, tile,
+                                                                                                      out, total);
     return check_launch("resample2d_fwd_kernel");
+}
+
+TVS_API int tvs_resample2d_u8(const float* in, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, const int32_t* iy, const float* wy,
+                              const int32_t* ix, const float* wx, int32_t ntaps, uint8_t* out, void* stream) {
+    TVS_REQUIRE(in && out && iy && wy && ix && wx && ntaps >= 1, "tvs_resample2d_u8: null pointer");
+    const long long total = static_cast<long long>(B) * Ho * Wo;
+    resample2d_fwd_kernel<true><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, Hi, Wi, Ho, Wo, iy, wy, ix, wx, ntaps, 0, out,
+                                                                                                     total);
+    return check_launch("resample2d_u8_kernel");
 }
 
 TVS_API int tvs_resample2d_bwd(const void* dout, int32_t dout_is_bf16, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, const int32_t* ty,

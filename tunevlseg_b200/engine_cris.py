@@ -97,27 +97,36 @@ def _mha_ops(sd, prefix, heads):
     return SimpleNamespace(q=q, k=k, v=v, qk=qk, o=o, heads=heads, hd=D // heads, D=D)
 
 
-def _bicubic_tables(n_in: int, n_out: int, device):
-    """Per-output taps of torch's bicubic (A = -0.75), align_corners=True, with border clamping - and their transpose."""
-    A = -0.75
-    scale = (n_in - 1) / (n_out - 1) if n_out > 1 else 0.0
+def _bicubic_tables(n_in: int, n_out: int, device, align_corners: bool = True):
+    """Per-output taps of torch's bicubic (A = -0.75) with border clamping - and their transpose.  align_corners=True:
+    src = o (n_in - 1) / (n_out - 1); False: src = (o + 0.5) n_in / n_out - 0.5 (aten upsample_bicubic2d).  The source
+    index and the cubic coefficients are evaluated in fp32, operation for operation as aten does, so the tables
+    reproduce F.interpolate to the last bit of the weights."""
+    import numpy as np
+
+    f = np.float32
+    A = f(-0.75)
+    if align_corners:
+        scale = f(n_in - 1) / f(n_out - 1) if n_out > 1 else f(0)
+    else:
+        scale = f(n_in) / f(n_out)
     idx = torch.zeros((n_out, 4), dtype=torch.int32)
     wt = torch.zeros((n_out, 4), dtype=torch.float32)
+
+    def c1(x):          # cubic_convolution1
+        return ((A + f(2)) * x - (A + f(3))) * x * x + f(1)
+
+    def c2(x):          # cubic_convolution2
+        return ((A * x - f(5) * A) * x + f(8) * A) * x - f(4) * A
+
     for o in range(n_out):
-        src = o * scale
-        fl = math.floor(src)
-        t = src - fl
-        # torch: get_cubic_upsample_coefficients(t)
-        def c1(x):
-            return ((A + 2) * x - (A + 3)) * x * x + 1
-
-        def c2(x):
-            return ((A * x - 5 * A) * x + 8 * A) * x - 4 * A
-
-        ws = (c2(t + 1.0), c1(t), c1(1.0 - t), c2(2.0 - t))
+        src = scale * f(o) if align_corners else scale * (f(o) + f(0.5)) - f(0.5)
+        fl = int(np.floor(src))
+        t = f(src - f(fl))
+        ws = (c2(t + f(1)), c1(t), c1(f(1) - t), c2(f(2) - t))
         for a in range(4):
             idx[o, a] = min(max(fl - 1 + a, 0), n_in - 1)
-            wt[o, a] = ws[a]
+            wt[o, a] = float(ws[a])
     rev = [[] for _ in range(n_in)]
     for o in range(n_out):
         for a in range(4):
@@ -133,9 +142,9 @@ def _bicubic_tables(n_in: int, n_out: int, device):
     return idx.to(device), wt.to(device), t_idx.to(device), t_w.to(device), cnt.to(device), mt
 
 
-def resample_tables(hi, wi, ho, wo, device):
-    iy, wy, ty, twy, cy, mty = _bicubic_tables(hi, ho, device)
-    ix, wx, tx, twx, cx, mtx = _bicubic_tables(wi, wo, device)
+def resample_tables(hi, wi, ho, wo, device, align_corners: bool = True):
+    iy, wy, ty, twy, cy, mty = _bicubic_tables(hi, ho, device, align_corners)
+    ix, wx, tx, twx, cx, mtx = _bicubic_tables(wi, wo, device, align_corners)
     mt = max(mty, mtx)
 
     def padto(t):
