@@ -70,6 +70,12 @@ typedef struct tvs_gemm_args {
                                               decoder, whose rounding dominates the logit error; K, lda, ldw % 4 == 0 */
     int32_t reserved;                      /* flags; bit 0: round out_f32 to nearest tf32 (cvt.rna) - for outputs that only
                                               feed further TVS_AB_TF32 GEMMs, whose MMA truncates its operands */
+    int32_t conv_h, conv_w;                /* != 0: implicit-GEMM 3x3 convolution, stride 1, pad 1 (cris_model/layers.py:14-26,
+                                              clip.py:26-27).  A = zero-bordered channels-last image [B, H+2, W+2, C] (from
+                                              tvs_pad_nhwc), lda = C, M = B*(H+2)*(W+2), K = 9*C, W = [N, 9*C] with K ordered
+                                              (ky, kx, c).  Outputs / residual / aux are UNPADDED [B*H*W, N] matrices: the
+                                              epilogue maps rows and skips the border.  No im2col matrix ever exists: each k-block
+                                              is a TMA load of the A rows shifted by its tap's offset. */
 } tvs_gemm_args;
 
 int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);
@@ -224,6 +230,10 @@ int tvs_counter_inc(int32_t* counter_dev, void* stream);
  * clip.py:199-218 (stem), :26-27 (bottleneck conv2), layers.py:14-26 (conv_layer 3x3). */
 int tvs_im2col_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize,
                     int32_t stride, int32_t pad, void* col, int64_t ldcol, int32_t round_tf32, void* stream);
+/* xp[b, y+1, x+1, :] = x[b, y, x, :], zero border: the operand layout of the implicit-GEMM convolution above.
+ * elem_bytes 2 or 4; round_tf32 rounds f32 elements to nearest tf32 on the way. */
+int tvs_pad_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_t H, int32_t W, int32_t C, void* xp, int32_t round_tf32,
+                 void* stream);
 /* y = x rounded to nearest tf32 (cvt.rna), [M, C] f32 views.  The kind::tf32 MMA truncates its operands (a
  * systematic -3.4e-4 relative bias per GEMM that compounds over the ~60 layers of CLIP-RN50), so forward operands are
  * rounded on their way into tvs_gemm_bf16: here, or inside tvs_im2col_nhwc (round_tf32 != 0) for k x k convolutions. */

@@ -38,10 +38,22 @@ def round_tf32(x, y):
     y.copy_(_tf32_rn(x))
 
 
-def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False):
-    assert A.dtype == W.dtype and A.dim() == 2 and W.dim() == 2 and A.shape[1] == W.shape[1], (A.shape, W.shape, A.dtype, W.dtype)
+def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False, conv_hw=None):
+    assert A.dtype == W.dtype and A.dim() == 2 and W.dim() == 2, (A.shape, W.shape, A.dtype, W.dtype)
     assert A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] % (8 if A.dtype == BF16 else 4) == 0
-    v = A.float() @ W.float().t() if A.dtype == BF16 else _tf32(A) @ _tf32(W).t()
+    Ar, Wr = (A.float(), W.float()) if A.dtype == BF16 else (_tf32(A), _tf32(W))
+    if conv_hw is not None:          # implicit-GEMM 3x3 conv: A = zero-bordered image [B*(H+2)*(W+2), C], W = [N, (ky, kx, c)]
+        H_, W_ = conv_hw
+        C, N = A.shape[1], W.shape[0]
+        assert A.is_contiguous() and W.shape[1] == 9 * C and C % (64 if A.dtype == BF16 else 32) == 0 and N % 32 == 0
+        B_ = A.shape[0] // ((H_ + 2) * (W_ + 2))
+        img = Ar.view(B_, H_ + 2, W_ + 2, C)
+        assert img[:, 0].abs().max() == 0 and img[:, -1].abs().max() == 0 and img[:, :, 0].abs().max() == 0 and img[:, :, -1].abs().max() == 0
+        v = F.conv2d(img.permute(0, 3, 1, 2), Wr.view(N, 3, 3, C).permute(0, 3, 1, 2))        # valid conv over the padded image
+        v = v.permute(0, 2, 3, 1).reshape(B_ * H_ * W_, N)
+    else:
+        assert A.shape[1] == W.shape[1]
+        v = Ar @ Wr.t()
     if bias is not None:
         assert bias.numel() == W.shape[0]
         v = v + bias
@@ -143,6 +155,12 @@ def wgrad_small(dy, x, dw):
 
 def cast_bf16(x, y):
     y.copy_(x)
+
+
+def pad_nhwc(x, B, H, W, C, xp, round_tf32=False):
+    assert x.is_contiguous() and xp.is_contiguous() and xp.shape == (B * (H + 2) * (W + 2), C)
+    v = _tf32_rn(x) if round_tf32 else x
+    xp.copy_(F.pad(v.view(B, H, W, C), (0, 0, 1, 1, 1, 1)).reshape(-1, C))
 
 
 def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col, round_tf32=False):
@@ -312,7 +330,7 @@ def head_bwd(dlogits, tconv, add_out, bias_t, ratio, blend, B, G, P, ksize, dtco
 
 def install(monkeypatch):
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "prompt_overwrite", "prompt_grad", "wgrad_small",
-                 "cast_bf16", "round_tf32", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd",
+                 "cast_bf16", "round_tf32", "pad_nhwc", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd",
                  "cross_attn_fwd", "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd", "head_fwd",
                  "head_bwd"):
         monkeypatch.setattr(abi, name, globals()[name])

@@ -35,6 +35,7 @@ class GemmArgs(Structure):
         ("pre_bf16", c_void_p), ("ldpre", c_int64),
         ("aux_bf16", c_void_p), ("ldaux", c_int64),
         ("act", c_int32), ("tile_n", c_int32), ("ab_dtype", c_int32), ("reserved", c_int32),
+        ("conv_h", c_int32), ("conv_w", c_int32),
     ]
 
 
@@ -88,6 +89,7 @@ def load():
         "tvs_counter_inc": [P, P],
         "tvs_im2col_nhwc": [P, I32, I32, I32, I32, I32, I32, I32, I32, P, I64, I32, P],
         "tvs_round_tf32": [P, I64, I64, I32, P, I64, P],
+        "tvs_pad_nhwc": [P, I32, I32, I32, I32, I32, P, I32, P],
         "tvs_col2im_nhwc": [P, I64, I32, I32, I32, I32, I32, I32, P, I64, P, I64, P],
         "tvs_relu_mask": [P, I64, P, I64, I64, I32, P, I64, P],
         "tvs_avgpool2_nhwc": [P, I32, I32, I32, I32, I32, P, I64, P],
@@ -164,9 +166,11 @@ def _chk(t: torch.Tensor | None, dtype, name: str, dim2: bool = False) -> None:
 
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=ACT_NONE,
-         tile_n=0, round_out=False):
+         tile_n=0, round_out=False, conv_hw=None):
     """C[M,N] = epilogue(A[M,K] @ W[N,K]^T); see tvs_gemm_bf16 in include/tvs_b200.h.  2-D views with a row stride
-    are accepted (ld = stride(0)).  ``round_out``: out_f32 is rounded to nearest tf32 (it only feeds further tf32 GEMMs)."""
+    are accepted (ld = stride(0)).  ``round_out``: out_f32 is rounded to nearest tf32 (it only feeds further tf32 GEMMs).
+    ``conv_hw=(H, W)``: implicit-GEMM 3x3 convolution - A is the zero-bordered image [B*(H+2)*(W+2), C] from ``pad_nhwc``,
+    W is [N, 9*C]; outputs / residual are unpadded [B*H*W, N]."""
     require_device()
     if A.dtype != W.dtype or A.dtype not in (torch.bfloat16, torch.float32):
         raise TvsError(f"gemm: A and W must both be bf16 or both f32 (tf32 MMA), got {A.dtype} / {W.dtype}")
@@ -176,12 +180,18 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     _chk(pre_bf16, torch.bfloat16, "pre_bf16", True); _chk(aux_bf16, torch.bfloat16, "aux_bf16", True)
     M, K = A.shape
     N, K2 = W.shape
-    if K != K2:
+    Mo = M
+    if conv_hw is not None:
+        H_, W_ = conv_hw
+        if K2 != 9 * K or M % ((H_ + 2) * (W_ + 2)) or not A.is_contiguous():
+            raise TvsError(f"gemm(conv): A {tuple(A.shape)} must be the contiguous padded image and W {tuple(W.shape)} = [N, 9*C]")
+        Mo, K = M // ((H_ + 2) * (W_ + 2)) * H_ * W_, K2
+    elif K != K2:
         raise TvsError(f"gemm: A is {tuple(A.shape)} but W is {tuple(W.shape)}")
     for name, t in (("residual", residual), ("out_f32", out_f32), ("out_bf16", out_bf16), ("pre_bf16", pre_bf16),
                     ("aux_bf16", aux_bf16)):
-        if t is not None and tuple(t.shape) != (M, N):
-            raise TvsError(f"gemm: {name} must be {(M, N)}, got {tuple(t.shape)}")
+        if t is not None and tuple(t.shape) != (Mo, N):
+            raise TvsError(f"gemm: {name} must be {(Mo, N)}, got {tuple(t.shape)}")
     if bias is not None and bias.numel() != N:
         raise TvsError("gemm: bias length")
     g = GemmArgs()
@@ -196,6 +206,7 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.act, g.tile_n = act, tile_n
     g.ab_dtype = 1 if A.dtype == torch.float32 else 0
     g.reserved = 1 if round_out else 0
+    g.conv_h, g.conv_w = conv_hw if conv_hw is not None else (0, 0)
     _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
 
 
@@ -414,8 +425,9 @@ def set_profiler(records: list | None) -> None:
 
 def _flops(name, args, kwargs) -> tuple[str, float]:
     if name == "gemm":
-        (M, K), N = args[0].shape, args[1].shape[0]
-        return f"{M}x{N}x{K}{'_tf32' if args[0].dtype == torch.float32 else ''}", 2.0 * M * N * K
+        M, (N, K) = args[0].shape[0], args[1].shape
+        conv = "conv3x3_" if kwargs.get("conv_hw") is not None else ""
+        return f"{conv}{M}x{N}x{K}{'_tf32' if args[0].dtype == torch.float32 else ''}", 2.0 * M * N * K
     if name == "attn_fwd":
         _, B, S, H, hd = args[:5]
         return f"B{B}S{S}H{H}d{hd}", 4.0 * B * H * S * S * hd
@@ -474,6 +486,15 @@ def round_tf32(x, y):
     if x.shape != y.shape:
         raise TvsError("round_tf32: shape mismatch")
     _ck(load().tvs_round_tf32(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], y.data_ptr(), y.stride(0), _stream()), "tvs_round_tf32")
+
+
+def pad_nhwc(x, B, H, W, C, xp, round_tf32=False):
+    """x contiguous [B*H*W, C] -> xp contiguous [B*(H+2)*(W+2), C] with a zero border (implicit-GEMM conv operand)."""
+    require_device()
+    _chk2(x, "x", (torch.float32, torch.bfloat16)); _chk2(xp, "xp", (x.dtype,))
+    if not x.is_contiguous() or not xp.is_contiguous() or tuple(x.shape) != (B * H * W, C) or tuple(xp.shape) != (B * (H + 2) * (W + 2), C):
+        raise TvsError("pad_nhwc: x must be contiguous [B*H*W, C] and xp contiguous [B*(H+2)*(W+2), C]")
+    _ck(load().tvs_pad_nhwc(x.data_ptr(), x.element_size(), B, H, W, C, xp.data_ptr(), int(round_tf32), _stream()), "tvs_pad_nhwc")
 
 
 def im2col_nhwc(x, B, H, W, C, ksize, stride, pad, col, round_tf32=False):
@@ -593,6 +614,6 @@ def resample2d_bwd(dout, B, Hi, Wi, Ho, Wo, tab, tile, din):
                                   tab["cx"].data_ptr(), tab["max_taps"], tile, din.data_ptr(), _stream()), "tvs_resample2d_bwd")
 
 
-for _n in ("round_tf32", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd", "cross_attn_fwd",
+for _n in ("round_tf32", "pad_nhwc", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd", "cross_attn_fwd",
            "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd", "resample2d_u8"):
     globals()[_n] = _wrap(globals()[_n], _n)

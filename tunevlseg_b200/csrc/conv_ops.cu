@@ -74,6 +74,26 @@ __global__ void __launch_bounds__(256) im2col_kernel(const V* __restrict__ x, V*
     }
 }
 
+// zero-bordered copy [B,H,W,C] -> [B,H+2,W+2,C] (the A operand of the implicit-GEMM 3x3 convolution), 16-byte vectors
+template <bool ROUND>
+__global__ void __launch_bounds__(256) pad_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ xp, int H, int W, int Cv, long long total) {
+    const int Wp = W + 2, Hp = H + 2;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long pix = idx / Cv;
+        const int cv = static_cast<int>(idx - pix * Cv);
+        const long long b = pix / (Hp * Wp);
+        const int rem = static_cast<int>(pix - b * (Hp * Wp));
+        const int yp = rem / Wp, xq = rem - yp * Wp;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (yp >= 1 && yp <= H && xq >= 1 && xq <= W) {
+            v = x[((b * H + (yp - 1)) * W + (xq - 1)) * Cv + cv];
+            if (ROUND) round_words(v);
+        }
+        xp[idx] = v;
+    }
+}
+
 // col2im (stride 1, pad = ks/2): dx[b,y,x,c] = sum_{ky,kx} dcol[(b, y-ky+p, x-kx+p), (ky,kx,c)], c < Cx <= Ccol,
 // optionally multiplied by the ReLU mask of the layer below (ymask > 0).  4 channels per thread.
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, long long ldcol, int H, int W, int Ccol, int Cx, int ks,
@@ -740,6 +760,21 @@ TVS_API int tvs_col2im_nhwc(const float* dcol, int64_t ldcol, int32_t B, int32_t
     col2im_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dcol, ldcol, H, W, Ccol, Cx, ksize, relu_mask, ld_mask, dx,
                                                                                        ld_dx, total);
     return check_launch("col2im_kernel");
+}
+
+TVS_API int tvs_pad_nhwc(const void* x, int32_t elem_bytes, int32_t B, int32_t H, int32_t W, int32_t C, void* xp, int32_t round_tf32,
+                         void* stream) {
+    TVS_REQUIRE(x && xp && (elem_bytes == 2 || elem_bytes == 4) && (static_cast<long long>(C) * elem_bytes) % 16 == 0,
+                "tvs_pad_nhwc: rows of C elements must be a multiple of 16 bytes");
+    TVS_REQUIRE(!round_tf32 || elem_bytes == 4, "tvs_pad_nhwc: round_tf32 needs f32 elements");
+    const int cv = C * elem_bytes / 16;
+    const long long total = static_cast<long long>(B) * (H + 2) * (W + 2) * cv;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (round_tf32)
+        pad_nhwc_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xp), H, W, cv, total);
+    else
+        pad_nhwc_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xp), H, W, cv, total);
+    return check_launch("pad_nhwc_kernel");
 }
 
 TVS_API int tvs_round_tf32(const float* x, int64_t ld_x, int64_t M, int32_t C, float* y, int64_t ld_y, void* stream) {

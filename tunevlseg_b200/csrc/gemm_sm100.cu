@@ -42,6 +42,11 @@ struct GemmEpilogue {
     int vec256_ok;   // 32-byte aligned rows for every operand -> direct 256-bit epilogue (the default)
     int staged;      // force the shared-memory staged (coalesced) epilogue
     int round_out;   // out_f32 is rounded to nearest tf32 (cvt.rna): it only feeds further kind::tf32 MMAs, which truncate
+    // implicit-GEMM 3x3 convolution (conv_wp != 0): A is a zero-bordered channels-last image [B, conv_hp, conv_wp, C] seen as
+    // a [B*hp*wp, C] matrix; k-block kb belongs to tap kb / conv_kpt and loads the A rows SHIFTED by that tap's offset
+    // in the flattened image (the physical zero border makes every interior pixel's 9 taps correct); the epilogue maps
+    // the padded row to the unpadded output row and skips border rows.
+    int conv_wp, conv_hp, conv_kpt;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -498,16 +503,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    int a_col = kb * BK, a_row = m_blk * BM;
+                    if (ep.conv_wp) {       // tap (ky, kx) = rows shifted by (ky - 1) * wp + (kx - 1); rows outside the matrix are zero-filled by TMA
+                        const int tap = kb / ep.conv_kpt;
+                        a_col = (kb - tap * ep.conv_kpt) * BK;
+                        a_row += (tap / 3 - 1) * ep.conv_wp + (tap % 3 - 1);
+                    }
                     if (!elect_one()) {
                     } else if (CL == 2) {
                         const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
                         else mbar_arrive_cluster(leader_full);
-                        tma_load_2d_cg2(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, leader_full);
+                        tma_load_2d_cg2(smem_a + stage * L::A_BYTES, &tmap_a, a_col, a_row, leader_full);
                         tma_load_2d_cg2(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN + cta_rank * (BN / 2), leader_full);   // (BN/2)-row box
                     } else {
                         mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                        tma_load_2d(smem_a + stage * L::A_BYTES, &tmap_a, kb * BK, m_blk * BM, &full_bar[stage]);
+                        tma_load_2d(smem_a + stage * L::A_BYTES, &tmap_a, a_col, a_row, &full_bar[stage]);
                         tma_load_2d(smem_b + stage * L::B_BYTES, &tmap_w, kb * BK, n_blk * BN, &full_bar[stage]);
                     }
                     __syncwarp();
@@ -573,7 +584,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
             float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + ew * EPI_WARP_FLOATS;
             const bool direct = ep.vec256_ok && !ep.staged;
-            const bool row_ok = row0 + lane < M;
+            bool row_ok = row0 + lane < M;
+            long long orow = row0 + lane;          // the row of the output (and residual / aux) matrices this accumulator row belongs to
+            if (ep.conv_wp) {
+                const int hpwp = ep.conv_hp * ep.conv_wp;
+                const long long b = orow / hpwp;
+                const int rem = static_cast<int>(orow - b * hpwp);
+                const int yp = rem / ep.conv_wp, xp = rem - yp * ep.conv_wp;
+                row_ok = row_ok && yp >= 1 && yp <= ep.conv_hp - 2 && xp >= 1 && xp <= ep.conv_wp - 2;     // border rows are padding
+                orow = (b * (ep.conv_hp - 2) + (yp - 1)) * (ep.conv_wp - 2) + (xp - 1);
+            }
             const bool extras = direct && row_ok && (ep.residual != nullptr || is_dact(ep.act));
             // a group takes PAIRS of adjacent chunks (64 columns): for the bf16 arrays a thread then reads / writes whole
             // 128-byte lines within a few hundred cycles instead of a quarter of a line per visit
@@ -586,9 +606,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 tmem_ld_32x32(t_row + c * 32, r);
                 if (direct && col0 + 32 <= N) {
                     EpiExtras ex;
-                    if (extras) load_extras(ep, row0 + lane, col0, ex);     // in flight together with the TMEM load
+                    if (extras) load_extras(ep, orow, col0, ex);     // in flight together with the TMEM load
                     tmem_ld_wait();
-                    if (row_ok) epilogue_direct(ep, r, row0 + lane, col0, ex);
+                    if (row_ok) epilogue_direct(ep, r, orow, col0, ex);
                 } else {
                     tmem_ld_wait();
                     // ragged / unaligned chunks go through the shared-memory stage, which exists once per lane quarter:
@@ -669,7 +689,7 @@ template <int BN, int STAGES, bool TF32, int CL>
 static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES, CL>;
     CUtensorMap ta, tw;
-    if (int rc = make_tmap(&ta, a.A, a.M, a.K, a.lda, BM, TF32)) return rc;
+    if (int rc = make_tmap(&ta, a.A, a.M, a.conv_h ? a.K / 9 : a.K, a.lda, BM, TF32)) return rc;
     if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN / CL, TF32)) return rc;
     auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, TF32, CL>;
     static bool attr_set = false;
@@ -765,6 +785,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.ldaux = a.ldaux;
     ep.act = a.act;
     ep.round_out = a.reserved & 1;
+    ep.conv_wp = ep.conv_hp = ep.conv_kpt = 0;
     ep.vec_ok = vec_ok ? 1 : 0;
     auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
     ep.vec256_ok = ((!a.out_f32 || (a.ldo32 % 8 == 0 && al32(a.out_f32))) && (!a.out_bf16 || (a.ldo16 % 16 == 0 && al32(a.out_bf16))) &&
@@ -773,6 +794,17 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
                        ? 1 : 0;
     static const bool force_staged = [] { const char* e = getenv("TVS_GEMM_EPILOGUE"); return e && e[0] == 's'; }();
     ep.staged = force_staged ? 1 : 0;
+    if (a.conv_h) {
+        const int bk = a.ab_dtype == TVS_AB_TF32 ? BK_BYTES / 4 : BK_BYTES / 2;
+        const long long hpwp = static_cast<long long>(a.conv_h + 2) * (a.conv_w + 2);
+        TVS_REQUIRE(a.conv_h > 0 && a.conv_w > 0 && a.K % 9 == 0 && (a.K / 9) % bk == 0 && a.lda == a.K / 9,
+                    "tvs_gemm_bf16 (conv): K must be 9 * C with C a multiple of %d and lda == C (K=%d lda=%lld)", bk, a.K, (long long)a.lda);
+        TVS_REQUIRE(a.M % hpwp == 0 && hpwp < (1LL << 31), "tvs_gemm_bf16 (conv): M=%d must be B * (H+2) * (W+2)", a.M);
+        TVS_REQUIRE(ep.vec256_ok && a.N % 32 == 0 && !ep.staged, "tvs_gemm_bf16 (conv): needs N %% 32 == 0 and 32-byte aligned output rows");
+        ep.conv_wp = a.conv_w + 2;
+        ep.conv_hp = a.conv_h + 2;
+        ep.conv_kpt = (a.K / 9) / bk;
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N);
     const bool tf32 = a.ab_dtype == TVS_AB_TF32;

@@ -60,6 +60,15 @@ class ConvOp:
         self.w = tf32_rn(wp) if dtype == F32 else wp.to(dtype).contiguous()     # forward operand: rounded to nearest tf32
         self.bias = b.contiguous()
         self.w_t = wp.t().contiguous() if dgrad else None      # dgrad: tf32 truncation is far inside the gradient tolerance
+        # implicit-GEMM path (tvs_gemm_bf16 conv mode): 3x3 / stride 1 with the channel count a multiple of one k-block
+        bk = 32 if dtype == F32 else 64
+        self.implicit = k == 3 and stride == 1 and cin % bk == 0 and cout % 32 == 0
+        self.implicit_dgrad = dgrad and self.implicit and cout % 32 == 0 and cin % 32 == 0
+        if self.implicit_dgrad:
+            # dx[q] = sum_t dy[q - off(t)] W_t^T: a 3x3 convolution of dy with the taps flipped (off(8 - t) = -off(t))
+            w4 = (w * a[:, None, None, None]).permute(0, 2, 3, 1)                              # [Cout, ky, kx, Cin]
+            self.w_dg = w4.flip(1, 2).permute(3, 1, 2, 0).reshape(cin, 9 * cout).contiguous()  # [Cin, (ky', kx', Cout)]
+            self.w_t = None
 
 
 class LinearOp:
@@ -304,6 +313,14 @@ def _conv_nograd(op: ConvOp, x, B, H, W, *, residual=None, act=None, x_rounded=F
     by the producer (``x_rounded``), inside im2col, or by an explicit pass; ``round_out`` rounds this conv's output in the
     GEMM epilogue for its consumers."""
     f32 = x.dtype == F32
+    if op.implicit:
+        xp = _e((B * (H + 2) * (W + 2), op.cin), x.dtype, x)
+        abi.pad_nhwc(x, B, H, W, op.cin, xp, round_tf32=f32 and not x_rounded)
+        y = _e((B * H * W, op.cout), x.dtype, x)
+        abi.gemm(xp, op.w, bias=op.bias, residual=None if residual is None else residual.to(F32), out_f32=y if f32 else None,
+                 out_bf16=None if f32 else y, act=(abi.ACT_RELU if op.relu else abi.ACT_NONE) if act is None else act,
+                 round_out=round_out and f32, conv_hw=(H, W))
+        return y, H, W
     if op.k == 1 and op.stride == 1:
         A, Ho, Wo = (rn_act(x) if (f32 and not x_rounded) else x), H, W
     else:
@@ -376,13 +393,18 @@ class ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, op: ConvOp, B, H, W):
         x = x.contiguous()
+        conv_hw = None
         if op.k == 1:
             A = rn_act(x)
+        elif op.implicit:                 # no im2col matrix: zero-bordered copy + shifted TMA loads inside the GEMM
+            A = _e((B * (H + 2) * (W + 2), op.cin), F32, x)
+            abi.pad_nhwc(x, B, H, W, op.cin, A, round_tf32=True)
+            conv_hw = (H, W)
         else:
             A = _e((B * H * W, op.Kp), F32, x)
             abi.im2col_nhwc(x, B, H, W, op.cin, op.k, 1, op.pad, A, round_tf32=True)
         y = _e((B * H * W, op.cout), F32, x)
-        abi.gemm(A, op.w, bias=op.bias, out_f32=y, act=abi.ACT_RELU if op.relu else abi.ACT_NONE)
+        abi.gemm(A, op.w, bias=op.bias, out_f32=y, act=abi.ACT_RELU if op.relu else abi.ACT_NONE, conv_hw=conv_hw)
         ctx.op, ctx.geom = op, (B, H, W)
         ctx.save_for_backward(y if op.relu else None)
         return y
@@ -400,6 +422,11 @@ class ConvFn(torch.autograd.Function):
         if op.k == 1:
             dx = _e((B * H * W, op.cin), F32, dy)
             abi.gemm(dz, op.w_t[: op.cin], out_f32=dx)
+        elif op.implicit_dgrad:
+            dzp = _e((B * (H + 2) * (W + 2), op.cout), F32, dy)
+            abi.pad_nhwc(dz, B, H, W, op.cout, dzp)
+            dx = _e((B * H * W, op.cin), F32, dy)
+            abi.gemm(dzp, op.w_dg, out_f32=dx, conv_hw=(H, W))
         else:
             dcol = _e((B * H * W, op.Kp), F32, dy)
             abi.gemm(dz, op.w_t, out_f32=dcol)
