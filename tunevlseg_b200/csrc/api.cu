@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tvs_b200.h"
 
@@ -38,6 +40,14 @@ int sm_count() {
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
+}
+
+// Programmatic dependent launch, see common.cuh.  Off unless TVS_PDL=1: measured on the MaPLe step (B200, one CUDA
+// graph of ~640 kernel nodes) it changes nothing - 11.41 / 11.29 ms with, 11.35 / 11.32 ms without - so the inter-kernel
+// gap is not what the step is waiting for; the plumbing stays for kernels with longer prologues.
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("TVS_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 
 }  // namespace tvs

@@ -124,6 +124,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tb = *tmem_slot;
+    pdl_wait();        // set-up above is private; q / k / v (and dO, lse, delta) come from the preceding kernels
+    pdl_trigger();
 
     if (warp == 4) {
         // ------------------------------------------------------------------ TMA producer
@@ -476,6 +478,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tb = *tmem_slot;
+    pdl_wait();        // set-up above is private; q / k / v (and dO, lse, delta) come from the preceding kernels
+    pdl_trigger();
 
     if (warp == 4) {
         const int cq = h * AHD, ck = E + h * AHD, cv = 2 * E + h * AHD;
@@ -673,7 +677,7 @@ static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, const CUtens
         attr_set = true;
     }
     dim3 grid((S + AT - 1) / AT, H, B);
-    kern<<<grid, ATC_THREADS, L::TOTAL, st>>>(mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv);
+    TVS_CUDA(launch_pdl(kern, grid, dim3(ATC_THREADS), L::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv));
     return check_launch(MODE == MODE_FWD ? "attn_tc_kernel<fwd>" : (MODE == MODE_DQ ? "attn_tc_kernel<dq>" : "attn_tc_kernel<dkv>"));
 }
 
@@ -694,7 +698,7 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
         attr_set = true;
     }
     dim3 grid((S + AT - 1) / AT, H, B);
-    attn_tc_fwd_kernel<<<grid, ATC_THREADS, FwdSmem::TOTAL, st>>>(mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse);
+    TVS_CUDA(launch_pdl(attn_tc_fwd_kernel, grid, dim3(ATC_THREADS), FwdSmem::TOTAL, st, 1, mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse));
     return check_launch("attn_tc_fwd_kernel");
 }
 

@@ -31,6 +31,43 @@ int check_launch(const char* what);
 
 int sm_count();
 
+// ---- programmatic dependent launch ----
+// A step is ~500 kernels of 5-100 us inside one CUDA graph; the drain -> launch -> prologue gap between two of them is
+// ~2 us.  Kernels launched through launch_pdl() may become resident while their predecessor in the stream is still
+// running: they do their private prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in
+// pdl_wait() until the predecessor has completed and its writes are visible.  Only kernels that call pdl_wait() before
+// their first global-memory access may be launched this way.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- small device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -495,6 +495,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();        // everything above is private set-up; from here on the kernel reads what its predecessor wrote
+    pdl_trigger();
 
     if (warp == 0) {
         {
@@ -700,23 +702,7 @@ static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaSt
     const int tiles = (((a.M + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
     const int max_clusters = sm_count() / CL;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    if (CL == 1) {
-        kern<<<clusters, GEMM_THREADS, L::TOTAL, stream>>>(ta, tw, a.M, a.N, a.K, ep);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(clusters * CL);
-        cfg.blockDim = dim3(GEMM_THREADS);
-        cfg.dynamicSmemBytes = L::TOTAL;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CL;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        TVS_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, a.M, a.N, a.K, ep));
-    }
+    TVS_CUDA(launch_pdl(kern, dim3(clusters * CL), dim3(GEMM_THREADS), L::TOTAL, stream, CL, ta, tw, a.M, a.N, a.K, ep));
     return check_launch("gemm_bf16_tcgen05_kernel");
 }
 

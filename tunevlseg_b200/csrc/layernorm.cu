@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M,
                      int D, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      int round_out) {
+    pdl_wait();
+    pdl_trigger();
     const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add,
                      long long M, int D, float* dx32, __nv_bfloat16* __restrict__ dx16) {
+    pdl_wait();
+    pdl_trigger();
     const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -128,11 +132,11 @@ extern "C" __attribute__((visibility("default"))) int tvs_layernorm_fwd(const fl
     TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_fwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
     const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
     if (D <= 1024)
-        layernorm_fwd_kernel<8><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
-                                                                                               static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32);
+        TVS_CUDA(launch_pdl(layernorm_fwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1, x, gamma, beta, eps,
+                            static_cast<long long>(M), D, y_f32, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
     else
-        layernorm_fwd_kernel<16><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, eps, M, D, y_f32,
-                                                                                                static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32);
+        TVS_CUDA(launch_pdl(layernorm_fwd_kernel<16>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1, x, gamma, beta, eps,
+                            static_cast<long long>(M), D, y_f32, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
     return check_launch("layernorm_fwd_kernel");
 }
 
@@ -145,12 +149,12 @@ extern "C" __attribute__((visibility("default"))) int tvs_layernorm_bwd(const vo
     TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_bwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
     const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
     if (D <= 1024)
-        layernorm_bwd_kernel<8><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, M, D, dx_out_f32,
-            static_cast<__nv_bfloat16*>(dx_out_bf16));
+        TVS_CUDA(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1,
+                            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, static_cast<long long>(M), D,
+                            dx_out_f32, static_cast<__nv_bfloat16*>(dx_out_bf16)));
     else
-        layernorm_bwd_kernel<16><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, M, D, dx_out_f32,
-            static_cast<__nv_bfloat16*>(dx_out_bf16));
+        TVS_CUDA(launch_pdl(layernorm_bwd_kernel<16>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1,
+                            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, static_cast<long long>(M), D,
+                            dx_out_f32, static_cast<__nv_bfloat16*>(dx_out_bf16)));
     return check_launch("layernorm_bwd_kernel");
 }
