@@ -276,14 +276,24 @@ __device__ __forceinline__ void bilin(int dst, int P, int G, int& i0, int& i1, f
 
 constexpr int HEAD_MAXK = 7;   // ksize <= 7
 
-// grid (G /*patch row gy*/, B); 256 threads; smem: addmap rows gy-1..gy+1  [3][G][KK]
-__global__ void __launch_bounds__(256)
+// grid (G /*patch row gy*/, B); HEAD_THREADS threads; thread X owns one image column of the P pixel rows of this patch row.
+// The additive branch is evaluated separably: the bilinear weights along x depend only on (X, kx), so the contraction
+// over ky and the interpolation along y are done ONCE per pixel row into T[xi][kx] (G*ks values, cooperatively), and a
+// pixel then needs 2*ks shared-memory reads instead of 4*ks*ks (the first version was LDS/ALU bound at 187 us; the
+// kernel's traffic - tconv in, logits (+ add_out) out - is worth ~10 us).
+constexpr int HEAD_THREADS = 512;     // upper bound; the launch uses the image width rounded up to a warp
+__global__ void __launch_bounds__(HEAD_THREADS)
 head_fwd_kernel(const float* __restrict__ tconv, long long ld_t, const float* __restrict__ addmap, long long ld_a, const float* __restrict__ bias_t,
                 const float* __restrict__ bias_a, const float* __restrict__ ratio, int blend, int G, int P, int ks, float* __restrict__ logits,
                 float* __restrict__ add_out) {
-    extern __shared__ float s_add[];
+    extern __shared__ float s_head[];
     const int gy = blockIdx.x, b = blockIdx.y;
     const int KK = ks * ks, W = G * P, half = (ks - 1) / 2;
+    float* s_add = s_head;                          // [3][G][KK]  addmap rows gy-1 .. gy+1 (clamped)
+    float* s_T = s_add + 3 * G * KK;                // [2][G][ks]  double-buffered per pixel row
+    int* s_y0 = reinterpret_cast<int*>(s_T + 2 * G * ks);       // [P][ks] row taps relative to gy-1
+    int* s_y1 = s_y0 + P * ks;
+    float* s_wy = reinterpret_cast<float*>(s_y1 + P * ks);
     float wa = 1.f, wb = 0.f;
     if (blend == 1) { const float r = *ratio; wa = 1.f - r; wb = r; }
     else if (blend == 2) { wa = 1.f; wb = 1.f; }
@@ -293,43 +303,60 @@ head_fwd_kernel(const float* __restrict__ tconv, long long ld_t, const float* __
             const int yi = min(max(gy - 1 + ry, 0), G - 1);
             s_add[i] = addmap[(static_cast<long long>(b) * G * G + yi * G + xi) * ld_a + k];
         }
-        __syncthreads();
+        for (int i = threadIdx.x; i < P * ks; i += blockDim.x) {
+            const int py = i / ks, ky = i - py * ks;
+            const int Yc = min(max(gy * P + py + ky - half, 0), W - 1);       // square images: H == W
+            int y0, y1;
+            float wy;
+            bilin(Yc, P, G, y0, y1, wy);
+            s_y0[i] = min(max(y0 - (gy - 1), 0), 2);
+            s_y1[i] = min(max(y1 - (gy - 1), 0), 2);
+            s_wy[i] = wy;
+        }
     }
     const float bt = bias_t ? *bias_t : 0.f;
     const float ba = (blend != 0 && bias_a) ? *bias_a : 0.f;
-    for (int i = threadIdx.x; i < P * W; i += blockDim.x) {
-        const int py = i / W, X = i % W;
+    const int X = threadIdx.x;
+    int x0[HEAD_MAXK], x1[HEAD_MAXK];
+    float wx[HEAD_MAXK];
+    if (blend != 0 && X < W) {
+#pragma unroll
+        for (int kx = 0; kx < HEAD_MAXK; ++kx)
+            if (kx < ks) bilin(min(max(X + kx - half, 0), W - 1), P, G, x0[kx], x1[kx], wx[kx]);
+    }
+    const int gx = X / P, px = X - gx * P;
+    __syncthreads();
+    for (int py = 0; py < P; ++py) {
         const int Y = gy * P + py;
-        const int gx = X / P, px = X % P;
-        float v = wa * (tconv[(static_cast<long long>(b) * G * G + gy * G + gx) * ld_t + py * P + px] + bt);
+        float* T = s_T + (py & 1) * G * ks;
         if (blend != 0) {
-            int y0[HEAD_MAXK], y1[HEAD_MAXK];
-            float wy[HEAD_MAXK];
-            for (int ky = 0; ky < ks; ++ky) {
-                const int Yc = min(max(Y + ky - half, 0), W - 1);   // square images: H == W
-                bilin(Yc, P, G, y0[ky], y1[ky], wy[ky]);
-                y0[ky] = min(max(y0[ky] - (gy - 1), 0), 2);
-                y1[ky] = min(max(y1[ky] - (gy - 1), 0), 2);
-            }
-            float acc = 0.f;
-            for (int kx = 0; kx < ks; ++kx) {
-                const int Xc = min(max(X + kx - half, 0), W - 1);
-                int x0, x1;
-                float wx;
-                bilin(Xc, P, G, x0, x1, wx);
+            for (int i = threadIdx.x; i < G * ks; i += blockDim.x) {
+                const int xi = i / ks, kx = i - xi * ks;
+                float acc = 0.f;
                 for (int ky = 0; ky < ks; ++ky) {
-                    const int k = ky * ks + kx;
-                    const float v00 = s_add[(y0[ky] * G + x0) * KK + k], v01 = s_add[(y0[ky] * G + x1) * KK + k];
-                    const float v10 = s_add[(y1[ky] * G + x0) * KK + k], v11 = s_add[(y1[ky] * G + x1) * KK + k];
-                    const float top = v00 + wx * (v01 - v00), bot = v10 + wx * (v11 - v10);
-                    acc += top + wy[ky] * (bot - top);
+                    const float lo = s_add[(s_y0[py * ks + ky] * G + xi) * KK + ky * ks + kx];
+                    const float hi = s_add[(s_y1[py * ks + ky] * G + xi) * KK + ky * ks + kx];
+                    acc += lo + s_wy[py * ks + ky] * (hi - lo);
                 }
+                T[i] = acc;
             }
-            acc += ba;
-            if (add_out) add_out[(static_cast<long long>(b) * W + Y) * W + X] = acc;
-            v += wb * acc;
+            __syncthreads();      // T of this row is complete; the other buffer is free for the next row
         }
-        logits[(static_cast<long long>(b) * W + Y) * W + X] = v;
+        if (X < W) {
+            float v = wa * (tconv[(static_cast<long long>(b) * G * G + gy * G + gx) * ld_t + py * P + px] + bt);
+            if (blend != 0) {
+                float acc = ba;
+#pragma unroll
+                for (int kx = 0; kx < HEAD_MAXK; ++kx)
+                    if (kx < ks) {
+                        const float lo = T[x0[kx] * ks + kx], hi = T[x1[kx] * ks + kx];
+                        acc += lo + wx[kx] * (hi - lo);
+                    }
+                if (add_out) add_out[(static_cast<long long>(b) * W + Y) * W + X] = acc;
+                v += wb * acc;
+            }
+            logits[(static_cast<long long>(b) * W + Y) * W + X] = v;
+        }
     }
 }
 
@@ -386,39 +413,70 @@ __device__ __forceinline__ float bilin_weight_on(int dst_clamped, int P, int G, 
     return w;
 }
 
+// grid (G /*yi*/, B), 256 threads.  w(c; t) = bilinear weight with which clamped coordinate c reads low-res index t; it is
+// tabulated once per block for every t over the 2P + 2 coordinates that can touch it (the image is square, so the same
+// table serves x and y).  Step 1 walks each (pixel row, xi) once and feeds all ks column taps from that table (pixel rows
+// staged through shared memory in coalesced chunks); step 2 contracts over the pixel rows.  The first version evaluated
+// the weight (a float division) per (row, xi, kx, X) and read dlogits uncoalesced: 200 us for ~25 us of work.
+constexpr int HB_CHUNK = 8;
 __global__ void __launch_bounds__(256)
 head_bwd_addmap_kernel(const float* __restrict__ dlogits, const float* __restrict__ ratio, int blend, int G, int P, int ks,
                        float* __restrict__ daddmap, long long ld_da) {
-    extern __shared__ float s_T[];   // [NR][G][ks]
+    extern __shared__ float s_hb[];
     const int yi = blockIdx.x, b = blockIdx.y;
     const int W = G * P, half = (ks - 1) / 2;
+    const int TW = 2 * P + 2;                                   // coordinates base(t) .. base(t) + TW - 1 can read index t
+    float* s_T = s_hb;                                          // [NRmax][G][ks]
+    const int NRmax = 2 * P + ks + 2;
+    float* s_w = s_T + NRmax * G * ks;                          // [G][TW]
+    float* s_dl = s_w + G * TW;                                 // [HB_CHUNK][W]
     float wb = 1.f;
     if (blend == 1) wb = *ratio;
+    for (int i = threadIdx.x; i < G * TW; i += blockDim.x) {
+        const int t = i / TW, c = t * P - P / 2 - 1 + (i - t * TW);
+        s_w[i] = (c >= 0 && c < W) ? bilin_weight_on(c, P, G, t) : 0.f;
+    }
     // rows Y whose clamped shifted coordinate can have bilinear support on yi
     const int Ylo = max(yi * P - P / 2 - half - 1, 0);
     const int Yhi = min(yi * P + P + P / 2 + half, W - 1);
     const int NR = Yhi - Ylo + 1;
     const float* dl = dlogits + static_cast<long long>(b) * W * W;
-    for (int i = threadIdx.x; i < NR * G * ks; i += blockDim.x) {
-        const int kx = i % ks, xi = (i / ks) % G, yr = i / (ks * G);
-        const int Y = Ylo + yr;
-        const int Xlo = max(xi * P - P / 2 - half - 1, 0), Xhi = min(xi * P + P + P / 2 + half, W - 1);
-        float acc = 0.f;
-        for (int X = Xlo; X <= Xhi; ++X) {
-            const int Xc = min(max(X + kx - half, 0), W - 1);
-            const float w = bilin_weight_on(Xc, P, G, xi);
-            if (w != 0.f) acc += w * dl[static_cast<long long>(Y) * W + X];
+    for (int r0 = 0; r0 < NR; r0 += HB_CHUNK) {
+        const int nr = min(HB_CHUNK, NR - r0);
+        __syncthreads();                                         // table ready / previous chunk consumed
+        for (int i = threadIdx.x; i < nr * W; i += blockDim.x) s_dl[i] = dl[static_cast<long long>(Ylo + r0) * W + i];
+        __syncthreads();
+        for (int task = threadIdx.x; task < nr * G; task += blockDim.x) {
+            const int yr = task / G, xi = task - yr * G;
+            const int base = xi * P - P / 2 - 1;
+            const int Xlo = max(base - half, 0), Xhi = min(base + TW - 1 + half, W - 1);
+            float acc[HEAD_MAXK];
+#pragma unroll
+            for (int kx = 0; kx < HEAD_MAXK; ++kx) acc[kx] = 0.f;
+            const float* row = s_dl + yr * W;
+            const float* wt = s_w + xi * TW;
+            for (int X = Xlo; X <= Xhi; ++X) {
+                const float g = row[X];
+#pragma unroll
+                for (int kx = 0; kx < HEAD_MAXK; ++kx)
+                    if (kx < ks) {
+                        const int rel = min(max(X + kx - half, 0), W - 1) - base;
+                        if (rel >= 0 && rel < TW) acc[kx] = fmaf(wt[rel], g, acc[kx]);
+                    }
+            }
+#pragma unroll
+            for (int kx = 0; kx < HEAD_MAXK; ++kx)
+                if (kx < ks) s_T[((r0 + yr) * G + xi) * ks + kx] = acc[kx];
         }
-        s_T[i] = acc;
     }
     __syncthreads();
+    const int ybase = yi * P - P / 2 - 1;
     for (int i = threadIdx.x; i < G * ks * ks; i += blockDim.x) {
         const int kx = i % ks, ky = (i / ks) % ks, xi = i / (ks * ks);
         float acc = 0.f;
         for (int yr = 0; yr < NR; ++yr) {
-            const int Yc = min(max(Ylo + yr + ky - half, 0), W - 1);
-            const float w = bilin_weight_on(Yc, P, G, yi);
-            if (w != 0.f) acc += w * s_T[(yr * G + xi) * ks + kx];
+            const int rel = min(max(Ylo + yr + ky - half, 0), W - 1) - ybase;
+            if (rel >= 0 && rel < TW) acc = fmaf(s_w[yi * TW + rel], s_T[(yr * G + xi) * ks + kx], acc);
         }
         daddmap[(static_cast<long long>(b) * G * G + yi * G + xi) * ld_da + ky * ks + kx] = wb * acc;
     }
@@ -529,10 +587,12 @@ extern "C" __attribute__((visibility("default"))) int tvs_head_fwd(const float* 
     TVS_REQUIRE(blend >= 0 && blend <= 2, "tvs_head_fwd: blend must be 0, 1 or 2");
     TVS_REQUIRE(blend == 0 || (addmap && ksize >= 1 && ksize <= HEAD_MAXK && (ksize & 1)), "tvs_head_fwd: additive branch needs addmap and odd ksize <= %d", HEAD_MAXK);
     TVS_REQUIRE(blend != 1 || ratio, "tvs_head_fwd: ratio required for blend=1");
-    const size_t sh = blend ? static_cast<size_t>(3) * G * ksize * ksize * sizeof(float) : 0;
+    TVS_REQUIRE(G * P <= HEAD_THREADS, "tvs_head_fwd: image width %d exceeds the %d columns one block covers", G * P, HEAD_THREADS);
+    const size_t sh = blend ? (static_cast<size_t>(3) * G * ksize * ksize + 2 * G * ksize + 3 * P * ksize) * sizeof(float) : 0;
     TVS_REQUIRE(sh <= 48 * 1024, "tvs_head_fwd: grid too large for the shared-memory neighbourhood");
-    head_fwd_kernel<<<dim3(G, B), 256, sh, static_cast<cudaStream_t>(stream)>>>(tconv, ld_tconv, addmap, ld_addmap, bias_t, bias_a, ratio, blend, G, P,
-                                                                               ksize, logits, add_out);
+    const int threads = max(128, (G * P + 31) / 32 * 32);
+    head_fwd_kernel<<<dim3(G, B), threads, sh, static_cast<cudaStream_t>(stream)>>>(tconv, ld_tconv, addmap, ld_addmap, bias_t, bias_a, ratio, blend, G, P,
+                                                                                   ksize, logits, add_out);
     return check_launch("head_fwd_kernel");
 }
 
@@ -549,7 +609,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_head_bwd(const float* 
     if (blend != 0 && daddmap) {
         TVS_REQUIRE(ksize >= 1 && ksize <= HEAD_MAXK && (ksize & 1), "tvs_head_bwd: odd ksize <= %d", HEAD_MAXK);
         const int nr = 2 * P + ksize + 2;
-        const size_t sh = static_cast<size_t>(nr) * G * ksize * sizeof(float);
+        const size_t sh = (static_cast<size_t>(nr) * G * ksize + static_cast<size_t>(G) * (2 * P + 2) + static_cast<size_t>(HB_CHUNK) * G * P) * sizeof(float);
         TVS_REQUIRE(sh <= 48 * 1024, "tvs_head_bwd: shared-memory tile too large");
         head_bwd_addmap_kernel<<<dim3(G, B), 256, sh, st>>>(dlogits, ratio, blend, G, P, ksize, daddmap, ld_daddmap);
         return check_launch("head_bwd_addmap_kernel");
