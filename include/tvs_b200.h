@@ -288,6 +288,20 @@ int tvs_resample2d_bwd(const void* dout, int32_t dout_is_bf16, int32_t B, int32_
                        int32_t Wo, const int32_t* ty, const float* twy, const int32_t* cy, const int32_t* tx,
                        const float* twx, const int32_t* cx, int32_t max_taps, int32_t tile, float* din, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused feed-forward block of the CLIPSeg decoder layer (reduce_dim 64): CLIPSegMLP inside CLIPSegDecoderLayer,
+ * hf::341-354 called from hf::421-431, with the residual of the post-LN block.  The [M, F] hidden activation stays in
+ * tensor memory.   fwd: out = x + relu(x W1^T + b1) W2^T + b2       bwd (dgrad only): dx = g + ((g W2) o [x W1^T + b1 > 0]) W1
+ * x, g, out, dx: f32 [M, 64]; w1_hi / w1_lo: bf16 [F, 64] head and tail of fc1.weight (w = hi + lo);
+ * w2t_hi / w2t_lo: bf16 [F, 64] head and tail of fc2.weight^T; both tails NULL = single bf16 products.
+ * With the tails every product is hi*hi + lo*hi + hi*lo in fp32 accumulation (~2^-17 relative).
+ * F must be a multiple of 64, <= 4096.
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_ffn64_fwd(const float* x, const void* w1_hi, const void* w1_lo, const void* w2t_hi, const void* w2t_lo,
+                  const float* b1, const float* b2, int64_t M, int32_t D, int32_t F, float* out, void* stream);
+int tvs_ffn64_bwd(const float* x, const float* g, const void* w1_hi, const void* w1_lo, const void* w2t_hi,
+                  const void* w2t_lo, const float* b1, int64_t M, int32_t D, int32_t F, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -392,6 +392,77 @@ static void test_attn() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused decoder FFN (D = 64)
+// ------------------------------------------------------------------------------------------------
+static void ffn_case(int M, int F, bool split, bool timeit = false) {
+    const int D = 64;
+    std::vector<float> x((size_t)M * D), g((size_t)M * D), w1((size_t)F * D), w2t((size_t)F * D), b1(F), b2(D);
+    for (auto& v : x) v = frand();
+    for (auto& v : g) v = frand();
+    for (auto& v : w1) v = frand(0.125f);
+    for (auto& v : w2t) v = frand(0.03f);
+    for (auto& v : b1) v = frand(0.3f);
+    for (auto& v : b2) v = frand(0.3f);
+    auto hi1 = to_bf16(w1), hi2 = to_bf16(w2t);
+    std::vector<float> r1(w1.size()), r2(w2t.size());
+    for (size_t i = 0; i < w1.size(); ++i) { r1[i] = w1[i] - bf(hi1[i]); r2[i] = w2t[i] - bf(hi2[i]); }
+    auto lo1 = to_bf16(r1), lo2 = to_bf16(r2);
+    float *dx = dev(x), *dg = dev(g), *db1 = dev(b1), *db2 = dev(b2);
+    __nv_bfloat16 *dh1 = dev(hi1), *dh2 = dev(hi2), *dl1 = dev(lo1), *dl2 = dev(lo2);
+    float *dout = dev_zero<float>((size_t)M * D), *ddx = dev_zero<float>((size_t)M * D);
+    TV(tvs_ffn64_fwd(dx, dh1, split ? dl1 : nullptr, dh2, split ? dl2 : nullptr, db1, db2, M, D, F, dout, nullptr));
+    TV(tvs_ffn64_bwd(dx, dg, dh1, split ? dl1 : nullptr, dh2, split ? dl2 : nullptr, db1, M, D, F, ddx, nullptr));
+    CK(cudaDeviceSynchronize());
+    auto out = host(dout, (size_t)M * D);
+    auto gx = host(ddx, (size_t)M * D);
+    double e_f = 0, e_b = 0, n_f = 0, n_b = 0;
+    const int step = M > 2000 ? 97 : 1;       // sample rows of the big case
+    std::vector<double> h(F), dh(F);
+    for (int m = 0; m < M; m += step) {
+        for (int f = 0; f < F; ++f) {
+            double s = b1[f], d = 0;
+            for (int k = 0; k < D; ++k) { s += (double)x[(size_t)m * D + k] * w1[(size_t)f * D + k]; d += (double)g[(size_t)m * D + k] * w2t[(size_t)f * D + k]; }
+            h[f] = s > 0 ? s : 0;
+            dh[f] = fabs(s) < (split ? 1e-4 : 6e-2) ? NAN : (s > 0 ? d : 0);       // mask decided within rounding distance of 0: skip the row
+        }
+        bool skip = false;
+        for (int f = 0; f < F; ++f) if (std::isnan(dh[f])) skip = true;
+        for (int k = 0; k < D; ++k) {
+            double o = b2[k] + x[(size_t)m * D + k], dd = g[(size_t)m * D + k];
+            for (int f = 0; f < F; ++f) { o += h[f] * w2t[(size_t)f * D + k]; if (!skip) dd += dh[f] * w1[(size_t)f * D + k]; }
+            e_f = std::max(e_f, fabs(o - out[(size_t)m * D + k])); n_f = std::max(n_f, fabs(o));
+            if (!skip) { e_b = std::max(e_b, fabs(dd - gx[(size_t)m * D + k])); n_b = std::max(n_b, fabs(dd)); }
+        }
+    }
+    char name[128];
+    snprintf(name, sizeof name, "ffn64 M=%d F=%d %s fwd (max |ref| %.2f)", M, F, split ? "split" : "bf16", n_f); report(name, e_f, split ? 2e-4 : 5e-2);
+    snprintf(name, sizeof name, "ffn64 M=%d F=%d %s bwd (max |ref| %.2f)", M, F, split ? "split" : "bf16", n_b); report(name, e_b, split ? 2e-4 : 5e-2);
+    if (timeit) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        float ms;
+        const int reps = 20;
+        CK(cudaEventRecord(e0));
+        for (int it = 0; it < reps; ++it) TV(tvs_ffn64_fwd(dx, dh1, split ? dl1 : nullptr, dh2, split ? dl2 : nullptr, db1, db2, M, D, F, dout, nullptr));
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("    timing fwd: %.1f us/launch\n", ms * 1e3 / reps);
+        CK(cudaEventRecord(e0));
+        for (int it = 0; it < reps; ++it) TV(tvs_ffn64_bwd(dx, dg, dh1, split ? dl1 : nullptr, dh2, split ? dl2 : nullptr, db1, M, D, F, ddx, nullptr));
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("    timing bwd: %.1f us/launch\n", ms * 1e3 / reps);
+    }
+    cudaFree(dx); cudaFree(dg); cudaFree(db1); cudaFree(db2); cudaFree(dh1); cudaFree(dh2); cudaFree(dl1); cudaFree(dl2); cudaFree(dout); cudaFree(ddx);
+}
+static void test_ffn(bool timeit) {
+    ffn_case(128, 64, true);
+    ffn_case(128, 64, false);
+    ffn_case(300, 256, true);
+    ffn_case(300, 256, false);
+    ffn_case(15648, 2048, true, timeit);
+    ffn_case(15648, 2048, false, timeit);
+}
+
+// ------------------------------------------------------------------------------------------------
 // layernorm
 // ------------------------------------------------------------------------------------------------
 static void ln_case(int M, int D) {
@@ -441,6 +512,37 @@ static void ln_case(int M, int D) {
     snprintf(name, sizeof name, "layernorm M=%d D=%d fwd bf16", M, D); report(name, e2, 4e-2);
     snprintf(name, sizeof name, "layernorm M=%d D=%d bwd f32", M, D); report(name, e3, 1e-4);
     cudaFree(dx); cudaFree(dg); cudaFree(db); cudaFree(ddy); cudaFree(dadd); cudaFree(dy32); cudaFree(dy16); cudaFree(dmean); cudaFree(drstd); cudaFree(ddx); cudaFree(ddx16);
+}
+// timing of the vision-tower LayerNorm shape over rotating buffer sets (each set 192 MB; three sets exceed the L2)
+static void ln_timing(int M, int D) {
+    const int NSET = 3;
+    const size_t n = (size_t)M * D;
+    float *x[NSET], *add[NSET], *o32[NSET], *mean, *rstd, *g, *b;
+    __nv_bfloat16 *dy[NSET], *o16[NSET];
+    std::vector<float> hx(n), hg(D, 1.f);
+    for (auto& v : hx) v = frand(2.f);
+    for (int s = 0; s < NSET; ++s) {
+        x[s] = dev(hx); add[s] = dev(hx); o32[s] = dev_zero<float>(n);
+        dy[s] = dev(to_bf16(hx)); o16[s] = dev_zero<__nv_bfloat16>(n);
+    }
+    g = dev(hg); b = dev(hg); mean = dev_zero<float>(M); rstd = dev_zero<float>(M);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float ms;
+    const int reps = 30;
+    for (int it = 0; it < 3; ++it) TV(tvs_layernorm_fwd(x[it], g, b, 1e-5f, M, D, nullptr, o16[it], mean, rstd, 0, nullptr));
+    CK(cudaEventRecord(e0));
+    for (int it = 0; it < reps; ++it) TV(tvs_layernorm_fwd(x[it % NSET], g, b, 1e-5f, M, D, nullptr, o16[it % NSET], mean, rstd, 0, nullptr));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("    layernorm fwd  M=%d D=%d: %.1f us/launch, %.0f GB/s (6 B/elem)\n", M, D, ms * 1e3 / reps, 6.0 * n / (ms * 1e-3 / reps) * 1e-9);
+    for (int it = 0; it < 3; ++it) TV(tvs_layernorm_bwd(dy[it], nullptr, x[it], g, mean, rstd, add[it], M, D, o32[it], o16[it], nullptr));
+    CK(cudaEventRecord(e0));
+    for (int it = 0; it < reps; ++it)
+        TV(tvs_layernorm_bwd(dy[it % NSET], nullptr, x[it % NSET], g, mean, rstd, add[it % NSET], M, D, o32[it % NSET], o16[it % NSET], nullptr));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("    layernorm bwd  M=%d D=%d: %.1f us/launch, %.0f GB/s (16 B/elem)\n", M, D, ms * 1e3 / reps, 16.0 * n / (ms * 1e-3 / reps) * 1e-9);
+    for (int s = 0; s < NSET; ++s) { cudaFree(x[s]); cudaFree(add[s]); cudaFree(o32[s]); cudaFree(dy[s]); cudaFree(o16[s]); }
+    cudaFree(g); cudaFree(b); cudaFree(mean); cudaFree(rstd);
 }
 static void test_ln() {
     ln_case(37, 768);
@@ -546,6 +648,8 @@ int main(int argc, char** argv) {
     if (what == "ln" || what == "all") test_ln();
     if (what == "attn" || what == "all") test_attn();
     if (what == "gemm" || what == "all") test_gemm();
+    if (what == "ffn" || what == "all") test_ffn(what == "ffn");
+    if (what == "lnprof") { ln_case(37, 768); ln_case(5, 512); ln_case(33, 256); ln_case(1003, 64); ln_case(9, 1024); ln_case(7, 2048); ln_timing(15648, 768); }
     if (what == "gemmprof") {   // epilogue cost isolation on the fc1 shape (for timing / ncu)
         const int bn = argc > 3 ? atoi(argv[3]) : 256;
         printf("-- N=3072: bf16 out only\n");

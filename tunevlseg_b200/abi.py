@@ -99,6 +99,8 @@ def load():
         "tvs_cross_attn_bwd": [P, I64, P, P, I64, P, P, P, I64, P, I32, I32, I32, I32, I32, I32, P, I64, P, P, I64, P, P],
         "tvs_dynconv_fwd": [P, P, I64, P, I64, I32, I32, I32, I32, P, P, P],
         "tvs_dynconv_bwd": [P, P, P, I64, I32, I32, I32, I32, P, P, I32, P],
+        "tvs_ffn64_fwd": [P, P, P, P, P, P, P, I64, I32, I32, P, P],
+        "tvs_ffn64_bwd": [P, P, P, P, P, P, P, I64, I32, I32, P, P],
         "tvs_resample2d_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, I32, P, P],
         "tvs_resample2d_u8": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, P, P],
         "tvs_resample2d_bwd": [P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, I32, I32, P, P],
@@ -234,6 +236,35 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_add=None, dx_f32=None, dx_bf16
         raise TvsError("dy must be bf16 or f32")
     _ck(load().tvs_layernorm_bwd(d16, d32, x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(dx_add),
                                  M, D, _p(dx_f32), _p(dx_bf16), _stream()), "tvs_layernorm_bwd")
+
+
+def ffn64_fwd(x, w1, w2t, b1, b2, out):
+    """out = x + relu(x W1^T + b1) W2^T + b2 in one kernel (decoder FFN, D = 64).  ``w1`` / ``w2t``: (hi, lo) pairs of
+    bf16 [F, 64] tensors (lo may be None for single bf16 products)."""
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(out, torch.float32, "out"); _chk(b1, torch.float32, "b1"); _chk(b2, torch.float32, "b2")
+    for t in (*w1, *w2t):
+        _chk(t, torch.bfloat16, "ffn weight")
+    M, D = x.shape
+    F = w1[0].shape[0]
+    if tuple(w1[0].shape) != (F, D) or tuple(w2t[0].shape) != (F, D) or b1.numel() != F or b2.numel() != D or out.shape != x.shape:
+        raise TvsError("ffn64_fwd: shape mismatch")
+    _ck(load().tvs_ffn64_fwd(x.data_ptr(), _p(w1[0]), _p(w1[1]), _p(w2t[0]), _p(w2t[1]), b1.data_ptr(), b2.data_ptr(), M, D, F,
+                             out.data_ptr(), _stream()), "tvs_ffn64_fwd")
+
+
+def ffn64_bwd(x, g, w1, w2t, b1, dx):
+    """dx = g + ((g W2) o [x W1^T + b1 > 0]) W1 (dgrad of ffn64_fwd including its residual)."""
+    require_device()
+    _chk(x, torch.float32, "x"); _chk(g, torch.float32, "g"); _chk(dx, torch.float32, "dx"); _chk(b1, torch.float32, "b1")
+    for t in (*w1, *w2t):
+        _chk(t, torch.bfloat16, "ffn weight")
+    M, D = x.shape
+    F = w1[0].shape[0]
+    if tuple(w1[0].shape) != (F, D) or tuple(w2t[0].shape) != (F, D) or b1.numel() != F or g.shape != x.shape or dx.shape != x.shape:
+        raise TvsError("ffn64_bwd: shape mismatch")
+    _ck(load().tvs_ffn64_bwd(x.data_ptr(), g.data_ptr(), _p(w1[0]), _p(w1[1]), _p(w2t[0]), _p(w2t[1]), b1.data_ptr(), M, D, F,
+                             dx.data_ptr(), _stream()), "tvs_ffn64_bwd")
 
 
 def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse, out_f32=None):

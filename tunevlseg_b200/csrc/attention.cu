@@ -24,6 +24,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ float ex2_fast(float x) {   // one MUFU.EX2; ex2(-inf) = 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -115,7 +120,10 @@ __device__ __forceinline__ void acc_to_afrag(const float (&s)[8][4], uint32_t (&
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int HD>
+// PLAIN: no causal mask and no key mask (the decoder's self-attention) - the per-element mask logic (a dozen integer
+// instructions per score) disappears from every full key tile; with head dim 16 those instructions, not the MMAs, were
+// the kernel (issue bound: 48 us for 2 GFLOP).
+template <int HD, bool PLAIN>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int H, int causal, const uint8_t* __restrict__ key_mask,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse) {
@@ -171,16 +179,24 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int H, int causal,
         // mask + online softmax (rows g and g+8 of this warp's 16)
         const int k0 = t * ATT_BN;
         float mx[2] = {-INFINITY, -INFINITY};
+        if (PLAIN && k0 + ATT_BN <= S) {
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
+            for (int nb = 0; nb < 8; ++nb) {
+                mx[0] = fmaxf(mx[0], fmaxf(s[nb][0], s[nb][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[nb][2], s[nb][3]));
+            }
+        } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = k0 + nb * 8 + 2 * tq + (e & 1);
-                const int q = q0 + warp * 16 + g + (e >> 1) * 8;
-                bool ok = key < S && (!causal || key <= q);
-                if (ok && km) ok = km[key] != 0;
-                s[nb][e] = ok ? s[nb][e] : -INFINITY;
-                mx[e >> 1] = fmaxf(mx[e >> 1], s[nb][e]);
+            for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int key = k0 + nb * 8 + 2 * tq + (e & 1);
+                    const int q = q0 + warp * 16 + g + (e >> 1) * 8;
+                    bool ok = key < S && (PLAIN || !causal || key <= q);
+                    if (!PLAIN && ok && km) ok = km[key] != 0;
+                    s[nb][e] = ok ? s[nb][e] : -INFINITY;
+                    mx[e >> 1] = fmaxf(mx[e >> 1], s[nb][e]);
+                }
             }
         }
         float m_use[2], corr[2];
@@ -194,11 +210,12 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int H, int causal,
             m_run[r] = m_new;
             l_run[r] *= corr[r];
         }
+        const float mL[2] = {m_use[0] * LOG2E, m_use[1] * LOG2E};
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float p = exp2f((s[nb][e] - m_use[e >> 1]) * LOG2E);
+                const float p = PLAIN ? ex2_fast(fmaf(s[nb][e], LOG2E, -mL[e >> 1])) : exp2f((s[nb][e] - m_use[e >> 1]) * LOG2E);
                 s[nb][e] = p;
                 l_run[e >> 1] += p;
             }
@@ -275,7 +292,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
 // ---------------------------------------------------------------------------------------------
 // backward: dQ (one CTA per query tile, loops over key tiles)
 // ---------------------------------------------------------------------------------------------
-template <int HD>
+template <int HD, bool PLAIN>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                    const float* __restrict__ delta, int S, int H, int causal, const uint8_t* __restrict__ key_mask,
@@ -320,6 +337,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         row_lse[r] = q < S ? lse[idx] : INFINITY;
         row_delta[r] = q < S ? delta[idx] : 0.f;
     }
+    const float lseL[2] = {row_lse[0] * LOG2E, row_lse[1] * LOG2E};
     float dq[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
@@ -347,16 +365,27 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         mma_a_tileT<HD>(s, qa, sk[buf]);
         mma_a_tileT<HD>(dp, da, sv[buf]);
         const int k0 = t * ATT_BN;
+        if (PLAIN && k0 + ATT_BN <= S) {
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
+            for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = k0 + nb * 8 + 2 * tq + (e & 1);
-                const int q = q0 + warp * 16 + g + (e >> 1) * 8;
-                bool ok = key < S && (!causal || key <= q);
-                if (ok && km) ok = km[key] != 0;
-                const float p = ok ? exp2f((s[nb][e] - row_lse[e >> 1]) * LOG2E) : 0.f;
-                s[nb][e] = p * (dp[nb][e] - row_delta[e >> 1]);
+                for (int e = 0; e < 4; ++e) {
+                    const float p = ex2_fast(fmaf(s[nb][e], LOG2E, -lseL[e >> 1]));      // lse = +inf for q >= S -> 0
+                    s[nb][e] = p * (dp[nb][e] - row_delta[e >> 1]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int key = k0 + nb * 8 + 2 * tq + (e & 1);
+                    const int q = q0 + warp * 16 + g + (e >> 1) * 8;
+                    bool ok = key < S && (PLAIN || !causal || key <= q);
+                    if (!PLAIN && ok && km) ok = km[key] != 0;
+                    const float p = ok ? exp2f((s[nb][e] - row_lse[e >> 1]) * LOG2E) : 0.f;
+                    s[nb][e] = p * (dp[nb][e] - row_delta[e >> 1]);
+                }
             }
         }
         uint32_t ds[4][4];
@@ -379,7 +408,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------
 // backward: dK, dV (one CTA per key tile, loops over query tiles; works on the transposed problem)
 // ---------------------------------------------------------------------------------------------
-template <int HD>
+template <int HD, bool PLAIN>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                     const float* __restrict__ delta, int S, int H, int causal, const uint8_t* __restrict__ key_mask,
@@ -421,7 +450,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
         load_tile<HD>(sb[buf], dob, E, t * ATT_BM, S);
         if (threadIdx.x < 64) {
             const int q = t * ATT_BM + threadIdx.x;
-            sLse[buf][threadIdx.x] = q < S ? lse_b[q] : INFINITY;
+            sLse[buf][threadIdx.x] = q < S ? (PLAIN ? lse_b[q] * LOG2E : lse_b[q]) : INFINITY;
             sDelta[buf][threadIdx.x] = q < S ? delta_b[q] : 0.f;
         }
     };
@@ -464,16 +493,30 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
         mma_a_tileT<HD>(dpt, va, sb[buf]);
         const int q0 = t * ATT_BM;
         float pt[8][4];
+        if (PLAIN) {
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
+            for (int nb = 0; nb < 8; ++nb) {
+                const float2 l2 = *reinterpret_cast<const float2*>(&sLse[buf][nb * 8 + 2 * tq]);      // pre-scaled by log2(e)
+                const float2 d2 = *reinterpret_cast<const float2*>(&sDelta[buf][nb * 8 + 2 * tq]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int qi = nb * 8 + 2 * tq + (e & 1);
-                const int key = k0 + warp * 16 + g + (e >> 1) * 8;
-                const bool ok = key_ok[e >> 1] && (!causal || key <= q0 + qi);
-                const float p = ok ? exp2f((st[nb][e] - sLse[buf][qi]) * LOG2E) : 0.f;   // lse = +inf for q >= S -> 0
-                pt[nb][e] = p;
-                st[nb][e] = p * (dpt[nb][e] - sDelta[buf][qi]);
+                for (int e = 0; e < 4; ++e) {
+                    const float p = key_ok[e >> 1] ? ex2_fast(fmaf(st[nb][e], LOG2E, -((e & 1) ? l2.y : l2.x))) : 0.f;   // lse = +inf for q >= S -> 0
+                    pt[nb][e] = p;
+                    st[nb][e] = p * (dpt[nb][e] - ((e & 1) ? d2.y : d2.x));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int qi = nb * 8 + 2 * tq + (e & 1);
+                    const int key = k0 + warp * 16 + g + (e >> 1) * 8;
+                    const bool ok = key_ok[e >> 1] && (!causal || key <= q0 + qi);
+                    const float p = ok ? exp2f((st[nb][e] - sLse[buf][qi]) * LOG2E) : 0.f;   // lse = +inf for q >= S -> 0
+                    pt[nb][e] = p;
+                    st[nb][e] = p * (dpt[nb][e] - sDelta[buf][qi]);
+                }
             }
         }
         uint32_t pf[4][4], dsf[4][4];
@@ -500,8 +543,12 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 template <int HD>
 static int attn_fwd_launch(const void* qkv, int B, int S, int H, int causal, const uint8_t* km, void* out, float* out32, float* lse, cudaStream_t st) {
     dim3 grid((S + ATT_BM - 1) / ATT_BM, H, B);
-    attn_fwd_kernel<HD><<<grid, ATT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), S, H, causal, km,
-                                                      static_cast<__nv_bfloat16*>(out), out32, lse);
+    if (!causal && !km)
+        attn_fwd_kernel<HD, true><<<grid, ATT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), S, H, 0, nullptr,
+                                                                static_cast<__nv_bfloat16*>(out), out32, lse);
+    else
+        attn_fwd_kernel<HD, false><<<grid, ATT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), S, H, causal, km,
+                                                                 static_cast<__nv_bfloat16*>(out), out32, lse);
     return check_launch("attn_fwd_kernel");
 }
 
@@ -513,11 +560,15 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
                                                                                   static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta);
     if (int rc = check_launch("attn_delta_kernel")) return rc;
     dim3 grid((S + ATT_BM - 1) / ATT_BM, H, B);
-    attn_bwd_dkv_kernel<HD><<<grid, ATT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse,
-                                                          delta, S, H, causal, km, static_cast<__nv_bfloat16*>(dqkv));
+    const __nv_bfloat16* q_ = static_cast<const __nv_bfloat16*>(qkv);
+    const __nv_bfloat16* do_ = static_cast<const __nv_bfloat16*>(dout);
+    __nv_bfloat16* dq_ = static_cast<__nv_bfloat16*>(dqkv);
+    const bool plain = !causal && !km;
+    if (plain) attn_bwd_dkv_kernel<HD, true><<<grid, ATT_THREADS, 0, st>>>(q_, do_, lse, delta, S, H, 0, nullptr, dq_);
+    else attn_bwd_dkv_kernel<HD, false><<<grid, ATT_THREADS, 0, st>>>(q_, do_, lse, delta, S, H, causal, km, dq_);
     if (int rc = check_launch("attn_bwd_dkv_kernel")) return rc;
-    attn_bwd_dq_kernel<HD><<<grid, ATT_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse,
-                                                         delta, S, H, causal, km, static_cast<__nv_bfloat16*>(dqkv));
+    if (plain) attn_bwd_dq_kernel<HD, true><<<grid, ATT_THREADS, 0, st>>>(q_, do_, lse, delta, S, H, 0, nullptr, dq_);
+    else attn_bwd_dq_kernel<HD, false><<<grid, ATT_THREADS, 0, st>>>(q_, do_, lse, delta, S, H, causal, km, dq_);
     return check_launch("attn_bwd_dq_kernel");
 }
 

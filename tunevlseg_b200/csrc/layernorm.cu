@@ -1,6 +1,8 @@
 // LayerNorm forward / backward (dgrad only), one warp per row, float4 loads, warp-shuffle reductions.
 // Replaces nn.LayerNorm on the path: transformers modeling_clipseg.py:362-365 (layer_norm1/2), :782 (pre_layrnorm),
 // :636 (final_layer_norm), :784 (post_layernorm), :395-398 (decoder post-norms).  HBM-bound: reads the fp32 row once.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tvs_b200.h"
 
@@ -66,7 +68,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     }
 }
 
-template <int MAXC>
+// VAR 0: dx_add is fetched after the reductions (two dependent DRAM round trips per row); VAR 1: every load of the row is
+// issued before the first reduction (one round trip, 24 more registers); VAR 2: VAR 1 + streaming (evict-first) hints on
+// the operands nobody re-reads (saved x, the incoming fp32 gradient stream and its fp32 successor).
+template <int MAXC, int VAR>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add,
@@ -77,25 +82,33 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
     const int nch = D >> 2;
-    const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const float4* ar = reinterpret_cast<const float4*>(dx_add ? dx_add + row * D : nullptr);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
-    float4 gg[MAXC], xh[MAXC];
+    float4 gg[MAXC], xh[MAXC], ad[VAR >= 1 ? MAXC : 1];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nch) {
+            if (dy16) {
+                const uint2 raw = VAR == 2 ? __ldcs(reinterpret_cast<const uint2*>(dy16 + row * D) + c) : reinterpret_cast<const uint2*>(dy16 + row * D)[c];
+                const float2 lo = unpack_bf16x2(raw.x), hi = unpack_bf16x2(raw.y);
+                gg[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                gg[i] = VAR == 2 ? __ldcs(reinterpret_cast<const float4*>(dy32 + row * D) + c) : reinterpret_cast<const float4*>(dy32 + row * D)[c];
+            }
+            xh[i] = VAR == 2 ? __ldcs(xr + c) : xr[c];
+            if (VAR >= 1) ad[i] = ar ? (VAR == 2 ? __ldcs(ar + c) : ar[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const float mu = mean[row], rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
         if (c < nch) {
-            float4 d;
-            if (dy16) {
-                const uint2 raw = reinterpret_cast<const uint2*>(dy16 + row * D)[c];
-                const float2 lo = unpack_bf16x2(raw.x), hi = unpack_bf16x2(raw.y);
-                d = make_float4(lo.x, lo.y, hi.x, hi.y);
-            } else {
-                d = reinterpret_cast<const float4*>(dy32 + row * D)[c];
-            }
             const float4 g = __ldg(g4 + c);
-            const float4 xv = xr[c];
+            const float4 d = gg[i], xv = xh[i];
             gg[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
             xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
             s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
@@ -113,12 +126,164 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
             o.y = rs * (gg[i].y - c1 - xh[i].y * c2);
             o.z = rs * (gg[i].z - c1 - xh[i].z * c2);
             o.w = rs * (gg[i].w - c1 - xh[i].w * c2);
-            if (dx_add) {
-                const float4 a = reinterpret_cast<const float4*>(dx_add + row * D)[c];
+            if (VAR >= 1) {
+                o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w;
+            } else if (dx_add) {
+                const float4 a = ar[c];
                 o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
             }
-            if (dx32) reinterpret_cast<float4*>(dx32 + row * D)[c] = o;
+            if (dx32) {
+                if (VAR == 2) __stcs(reinterpret_cast<float4*>(dx32 + row * D) + c, o);
+                else reinterpret_cast<float4*>(dx32 + row * D)[c] = o;
+            }
             if (dx16) reinterpret_cast<uint2*>(dx16 + row * D)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+    }
+}
+
+// VAR 3: two warps per row (64 lanes x <= 3 chunks): half the registers of VAR 1, twice the resident rows per SM; the two
+// partial sums of a row meet in shared memory.  Every load of the row is issued before the reduction.
+constexpr int LNW_ROWS = 4;     // rows per block
+template <int MAXC, int WPR>
+__global__ void __launch_bounds__(LNW_ROWS * WPR * 32)
+layernorm_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
+                          const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, const float* dx_add,
+                          long long M, int D, float* dx32, __nv_bfloat16* __restrict__ dx16) {
+    constexpr int TPR = WPR * 32;
+    __shared__ float s_part[LNW_ROWS][WPR][2];
+    pdl_wait();
+    pdl_trigger();
+    const int r = threadIdx.x / TPR, t = threadIdx.x - r * TPR, half = t >> 5;
+    const long long row = static_cast<long long>(blockIdx.x) * LNW_ROWS + r;
+    const bool ok = row < M;
+    const int nch = D >> 2;
+    const long long off = ok ? row * D : 0;
+    const float4* xr = reinterpret_cast<const float4*>(x + off);
+    const float4* ar = reinterpret_cast<const float4*>(dx_add ? dx_add + off : nullptr);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    float4 gg[MAXC], xh[MAXC], ad[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = t + TPR * i;
+        if (ok && c < nch) {
+            if (dy16) {
+                const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(dy16 + off) + c);
+                const float2 lo = unpack_bf16x2(raw.x), hi = unpack_bf16x2(raw.y);
+                gg[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                gg[i] = __ldcs(reinterpret_cast<const float4*>(dy32 + off) + c);
+            }
+            xh[i] = __ldcs(xr + c);
+            ad[i] = ar ? __ldcs(ar + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const float mu = ok ? mean[row] : 0.f, rs = ok ? rstd[row] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = t + TPR * i;
+        if (ok && c < nch) {
+            const float4 g = __ldg(g4 + c);
+            const float4 d = gg[i], xv = xh[i];
+            gg[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+            xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+            s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+            s2 += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+        }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { s_part[r][half][0] = s1; s_part[r][half][1] = s2; }
+    __syncthreads();
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) { c1 += s_part[r][w][0]; c2 += s_part[r][w][1]; }
+    c1 /= static_cast<float>(D);
+    c2 /= static_cast<float>(D);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = t + TPR * i;
+        if (ok && c < nch) {
+            float4 o;
+            o.x = rs * (gg[i].x - c1 - xh[i].x * c2) + ad[i].x;
+            o.y = rs * (gg[i].y - c1 - xh[i].y * c2) + ad[i].y;
+            o.z = rs * (gg[i].z - c1 - xh[i].z * c2) + ad[i].z;
+            o.w = rs * (gg[i].w - c1 - xh[i].w * c2) + ad[i].w;
+            if (dx32) __stcs(reinterpret_cast<float4*>(dx32 + off) + c, o);
+            if (dx16) reinterpret_cast<uint2*>(dx16 + off)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+    }
+}
+
+// forward, WPR warps per row (see layernorm_bwd_wide_kernel): more resident rows per SM than the one-warp form
+template <int MAXC, int WPR>
+__global__ void __launch_bounds__(LNW_ROWS * WPR * 32)
+layernorm_fwd_wide_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M,
+                          int D, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out, int round_out) {
+    constexpr int TPR = WPR * 32;
+    __shared__ float s_part[LNW_ROWS][WPR][2];
+    pdl_wait();
+    pdl_trigger();
+    const int r = threadIdx.x / TPR, t = threadIdx.x - r * TPR, w = t >> 5;
+    const long long row = static_cast<long long>(blockIdx.x) * LNW_ROWS + r;
+    const bool ok = row < M;
+    const int nch = D >> 2;
+    const long long off = ok ? row * D : 0;
+    const float4* xr = reinterpret_cast<const float4*>(x + off);
+    float4 v[MAXC];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = t + TPR * i;
+        if (ok && c < nch) {
+            v[i] = xr[c];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) s_part[r][w][0] = sum;
+    __syncthreads();
+    float mean = 0.f;
+#pragma unroll
+    for (int k = 0; k < WPR; ++k) mean += s_part[r][k][0];
+    mean /= static_cast<float>(D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = t + TPR * i;
+        if (ok && c < nch) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) s_part[r][w][1] = sq;
+    __syncthreads();
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < WPR; ++k) var += s_part[r][k][1];
+    const float rstd = 1.0f / sqrtf(var / static_cast<float>(D) + eps);
+    if (ok && t == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = t + TPR * i;
+        if (ok && c < nch) {
+            const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + b.x;
+            o.y = (v[i].y - mean) * rstd * g.y + b.y;
+            o.z = (v[i].z - mean) * rstd * g.z + b.z;
+            o.w = (v[i].w - mean) * rstd * g.w + b.w;
+            if (y32)
+                reinterpret_cast<float4*>(y32 + off)[c] =
+                    round_out ? make_float4(round_tf32_rn(o.x), round_tf32_rn(o.y), round_tf32_rn(o.z), round_tf32_rn(o.w)) : o;
+            if (y16) reinterpret_cast<uint2*>(y16 + off)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         }
     }
 }
@@ -131,7 +296,16 @@ extern "C" __attribute__((visibility("default"))) int tvs_layernorm_fwd(const fl
     TVS_REQUIRE(x && gamma && beta && (y_f32 || y_bf16), "tvs_layernorm_fwd: null pointer");
     TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_fwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
     const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
-    if (D <= 1024)
+    static const int variant = [] { const char* e = getenv("TVS_LN_FWD"); return e ? atoi(e) : 1; }();   // warps per row for D <= 768 (1: one-warp kernel)
+    if (variant >= 2 && D <= 768 && D > 128) {
+        const unsigned gridw = static_cast<unsigned>((M + LNW_ROWS - 1) / LNW_ROWS);
+        if (variant == 2)
+            TVS_CUDA(launch_pdl(layernorm_fwd_wide_kernel<3, 2>, dim3(gridw), dim3(LNW_ROWS * 64), 0, static_cast<cudaStream_t>(stream), 1, x, gamma, beta,
+                                eps, static_cast<long long>(M), D, y_f32, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
+        else
+            TVS_CUDA(launch_pdl(layernorm_fwd_wide_kernel<2, 3>, dim3(gridw), dim3(LNW_ROWS * 96), 0, static_cast<cudaStream_t>(stream), 1, x, gamma, beta,
+                                eps, static_cast<long long>(M), D, y_f32, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
+    } else if (D <= 1024)
         TVS_CUDA(launch_pdl(layernorm_fwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1, x, gamma, beta, eps,
                             static_cast<long long>(M), D, y_f32, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
     else
@@ -148,13 +322,28 @@ extern "C" __attribute__((visibility("default"))) int tvs_layernorm_bwd(const vo
     TVS_REQUIRE(x && gamma && mean && rstd && (dx_out_f32 || dx_out_bf16), "tvs_layernorm_bwd: null pointer");
     TVS_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAXC, "tvs_layernorm_bwd: D=%d must be a multiple of 4 and <= %d", D, 128 * LN_MAXC);
     const unsigned grid = static_cast<unsigned>((M + LN_WARPS - 1) / LN_WARPS);
-    if (D <= 1024)
-        TVS_CUDA(launch_pdl(layernorm_bwd_kernel<8>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1,
-                            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, static_cast<long long>(M), D,
-                            dx_out_f32, static_cast<__nv_bfloat16*>(dx_out_bf16)));
-    else
-        TVS_CUDA(launch_pdl(layernorm_bwd_kernel<16>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1,
-                            static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, static_cast<long long>(M), D,
-                            dx_out_f32, static_cast<__nv_bfloat16*>(dx_out_bf16)));
+    static const int variant = [] { const char* e = getenv("TVS_LN_BWD"); return e ? atoi(e) : 4; }();   // see the kernel comments
+#define TVS_LN_BWD_LAUNCH(MAXC, VAR)                                                                                                      \
+    TVS_CUDA(launch_pdl(layernorm_bwd_kernel<MAXC, VAR>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1,        \
+                        static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, static_cast<long long>(M), D, \
+                        dx_out_f32, static_cast<__nv_bfloat16*>(dx_out_bf16)))
+    if (variant >= 3 && D <= 768 && D > 128) {
+        const unsigned gridw = static_cast<unsigned>((M + LNW_ROWS - 1) / LNW_ROWS);
+        if (variant == 3)
+            TVS_CUDA(launch_pdl(layernorm_bwd_wide_kernel<3, 2>, dim3(gridw), dim3(LNW_ROWS * 64), 0, static_cast<cudaStream_t>(stream), 1,
+                                static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, static_cast<long long>(M), D,
+                                dx_out_f32, static_cast<__nv_bfloat16*>(dx_out_bf16)));
+        else
+            TVS_CUDA(launch_pdl(layernorm_bwd_wide_kernel<2, 3>, dim3(gridw), dim3(LNW_ROWS * 96), 0, static_cast<cudaStream_t>(stream), 1,
+                                static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_add_f32, static_cast<long long>(M), D,
+                                dx_out_f32, static_cast<__nv_bfloat16*>(dx_out_bf16)));
+    } else if (D <= 768) {
+        if (variant == 0) TVS_LN_BWD_LAUNCH(6, 0); else if (variant == 1) TVS_LN_BWD_LAUNCH(6, 1); else TVS_LN_BWD_LAUNCH(6, 2);
+    } else if (D <= 1024) {
+        if (variant == 0) TVS_LN_BWD_LAUNCH(8, 0); else if (variant == 1) TVS_LN_BWD_LAUNCH(8, 1); else TVS_LN_BWD_LAUNCH(8, 2);
+    } else {
+        if (variant == 0) TVS_LN_BWD_LAUNCH(16, 0); else TVS_LN_BWD_LAUNCH(16, 1);
+    }
+#undef TVS_LN_BWD_LAUNCH
     return check_launch("layernorm_bwd_kernel");
 }

@@ -21,6 +21,7 @@ Reference arithmetic being replaced (see oracle/clipseg.py for the restatement t
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -49,6 +50,20 @@ def tf32_rn(w: torch.Tensor) -> torch.Tensor:
     ``rn_act`` / the im2col kernel."""
     w = w.detach().to(F32).contiguous()
     return ((w.view(torch.int32) + 0x1000) & ~0x1FFF).view(F32)
+
+
+# TVS_FFN: "split" (default) fused decoder FFN with bf16 head + tail operands, "bf16" fused with heads only,
+# "gemm" the two kind::tf32 GEMMs that materialise the hidden activation (kept for A/B measurements)
+FFN_MODE = os.environ.get("TVS_FFN", "split")
+
+
+def split_bf16(w: torch.Tensor, head_only: bool = False):
+    """w = hi + lo with both parts bf16 (|lo| <= 2^-9 |w|): operands of the three-product MMAs of the fused FFN."""
+    w = w.detach().to(F32).contiguous()
+    hi = w.to(BF16)
+    if head_only:
+        return hi, None
+    return hi, (w - hi.to(F32)).to(BF16)
 
 
 def rn_act(a: torch.Tensor) -> torch.Tensor:
@@ -96,6 +111,10 @@ class PackedLayer:
             self.w1_32, self.w2_32 = pack(mlp.fc1.weight), pack(mlp.fc2.weight)
             self.wo_t32 = _f(sa.out_proj.weight.t())
             self.w1_t32, self.w2_t32 = _f(mlp.fc1.weight.t()), _f(mlp.fc2.weight.t())
+            if D == 64 and self.F % 64 == 0 and self.F <= 4096 and FFN_MODE != "gemm":
+                # fused FFN (csrc/ffn_sm100.cu): bf16 head + tail of fc1.weight [F, D] and fc2.weight^T [F, D]
+                self.ffn_w1 = split_bf16(mlp.fc1.weight, FFN_MODE == "bf16")
+                self.ffn_w2t = split_bf16(mlp.fc2.weight.t(), FFN_MODE == "bf16")
 
 
 class PackedClipSeg:
@@ -291,10 +310,14 @@ def decoder_layer_fwd(pk: PackedLayer, x, B, S, eps):
     y1 = _e((M, D), F32, x)
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
     abi.layernorm_fwd(s1, pk.g1, pk.be1, eps, y_f32=y1, mean=mean1, rstd=rstd1)
-    a32, a16 = _e((M, F), F32, x), _e((M, F), BF16, x)
-    abi.gemm(rn_act(y1), pk.w1_32, bias=pk.b1, out_f32=a32, out_bf16=a16, act=abi.ACT_RELU, round_out=True)
     s2 = _e((M, D), F32, x)
-    abi.gemm(a32, pk.w2_32, bias=pk.b2, residual=y1, out_f32=s2)
+    if hasattr(pk, "ffn_w1"):
+        a16 = y1                                                          # the dgrad recomputes the ReLU mask from y1
+        abi.ffn64_fwd(y1, pk.ffn_w1, pk.ffn_w2t, pk.b1, pk.b2, s2)
+    else:
+        a32, a16 = _e((M, F), F32, x), _e((M, F), BF16, x)
+        abi.gemm(rn_act(y1), pk.w1_32, bias=pk.b1, out_f32=a32, out_bf16=a16, act=abi.ACT_RELU, round_out=True)
+        abi.gemm(a32, pk.w2_32, bias=pk.b2, residual=y1, out_f32=s2)
     y2 = _e((M, D), F32, x)
     mean2, rstd2 = _e((M,), F32, x), _e((M,), F32, x)
     abi.layernorm_fwd(s2, pk.g2, pk.be2, eps, y_f32=y2, mean=mean2, rstd=rstd2)
@@ -306,10 +329,13 @@ def decoder_layer_bwd(pk: PackedLayer, sv: SavedDec, g, B, S):
     M, D, F = B * S, pk.D, pk.F
     ds2 = _e((M, D), F32, g)
     abi.layernorm_bwd(g, sv.s2, pk.g2, sv.mean2, sv.rstd2, dx_f32=ds2)
-    da = _e((M, F), F32, g)
-    abi.gemm(ds2, pk.w2_t32, aux_bf16=sv.a, out_f32=da, act=abi.ACT_DRELU)
     dy1 = _e((M, D), F32, g)
-    abi.gemm(da, pk.w1_t32, residual=ds2, out_f32=dy1)
+    if hasattr(pk, "ffn_w1"):
+        abi.ffn64_bwd(sv.a, ds2, pk.ffn_w1, pk.ffn_w2t, pk.b1, dy1)       # sv.a is y1 here
+    else:
+        da = _e((M, F), F32, g)
+        abi.gemm(ds2, pk.w2_t32, aux_bf16=sv.a, out_f32=da, act=abi.ACT_DRELU)
+        abi.gemm(da, pk.w1_t32, residual=ds2, out_f32=dy1)
     ds1 = ds2
     abi.layernorm_bwd(dy1, sv.s1, pk.g1, sv.mean1, sv.rstd1, dx_f32=ds1)
     datt = _e((M, D), BF16, g)
