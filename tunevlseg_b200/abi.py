@@ -465,6 +465,9 @@ def _flops(name, args, kwargs) -> tuple[str, float]:
     if name == "attn_bwd":
         B, S, H, hd = args[4:8]
         return f"B{B}S{S}H{H}d{hd}", 10.0 * B * H * S * S * hd
+    if name in ("ffn64_fwd", "ffn64_bwd"):
+        (M, D), F = args[0].shape, (args[1] if name == "ffn64_fwd" else args[2])[0].shape[0]
+        return f"{M}x{D}x{F}", (4.0 if name == "ffn64_fwd" else 6.0) * M * D * F
     if name in ("cross_attn_fwd", "cross_attn_bwd"):
         i = 4 if name == "cross_attn_fwd" else 7
         B, Sq, Sk, H = args[i:i + 4]
@@ -494,7 +497,7 @@ def _wrap(fn, name):
 for _n in ("gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "im2col_patches", "vision_assemble",
            "prompt_overwrite", "prompt_grad", "slice_rows", "unslice_rows", "wgrad_small", "cast_bf16", "add_f32", "film_fwd",
            "film_bwd", "head_fwd", "head_bwd", "dicebce_metrics_fwd", "dicebce_bwd", "metrics_from_probs", "adamw_flat",
-           "counter_inc"):
+           "counter_inc", "ffn64_fwd", "ffn64_bwd"):
     globals()[_n] = _wrap(globals()[_n], _n)
 
 

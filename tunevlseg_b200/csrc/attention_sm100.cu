@@ -634,6 +634,219 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// one-pass forward: the two-pass kernel above reads every fp32 score out of TMEM twice (734 MB per layer at ~64 B/clk/SM
+// = ~45 us, its floor).  Here each score tile is read once: the running row maximum is kept STALE until a tile exceeds it
+// by more than 2^8 (probabilities then stay below 256, exact in fp32 and safe in bf16), and only then is O rescaled in
+// TMEM - by the element-wise warp itself, after the previous P V has completed (o_done).  With real attention logits the
+// first tile fixes the maximum and rescales are rare.  Same pipeline otherwise: two score buffers, Q K_{j+1}^T queued
+// before P_j V_j, 4-stage K/V ring, 256 TMEM columns, two CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+constexpr float RESCALE_LOG2 = 8.0f;
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_in, int S, int H,
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* s_q = smem + FwdSmem::Q;
+    uint8_t* s_inner = smem + FwdSmem::INNER;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR);
+    uint64_t* q_full = bars;
+    uint64_t* in_full = bars + 1;       // [FST]
+    uint64_t* in_empty = bars + 5;      // [FST]
+    uint64_t* s_full = bars + 9;        // [2]
+    uint64_t* ew_done = bars + 11;      // [2]
+    uint64_t* o_done = bars + 13;       // one phase per P V
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int ot = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int E = H * AHD;
+    const int warp = threadIdx.x >> 5;
+    const int n_it = (S + FTI - 1) / FTI;
+    constexpr uint32_t TMEM_COLS = 256, C_O = 128;
+    const long long bh = static_cast<long long>(b) * H + h;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_in);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < FST; ++s) {
+            mbar_init(&in_full[s], 1);
+            mbar_init(&in_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&ew_done[s], 128);
+        }
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 4) {
+        const int cq = h * AHD, ck = E + h * AHD, cv = 2 * E + h * AHD;
+        if (elect_one()) {
+            mbar_expect_tx(q_full, ATILE);
+            tma_load_3d(s_q, &map_q, cq, ot * AT, b, q_full);
+        }
+        for (int it = 0; it < n_it; ++it) {
+            const int stage = it % FST, par = (it / FST) & 1;
+            mbar_wait(&in_empty[stage], par ^ 1);
+            if (elect_one()) {
+                uint8_t* t0 = s_inner + stage * 2 * FITILE;
+                mbar_expect_tx(&in_full[stage], 2 * FITILE);
+                tma_load_3d(t0, &map_in, ck, it * FTI, b, &in_full[stage]);
+                tma_load_3d(t0 + FITILE, &map_in, cv, it * FTI, b, &in_full[stage]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 5) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(AT, FTI, 0, 0);
+        constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        const uint64_t a0 = umma_desc_sw128(smem_u32(s_q));
+        auto issue_pv = [&](int j) {     // O += P_j V_j ; releases the K/V stage of step j, completes phase j of o_done
+            const int bfj = j & 1, stg = j % FST;
+            mbar_wait(&ew_done[bfj], (j >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t bv = umma_desc_sw128(smem_u32(s_inner + stg * 2 * FITILE + FITILE));
+#pragma unroll
+                for (int k = 0; k < FTI / 16; ++k)
+                    umma_ts(tb + C_O, tb + 64 * bfj + 8 * k, bv + 128 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&in_empty[stg]);
+                umma_commit(o_done);
+            }
+            __syncwarp();
+        };
+        for (int it = 0; it < n_it; ++it) {
+            const int stage = it % FST, par = (it / FST) & 1, bf = it & 1;
+            mbar_wait(&in_full[stage], par);
+            tc_fence_after();
+            // score buffer bf was last read as P by P V of step it - 2: issued earlier in program order, after its ew_done
+            if (elect_one()) {
+                const uint64_t bk = umma_desc_sw128(smem_u32(s_inner + stage * 2 * FITILE));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb + 64 * bf, a0 + 2 * k, bk + 2 * k, idesc_s, k > 0);
+                umma_commit(&s_full[bf]);
+            }
+            __syncwarp();
+            if (it >= 1) issue_pv(it - 1);
+        }
+        issue_pv(n_it - 1);
+    } else {
+        const int tid = threadIdx.x;
+        const uint32_t tl = tb + (static_cast<uint32_t>(warp * 32) << 16);
+        const int row = ot * AT + tid;
+        const bool row_ok = row < S;
+        float mL = -INFINITY;          // (stale) running maximum, in log2 units
+        float l = 0.f;
+        for (int it = 0; it < n_it; ++it) {
+            const int bf = it & 1;
+            mbar_wait(&s_full[bf], (it >> 1) & 1);
+            tc_fence_after();
+            const int k0 = it * FTI;
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tl + 64 * bf, r0);
+            tmem_ld32(tl + 64 * bf + 32, r1);
+            tmem_ld_wait();
+            const bool full = k0 + FTI <= S;
+            float mt = -INFINITY;
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mt = fmaxf(mt, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (k0 + i < S) mt = fmaxf(mt, __uint_as_float(r0[i]));
+                    if (k0 + 32 + i < S) mt = fmaxf(mt, __uint_as_float(r1[i]));
+                }
+            }
+            const float mtL = mt * L2E;
+            const bool need = mtL > mL + RESCALE_LOG2;      // always true on the first tile (mL = -inf, key 0 is valid)
+            if (__any_sync(0xffffffffu, need)) {
+                const float scale = need ? fast_exp2(mL - mtL) : 1.0f;      // exp2(-inf) = 0 on the first tile
+                if (it > 0) {
+                    // the previous P V must have landed in O before it is rescaled; the next one is not issued before ew_done
+                    mbar_wait(o_done, (it - 1) & 1);
+                    tc_fence_after();
+                    uint32_t o0[32], o1[32];
+                    tmem_ld32(tl + C_O, o0);
+                    tmem_ld32(tl + C_O + 32, o1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        o0[i] = __float_as_uint(__uint_as_float(o0[i]) * scale);
+                        o1[i] = __float_as_uint(__uint_as_float(o1[i]) * scale);
+                    }
+                    tmem_st32(tl + C_O, o0);
+                    tmem_st32(tl + C_O + 32, o1);
+                }
+                l *= scale;
+                if (need) mL = mtL;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(c == 0 ? r0[i] : r1[i]), L2E, -mL));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(c == 0 ? r0[i + 1] : r1[i + 1]), L2E, -mL));
+                    if (!full) {
+                        if (k0 + 32 * c + i >= S) p0 = 0.f;
+                        if (k0 + 32 * c + i + 1 >= S) p1 = 0.f;
+                    }
+                    l += p0 + p1;
+                    pk[i / 2] = pack_bf16x2(p0, p1);
+                }
+                tmem_st16(tl + 64 * bf + 16 * c, pk);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&ew_done[bf]);
+        }
+        mbar_wait(o_done, (n_it - 1) & 1);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tl + C_O, o0);
+        tmem_ld32(tl + C_O + 32, o1);
+        tmem_ld_wait();
+        if (row_ok) {
+            const float inv = l > 0.f ? 1.0f / l : 0.f;
+            const long long tok = static_cast<long long>(b) * S + row;
+            store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv);
+            if (out32) {
+                float* f = out32 + tok * E + h * AHD;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int e = 8 * q + i;
+                        w[i] = __float_as_uint(round_tf32_rn(__uint_as_float(e < 32 ? o0[e] : o1[e - 32]) * inv));     // feeds a tf32 GEMM
+                    }
+                    st_global_256(f + 8 * q, w);
+                }
+            }
+            lse_out[bh * S + row] = (mL == -INFINITY ? 0.f : mL * 0.6931471805599453f) + logf(fmaxf(l, 1e-30f));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tb, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -692,12 +905,18 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
     if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, 64)) return rc;
     static const bool legacy = [] { const char* e = getenv("TVS_ATTN_FWD"); return e && e[0] == '1'; }();   // TVS_ATTN_FWD=1: single-buffer variant
     if (legacy) return launch_atc<MODE_FWD>(mq, mq, mqi, mqi, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st);
+    static const bool two_pass = [] { const char* e = getenv("TVS_ATTN_FWD"); return e && e[0] == '2'; }();   // TVS_ATTN_FWD=2: two-pass pipelined variant
     static bool attr_set = false;
     if (!attr_set) {
         TVS_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+        TVS_CUDA(cudaFuncSetAttribute(attn_tc_fwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
         attr_set = true;
     }
     dim3 grid((S + AT - 1) / AT, H, B);
+    if (!two_pass) {
+        TVS_CUDA(launch_pdl(attn_tc_fwd1_kernel, grid, dim3(ATC_THREADS), FwdSmem::TOTAL, st, 1, mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse));
+        return check_launch("attn_tc_fwd1_kernel");
+    }
     TVS_CUDA(launch_pdl(attn_tc_fwd_kernel, grid, dim3(ATC_THREADS), FwdSmem::TOTAL, st, 1, mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse));
     return check_launch("attn_tc_fwd_kernel");
 }

@@ -14,9 +14,12 @@
 // hi*hi + lo*hi + hi*lo (error ~2^-17 relative, tighter than the kind::tf32 GEMMs this replaces); all MMAs are
 // kind::f16 with fp32 accumulation.  SPLIT = false keeps the heads only.
 //
-// One CTA = 128 rows; 192 threads: warps 0-3 element-wise stage (thread = row = TMEM lane), warp 4 TMA producer of the
-// weight tiles (3-stage ring), warp 5 MMA issuer.  The activation rows are read as fp32 by their own thread, split and
-// written into the 128-byte-swizzled operand tiles by hand (no activation tensor map, no separate split pass).
+// One CTA = 128 rows; 320 threads: warps 0-7 element-wise stage (two warps per TMEM lane quarter, each owning half of the
+// 64 hidden units of a step: with one warp per scheduler every dependent-instruction latency was exposed, 36 / 46 us;
+// two warps per scheduler: see DESIGN.md), warp 8 TMA producer of the weight tiles (3-stage ring), warp 9 MMA issuer.
+// The activation rows are read as fp32 by their own threads, split and written into the 128-byte-swizzled operand tiles
+// by hand (no activation tensor map, no separate split pass).  P has its own TMEM columns, so no store of the
+// element-wise stage can land on a score column another warp has not read yet.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tvs_b200.h"
@@ -30,7 +33,8 @@ constexpr int FC = 64;                   // hidden units per step
 constexpr int F_ATILE = FT * FD * 2;     // 16 KB
 constexpr int F_WTILE = FC * FD * 2;     // 8 KB
 constexpr int F_NST = 3;                 // weight stages
-constexpr int F_THREADS = 192;
+constexpr int F_THREADS = 320;
+constexpr int F_EW = 256;                // element-wise threads
 constexpr int F_MAXF = 4096;             // b1 lives in shared memory
 
 template <bool BWD, bool SPLIT>
@@ -46,14 +50,14 @@ struct FfnSmem {
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_ew() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // one fp32 row of 64 -> bf16 head (and tail) rows of the swizzled [128][64] operand tiles: 16-byte chunk c of row r sits at
 // chunk position c ^ (r & 7) (CU_TENSOR_MAP_SWIZZLE_128B / UMMA layout SWIZZLE_128B on a 1024-byte aligned tile)
 template <bool SPLIT>
-__device__ __forceinline__ void stage_row(const float* __restrict__ src, bool ok, int r, uint8_t* tile_hi, uint8_t* tile_lo) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
+__device__ __forceinline__ void stage_row(const float* __restrict__ src, bool ok, int r, uint8_t* tile_hi, uint8_t* tile_lo, int c_begin, int c_end) {
+#pragma unroll 4
+    for (int c = c_begin; c < c_end; ++c) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
         if (ok) {
             a = reinterpret_cast<const float4*>(src)[2 * c];
@@ -97,9 +101,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int n_it = F / FC;
-    // TMEM: buffer bf at columns [128 bf, 128 bf + 128): S at +0, dH at +64; accumulator at 256 (64 columns)
-    constexpr uint32_t TMEM_COLS = 512, C_DH = 64, C_ACC = 256;
-    constexpr uint32_t C_LO = BWD ? 64 : 32;          // where the tail of P goes (see the element-wise stage)
+    // TMEM: buffer bf at columns [128 bf, 128 bf + 128): S at +0, dH at +64; accumulator at 256 (64 columns);
+    // P of buffer bf at 320 + 64 bf: packed head in columns [0, 32), packed tail in [32, 64)
+    constexpr uint32_t TMEM_COLS = 512, C_DH = 64, C_ACC = 256, C_P = 320, C_LO = 32;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_w1_hi);
@@ -108,19 +112,19 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
             tma_prefetch_desc(&map_w1_lo);
             tma_prefetch_desc(&map_w2t_lo);
         }
-        mbar_init(a_ready, 128);
+        mbar_init(a_ready, F_EW);
         for (int s = 0; s < F_NST; ++s) {
             mbar_init(&w_full[s], 1);
             mbar_init(&w_empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&ew_done[s], 128);
+            mbar_init(&ew_done[s], F_EW);
         }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -128,7 +132,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
     pdl_wait();
     pdl_trigger();
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ------------------------------------------------------------------ TMA producer: weight tiles of 64 hidden units
         for (int it = 0; it < n_it; ++it) {
             const int stage = it % F_NST, par = (it / F_NST) & 1;
@@ -143,7 +147,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
             }
             __syncwarp();
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ------------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc_s = umma_idesc_bf16(FT, FC, 0, 0);
         constexpr uint32_t idesc_acc = umma_idesc_bf16(FT, FD, 0, 1);
@@ -166,7 +170,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
                 bool first = (j == 0);
 #pragma unroll
                 for (int pr = 0; pr < NPROD; ++pr) {
-                    const uint32_t pa = tb + 128 * bfj + (PA[pr] ? C_LO : 0);
+                    const uint32_t pa = tb + C_P + 64 * bfj + (PA[pr] ? C_LO : 0);
                     const uint64_t bw = umma_desc_sw128(wbase + PB[pr] * F_WTILE);
 #pragma unroll
                     for (int k = 0; k < FC / 16; ++k) {   // 16 hidden units per MMA = 8 TMEM columns of P, 16 rows (2048 bytes) of the tile
@@ -183,8 +187,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
             const int stage = it % F_NST, par = (it / F_NST) & 1, bf = it & 1;
             mbar_wait(&w_full[stage], par);
             tc_fence_after();
-            // buffer bf was last read (as P) by the accumulate MMAs of step it - 2, issued earlier in program order, and its
-            // element-wise stage finished before those were issued
+            // S / dH of buffer bf were last read by the element-wise stage of step it - 2, which finished before the accumulate
+            // MMAs of that step were issued (ew_done); P of buffer bf is rewritten only after s_full[bf] of this step, a
+            // commit that also covers those accumulate MMAs
             if (elect_one()) {
                 const uint32_t w1 = smem_u32(s_w + stage * NW * F_WTILE);
                 const uint32_t w2 = w1 + NP * F_WTILE;
@@ -210,92 +215,72 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
         }
         issue_acc(n_it - 1);
     } else {
-        // ------------------------------------------------------------------ element-wise stage (thread = row = TMEM lane)
-        const int tid = threadIdx.x;
-        const uint32_t tl = tb + (static_cast<uint32_t>(warp * 32) << 16);
-        const long long row = static_cast<long long>(blockIdx.x) * FT + tid;
+        // ------------------------------------------------------------------ element-wise stage: thread = (row = TMEM lane, column half)
+        const int lane = threadIdx.x & 31;
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;
+        const uint32_t tl = tb + (static_cast<uint32_t>(quarter * 32) << 16);
+        const long long row = static_cast<long long>(blockIdx.x) * FT + r;
         const bool row_ok = row < M;
-        stage_row<SPLIT>(x + row * FD, row_ok, tid, s_a, s_a + F_ATILE);
-        if (BWD) stage_row<SPLIT>(g + row * FD, row_ok, tid, s_a + NP * F_ATILE, s_a + (NP + 1) * F_ATILE);
-        for (int i = tid; i < F; i += 128) s_b1[i] = b1[i];
+        if (BWD) {
+            if (half == 0) stage_row<SPLIT>(x + row * FD, row_ok, r, s_a, s_a + F_ATILE, 0, 8);
+            else stage_row<SPLIT>(g + row * FD, row_ok, r, s_a + NP * F_ATILE, s_a + (NP + 1) * F_ATILE, 0, 8);
+        } else {
+            stage_row<SPLIT>(x + row * FD, row_ok, r, s_a, s_a + F_ATILE, 4 * half, 4 * half + 4);
+        }
+        for (int i = threadIdx.x; i < F; i += F_EW) s_b1[i] = b1[i];
         fence_proxy_async_smem();       // the operand tiles were written through the generic proxy; the MMA reads them through the async proxy
         mbar_arrive(a_ready);
-        bar_sync_128();                 // s_b1 complete
+        bar_sync_ew();                  // s_b1 complete
         for (int it = 0; it < n_it; ++it) {
             const int bf = it & 1;
-            const float* bj = s_b1 + it * FC;
+            const float* bj = s_b1 + it * FC + 32 * half;
             mbar_wait(&s_full[bf], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t tS = tl + 128 * bf;
-            if (!BWD) {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(tS, r0);
-                tmem_ld32(tS + 32, r1);
-                tmem_ld_wait();          // both halves are in registers before anything is written back
+            const uint32_t tS = tl + 128 * bf + 32 * half;
+            const uint32_t tP = tl + C_P + 64 * bf + 16 * half;
+            uint32_t sv[32], dv[32];
+            tmem_ld32(tS, sv);
+            if (BWD) tmem_ld32(tS + C_DH, dv);
+            tmem_ld_wait();
+            uint32_t ph[16], pl[16];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t ph[16], pl[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float h0 = fmaxf(__uint_as_float(c == 0 ? r0[i] : r1[i]) + bj[32 * c + i], 0.f);
-                        const float h1 = fmaxf(__uint_as_float(c == 0 ? r0[i + 1] : r1[i + 1]) + bj[32 * c + i + 1], 0.f);
-                        const __nv_bfloat16 a0 = __float2bfloat16_rn(h0), a1 = __float2bfloat16_rn(h1);
-                        ph[i / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(a0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(a1)) << 16);
-                        if (SPLIT) pl[i / 2] = pack_bf16x2(h0 - __bfloat162float(a0), h1 - __bfloat162float(a1));
-                    }
-                    tmem_st16(tS + 16 * c, ph);                       // head: columns [0, 32)
-                    if (SPLIT) tmem_st16(tS + C_LO + 16 * c, pl);     // tail: columns [32, 64)
+            for (int i = 0; i < 32; i += 2) {
+                float h0 = __uint_as_float(sv[i]) + bj[i], h1 = __uint_as_float(sv[i + 1]) + bj[i + 1];
+                if (BWD) {
+                    h0 = h0 > 0.f ? __uint_as_float(dv[i]) : 0.f;
+                    h1 = h1 > 0.f ? __uint_as_float(dv[i + 1]) : 0.f;
+                } else {
+                    h0 = fmaxf(h0, 0.f);
+                    h1 = fmaxf(h1, 0.f);
                 }
-            } else {
-                // software pipeline over the two 32-column halves; the packed head overwrites S columns [0, 32) and the packed
-                // tail dH columns [0, 32): both lie in the first halves, already in registers when the first store is issued
-                uint32_t sA[32], dA[32], sB[32], dB[32];
-                tmem_ld32(tS, sA);
-                tmem_ld32(tS + C_DH, dA);
-                tmem_ld_wait();
-                tmem_ld32(tS + 32, sB);
-                tmem_ld32(tS + C_DH + 32, dB);
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t ph[16], pl[16];
-                    if (c == 1) tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float s0 = __uint_as_float(c == 0 ? sA[i] : sB[i]) + bj[32 * c + i];
-                        const float s1 = __uint_as_float(c == 0 ? sA[i + 1] : sB[i + 1]) + bj[32 * c + i + 1];
-                        const float d0 = s0 > 0.f ? __uint_as_float(c == 0 ? dA[i] : dB[i]) : 0.f;
-                        const float d1 = s1 > 0.f ? __uint_as_float(c == 0 ? dA[i + 1] : dB[i + 1]) : 0.f;
-                        const __nv_bfloat16 a0 = __float2bfloat16_rn(d0), a1 = __float2bfloat16_rn(d1);
-                        ph[i / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(a0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(a1)) << 16);
-                        if (SPLIT) pl[i / 2] = pack_bf16x2(d0 - __bfloat162float(a0), d1 - __bfloat162float(a1));
-                    }
-                    tmem_st16(tS + 16 * c, ph);
-                    if (SPLIT) tmem_st16(tS + C_LO + 16 * c, pl);
-                }
+                const __nv_bfloat16 a0 = __float2bfloat16_rn(h0), a1 = __float2bfloat16_rn(h1);
+                ph[i / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(a0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(a1)) << 16);
+                if (SPLIT) pl[i / 2] = pack_bf16x2(h0 - __bfloat162float(a0), h1 - __bfloat162float(a1));
             }
+            tmem_st16(tP, ph);
+            if (SPLIT) tmem_st16(tP + C_LO, pl);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&ew_done[bf]);
         }
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        uint32_t a0[32], a1[32];
-        tmem_ld32(tl + C_ACC, a0);
-        tmem_ld32(tl + C_ACC + 32, a1);
+        uint32_t acc[32];
+        tmem_ld32(tl + C_ACC + 32 * half, acc);
         tmem_ld_wait();
         if (row_ok) {
-            const float* res = (BWD ? g : x) + row * FD;      // residual: x (forward), g (dgrad)
-            float* o = out + row * FD;
+            const float* res = (BWD ? g : x) + row * FD + 32 * half;      // residual: x (forward), g (dgrad)
+            float* o = out + row * FD + 32 * half;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const float4 ra = reinterpret_cast<const float4*>(res)[2 * q], rb = reinterpret_cast<const float4*>(res)[2 * q + 1];
                 const float rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
                 uint32_t w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int e = 8 * q + i;
-                    float v = __uint_as_float(e < 32 ? a0[e] : a1[e - 32]) + rr[i];
-                    if (!BWD) v += __ldg(b2 + e);
+                    float v = __uint_as_float(acc[8 * q + i]) + rr[i];
+                    if (!BWD) v += __ldg(b2 + 32 * half + 8 * q + i);
                     w[i] = __float_as_uint(v);
                 }
                 st_global_256(o + 8 * q, w);
@@ -305,7 +290,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc(tb, TMEM_COLS);
     }
