@@ -112,6 +112,13 @@ int tvs_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t hd, i
 int tvs_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
                  int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv,
                  void* stream);
+/* Bottom block of a prompted tower: below it only the prompt rows (the last n of every sample) still carry a gradient
+ * (base_visual_learner.py:18-23 appends them last; the patch / class embeddings are frozen), so dqkv is only needed for
+ * rows >= row_begin.  Rows of dqkv below the 128-row tile that contains row_begin are left untouched (hd = 64 without
+ * masks); other configurations compute every row like tvs_attn_bwd. */
+int tvs_attn_bwd_tail(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
+                      int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv,
+                      int32_t row_begin, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Vision embedding pieces (hf::196-212 CLIPSegVisionEmbeddings.forward; base_multimodal_clipseg.py:449-465)

@@ -69,6 +69,7 @@ def load():
         "tvs_layernorm_bwd": [P, P, P, P, P, P, P, I64, I32, P, P, P],
         "tvs_attn_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, P],
         "tvs_attn_bwd": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, P],
+        "tvs_attn_bwd_tail": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, I32, P],
         "tvs_im2col_patches": [P, I32, I32, I32, I32, I32, P, P],
         "tvs_vision_assemble": [P, P, P, P, I64, I32, I32, I32, I32, P, P],
         "tvs_prompt_overwrite": [P, P, I32, I32, I32, I32, I32, P, I64, P],
@@ -275,10 +276,16 @@ def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse, out_f32=None):
                             lse.data_ptr(), _stream()), "tvs_attn_fwd")
 
 
-def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv):
+def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv, row_begin=0):
+    """``row_begin`` > 0 (tvs_attn_bwd_tail): only rows >= row_begin of dqkv are needed; rows below the 128-row tile of
+    row_begin may be left unwritten."""
     require_device()
     _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(dout, torch.bfloat16, "dout")
     _chk(dqkv, torch.bfloat16, "dqkv"); _chk(lse, torch.float32, "lse"); _chk(delta, torch.float32, "delta")
+    if row_begin:
+        _ck(load().tvs_attn_bwd_tail(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, S, H, hd, int(causal),
+                                     _p(key_mask), delta.data_ptr(), dqkv.data_ptr(), int(row_begin), _stream()), "tvs_attn_bwd_tail")
+        return
     _ck(load().tvs_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, S, H, hd, int(causal),
                             _p(key_mask), delta.data_ptr(), dqkv.data_ptr(), _stream()), "tvs_attn_bwd")
 
@@ -464,7 +471,9 @@ def _flops(name, args, kwargs) -> tuple[str, float]:
         return f"B{B}S{S}H{H}d{hd}", 4.0 * B * H * S * S * hd
     if name == "attn_bwd":
         B, S, H, hd = args[4:8]
-        return f"B{B}S{S}H{H}d{hd}", 10.0 * B * H * S * S * hd
+        rb = kwargs.get("row_begin", 0)
+        frac = 1.0 if not rb else (-(-S // 128) - rb // 128) / -(-S // 128)
+        return f"B{B}S{S}H{H}d{hd}" + (f"_from{rb}" if rb else ""), 10.0 * B * H * S * S * hd * frac
     if name in ("ffn64_fwd", "ffn64_bwd"):
         (M, D), F = args[0].shape, (args[1] if name == "ffn64_fwd" else args[2])[0].shape[0]
         return f"{M}x{D}x{F}", (4.0 if name == "ffn64_fwd" else 6.0) * M * D * F

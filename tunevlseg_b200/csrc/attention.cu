@@ -575,7 +575,7 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
 // tcgen05 / TMEM kernels for head dim 64 without masks (attention_sm100.cu)
 bool attn_tc_enabled();
 int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st);
-int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st);
+int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st, int row_begin);
 
 }  // namespace tvs
 
@@ -592,21 +592,27 @@ extern "C" __attribute__((visibility("default"))) int tvs_attn_fwd(const void* q
     return -1;
 }
 
-extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S, int32_t H,
-                            int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv, void* stream) {
+extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd_tail(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S, int32_t H,
+                            int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv, int32_t row_begin, void* stream) {
     using namespace tvs;
-    TVS_REQUIRE(qkv && out && dout && lse && delta && dqkv, "tvs_attn_bwd: null pointer");
-    TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_bwd: bad shape B=%d S=%d H=%d", B, S, H);
+    TVS_REQUIRE(row_begin >= 0 && row_begin < S, "tvs_attn_bwd_tail: row_begin %d outside [0, %d)", row_begin, S);
+    TVS_REQUIRE(qkv && out && dout && lse && delta && dqkv, "tvs_attn_bwd_tail: null pointer");
+    TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_bwd_tail: bad shape B=%d S=%d H=%d", B, S, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (hd == 64 && !causal && !key_mask && attn_tc_enabled()) {
         const long long rows = static_cast<long long>(B) * S;
         attn_delta_kernel<64><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
                                                                                       static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta);
         if (int rc = check_launch("attn_delta_kernel")) return rc;
-        return attn_tc_bwd(qkv, dout, lse, delta, B, S, H, dqkv, st);
+        return attn_tc_bwd(qkv, dout, lse, delta, B, S, H, dqkv, st, row_begin);
     }
     if (hd == 64) return attn_bwd_launch<64>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);
     if (hd == 16) return attn_bwd_launch<16>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);
-    set_error("tvs_attn_bwd: head dim %d not supported (64 or 16)", hd);
+    set_error("tvs_attn_bwd_tail: head dim %d not supported (64 or 16)", hd);
     return -1;
+}
+
+extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S, int32_t H,
+                            int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv, void* stream) {
+    return tvs_attn_bwd_tail(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv, 0, stream);
 }

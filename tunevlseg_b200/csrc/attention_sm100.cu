@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(ATC_THREADS, MODE == MODE_FWD ? 3 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                const __grid_constant__ CUtensorMap map_qkv_in, const __grid_constant__ CUtensorMap map_do_in, int S, int H,
                __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out,
-               const float* __restrict__ lse_in, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv) {
+               const float* __restrict__ lse_in, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv, int ot0) {
     using L = AtcSmem<MODE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -94,7 +94,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     uint64_t* acc_full = bars + 7;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int ot = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int ot = blockIdx.x + ot0, h = blockIdx.y, b = blockIdx.z;     // ot0 > 0: only the outer tiles from ot0 on (tvs_attn_bwd_tail)
     const int E = H * AHD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int TI = L::TI, ITILE = L::ITILE;
@@ -881,7 +881,7 @@ static int make_tmap3(CUtensorMap* map, const void* ptr, int cols, int S, int B,
 template <int MODE>
 static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mqi, const CUtensorMap& mdi, int B, int S, int H,
                       __nv_bfloat16* out, float* out32, float* lse_out,
-                      const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st) {
+                      const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st, int ot0 = 0) {
     using L = AtcSmem<MODE>;
     auto kern = attn_tc_kernel<MODE>;
     static bool attr_set = false;
@@ -889,8 +889,8 @@ static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, const CUtens
         TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    dim3 grid((S + AT - 1) / AT, H, B);
-    TVS_CUDA(launch_pdl(kern, grid, dim3(ATC_THREADS), L::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv));
+    dim3 grid((S + AT - 1) / AT - ot0, H, B);
+    TVS_CUDA(launch_pdl(kern, grid, dim3(ATC_THREADS), L::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv, ot0));
     return check_launch(MODE == MODE_FWD ? "attn_tc_kernel<fwd>" : (MODE == MODE_DQ ? "attn_tc_kernel<dq>" : "attn_tc_kernel<dkv>"));
 }
 
@@ -922,14 +922,16 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
 }
 
 // delta must already hold rowsum(dO o O)
-int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st) {
+// row_begin > 0: dqkv is produced only for the 128-row tiles that contain rows >= row_begin (queries for dQ, keys for dK / dV)
+int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st, int row_begin) {
+    const int ot0 = row_begin / AT;
     CUtensorMap mq, md, mqi, mdi;      // 128-row boxes for the outer tiles, 64-row boxes for the inner ones
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&md, dout, H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, 64)) return rc;
     if (int rc = make_tmap3(&mdi, dout, H * AHD, S, B, 64)) return rc;
-    if (int rc = launch_atc<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st)) return rc;
-    return launch_atc<MODE_DQ>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st);
+    if (int rc = launch_atc<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st, ot0)) return rc;
+    return launch_atc<MODE_DQ>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st, ot0);
 }
 
 }  // namespace tvs

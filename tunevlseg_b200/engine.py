@@ -57,6 +57,10 @@ def tf32_rn(w: torch.Tensor) -> torch.Tensor:
 FFN_MODE = os.environ.get("TVS_FFN", "split")
 
 
+# TVS_TAIL=0: run the bottom block's backward on every row (A/B measurements); default: prompt rows only
+TAIL_PRUNE = os.environ.get("TVS_TAIL", "1") != "0"
+
+
 def split_bf16(w: torch.Tensor, head_only: bool = False):
     """w = hi + lo with both parts bf16 (|lo| <= 2^-9 |w|): operands of the three-product MMAs of the fused FFN."""
     w = w.detach().to(F32).contiguous()
@@ -237,9 +241,17 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     return x2, sv
 
 
-def encoder_layer_bwd(pk: PackedLayer, sv: Saved, g, g16, B, S, causal, key_mask):
+def _tail(t: torch.Tensor, B: int, S: int, n: int) -> torch.Tensor:
+    """The last n rows of every sample of a [B*S, ...] tensor as a contiguous [B*n, ...] copy."""
+    return t.view(B, S, -1)[:, S - n:].reshape(B * n, -1) if t.dim() > 1 else t.view(B, S)[:, S - n:].reshape(B * n)
+
+
+def encoder_layer_bwd(pk: PackedLayer, sv: Saved, g, g16, B, S, causal, key_mask, tail_rows: int = 0):
     """dgrad of the pre-LN block.  g / g16: f32 and bf16 copies of d(out) [B*S, D] -> (dx f32, dx bf16).
-    tf32 layers (text tower) keep the gradient stream in fp32 and ignore / do not produce the bf16 copy."""
+    tf32 layers (text tower) keep the gradient stream in fp32 and ignore / do not produce the bf16 copy.
+    ``tail_rows`` = n > 0 (bottom block of a prompted tower): only the last n rows of every sample still need a gradient
+    below this block, so the attention backward runs on the tiles holding them and the QKV dgrad / LayerNorm backward on
+    the gathered [B*n, D] rows; returns (dx rows f32 [B*n, D], None)."""
     M, D, F = B * S, pk.D, pk.F
     hi = pk.tf32
     if hi:
@@ -266,6 +278,16 @@ def encoder_layer_bwd(pk: PackedLayer, sv: Saved, g, g16, B, S, causal, key_mask
         q, k, v = sv.qkv[:, :D], sv.qkv[:, D:2 * D], sv.qkv[:, 2 * D:]
         abi.cross_attn_bwd(q, k, v, key_mask, sv.att, datt, sv.lse, B, S, S, pk.heads, pk.hd, dqkv[:, :D], dqkv[:, D:2 * D],
                            dqkv[:, 2 * D:], delta, causal=causal)
+    elif tail_rows and not hi:
+        n = tail_rows
+        dqkv = _e((M, 3 * D), BF16, g)      # rows below the tile of row S - n stay unwritten and unread
+        abi.attn_bwd(sv.qkv, sv.att, datt, sv.lse, B, S, pk.heads, pk.hd, causal, key_mask, delta, dqkv, row_begin=S - n)
+        dln1 = _e((B * n, D), BF16, g)
+        abi.gemm(_tail(dqkv, B, S, n), pk.wqkv_t, out_bf16=dln1)
+        g0 = _e((B * n, D), F32, g)
+        abi.layernorm_bwd(dln1, _tail(sv.x, B, S, n), pk.g1, _tail(sv.mean1, B, S, n), _tail(sv.rstd1, B, S, n),
+                          dx_add=_tail(g1, B, S, n), dx_f32=g0)
+        return g0, None
     else:
         dqkv = _e((M, 3 * D), BF16, g)
         abi.attn_bwd(sv.qkv, sv.att, datt, sv.lse, B, S, pk.heads, pk.hd, causal, key_mask, delta, dqkv)
@@ -427,11 +449,17 @@ class VisionTowerFn(torch.autograd.Function):
                 abi.prompt_grad(g.view(B, S, D), S - n, n, dctx[idx], zero_rows=True, dx_bf16=None if fresh else g16.view(B, S, D))
             if fresh:
                 abi.cast_bf16(g, g16)
-            g, g16 = encoder_layer_bwd(pk.v_layers[idx - 1], ctx.saved[idx - 1], g, g16, B, S, False, None)
+            tail = n if (idx == 1 and TAIL_PRUNE and n > 0) else 0     # below block 1 only the prompt rows carry a gradient
+            g, g16 = encoder_layer_bwd(pk.v_layers[idx - 1], ctx.saved[idx - 1], g, g16, B, S, False, None, tail_rows=tail)
         h_pre, mean_pre, rstd_pre = ctx.pre
-        dh = _e((B * S, D), F32, g)
-        abi.layernorm_bwd(g, h_pre, pk.pre_g, mean_pre, rstd_pre, dx_f32=dh)
-        abi.prompt_grad(dh.view(B, S, D), S - n, n, dctx[0], zero_rows=False)
+        if TAIL_PRUNE and n > 0:                # g holds the [B*n, D] prompt rows only
+            dh = _e((B * n, D), F32, g)
+            abi.layernorm_bwd(g, _tail(h_pre, B, S, n), pk.pre_g, _tail(mean_pre, B, S, n), _tail(rstd_pre, B, S, n), dx_f32=dh)
+            abi.prompt_grad(dh.view(B, n, D), 0, n, dctx[0], zero_rows=False)
+        else:
+            dh = _e((B * S, D), F32, g)
+            abi.layernorm_bwd(g, h_pre, pk.pre_g, mean_pre, rstd_pre, dx_f32=dh)
+            abi.prompt_grad(dh.view(B, S, D), S - n, n, dctx[0], zero_rows=False)
         ctx.saved = None
         return dctx, None, None, None
 
