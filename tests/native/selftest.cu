@@ -202,6 +202,28 @@ static void gemm_tf32_case(int M, int N, int K, int tile_n) {
     cudaFree(dA); cudaFree(dW); cudaFree(dBias); cudaFree(dOut);
 }
 
+// the shapes of the B = 32 training step with the automatic tile choice (dynamic tile scheduler on every multi-wave one)
+static void test_gemm_step_shapes() {
+#define STEP_CASE(...) do { printf("start %s\n", #__VA_ARGS__); __VA_ARGS__; } while (0)
+    STEP_CASE(gemm_case(15488, 768, 768, TVS_ACT_NONE, false, false, true, false, false, 0));
+    STEP_CASE(gemm_case(15648, 2304, 768, TVS_ACT_NONE, true, false, false, true, false, 0));
+    STEP_CASE(gemm_case(15648, 768, 768, TVS_ACT_NONE, true, true, true, false, false, 0));
+    STEP_CASE(gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, 0));
+    STEP_CASE(gemm_case(15648, 768, 3072, TVS_ACT_NONE, true, true, true, false, false, 0));
+    STEP_CASE(gemm_case(15648, 3072, 768, TVS_ACT_DQGELU, false, false, false, true, false, 0));
+    STEP_CASE(gemm_case(15648, 768, 3072, TVS_ACT_NONE, false, false, false, true, false, 0));
+    STEP_CASE(gemm_case(15648, 768, 768, TVS_ACT_NONE, false, false, false, true, false, 0));
+    STEP_CASE(gemm_case(15648, 768, 2304, TVS_ACT_NONE, false, false, false, true, false, 0));
+    STEP_CASE(gemm_case(15648, 768, 64, TVS_ACT_NONE, false, false, false, true, false, 0));
+    STEP_CASE(gemm_case(15648, 64, 192, TVS_ACT_NONE, false, true, true, false, false, 0));
+    STEP_CASE(gemm_tf32_case(15648, 64, 768, 0));
+    STEP_CASE(gemm_tf32_case(15648, 192, 64, 0));
+    STEP_CASE(gemm_tf32_case(15648, 64, 64, 0));
+    STEP_CASE(gemm_tf32_case(15488, 256, 64, 0));
+    STEP_CASE(gemm_tf32_case(15488, 25, 64, 0));
+    STEP_CASE(gemm_tf32_case(384, 2048, 512, 0));
+#undef STEP_CASE
+}
 static void test_gemm() {
     gemm_tf32_case(128, 64, 32, 64);
     gemm_tf32_case(300, 192, 64, 0);
@@ -649,6 +671,7 @@ int main(int argc, char** argv) {
     if (what == "attn" || what == "all") test_attn();
     if (what == "gemm" || what == "all") test_gemm();
     if (what == "ffn" || what == "all") test_ffn(what == "ffn");
+    if (what == "gemmstep" || what == "all") test_gemm_step_shapes();
     if (what == "lnprof") { ln_case(37, 768); ln_case(5, 512); ln_case(33, 256); ln_case(1003, 64); ln_case(9, 1024); ln_case(7, 2048); ln_timing(15648, 768); }
     if (what == "gemmprof") {   // epilogue cost isolation on the fc1 shape (for timing / ncu)
         const int bn = argc > 3 ? atoi(argv[3]) : 256;

@@ -378,13 +378,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int SCHED_D = 4;      // depth of the dynamic tile ring
+
 template <int BN, int STAGES, int CL>
 struct GemmSmem {
     static constexpr int A_BYTES = BM * BK_BYTES;
     static constexpr int B_BYTES = (BN / CL) * BK_BYTES;        // cta_group::2: each CTA of the pair holds half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int EPI_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;     // 16-byte aligned
+    static constexpr int SCHED_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;   // tile ring: full[4], empty[4] barriers, 4 tile indices
+    static constexpr int EPI_OFFSET = SCHED_OFFSET + 2 * SCHED_D * 8 + SCHED_D * 4;   // 16-byte aligned
     static constexpr int TOTAL = EPI_OFFSET + 4 * EPI_WARP_FLOATS * 4 + 1024;     // + alignment slack
 };
 
@@ -441,10 +444,79 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {   // arrives on
                  : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// dynamic tile scheduler
+// ---------------------------------------------------------------------------------------------
+// The kernel is persistent with one CTA (pair) per SM.  With a static round-robin tile list a CTA that STARTS late
+// finishes late by the same amount, and the whole kernel with it: inside the training step the text tower runs on a
+// second stream, and whenever one of its ~250 small kernels holds a few SMs at the moment a vision-tower GEMM is launched
+// the GEMM's tail grows by that kernel's duration (measured: the 15648x3072x768 GEMM 89 -> 103 us, QKV 52 -> 71 us).
+// With a shared counter a late CTA simply takes fewer tiles.  [Result: no gain, see launch_gemm_cl - the static list stays
+// the default and this path is an opt-in experiment.]  Warp 3 of the (leader) CTA draws tile indices from a
+// global counter and publishes them through a 4-deep shared-memory ring (in pair mode also into the peer's ring, remote
+// store + cluster-scope release arrive); producer, MMA issuer and the eight epilogue warps each read every entry and
+// release it on the leader's `empty` barrier.  -1 ends the loops.  The cluster that draws the last sentinel resets the
+// counter pair, so a slot is clean again when its kernel has finished (graph replays reuse the slot of their node).
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "WAIT_DONE_C:\n\t"
+        "}" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int CL>
+struct TileIter {
+    // static part
+    int cur, step, num;
+    // dynamic part
+    bool dyn;
+    volatile int* s_tile;
+    uint64_t* sf;
+    uint64_t* se;
+    uint32_t slot, par, cta_rank;
+
+    __device__ __forceinline__ int next() {      // called by every lane of a converged warp
+        if (!dyn) {
+            const int t = cur;
+            cur += step;
+            return t < num ? t : -1;
+        }
+        if (CL == 2) {
+            mbar_wait_acq_cluster(&sf[slot], par);
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        } else {
+            mbar_wait(&sf[slot], par);
+        }
+        const int t = s_tile[slot];
+        __syncwarp();                                                  // every lane has read the entry
+        if ((threadIdx.x & 31) == 0) {
+            if (CL == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&se[slot]), 0));
+            else mbar_arrive(&se[slot]);
+        }
+        if (++slot == SCHED_D) { slot = 0; par ^= 1; }
+        return t;
+    }
+};
+
 template <int BN, int STAGES, bool TF32, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
-                         int N, int K, GemmEpilogue ep) {
+                         int N, int K, GemmEpilogue ep, int* __restrict__ sched) {
     using L = GemmSmem<BN, STAGES, CL>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -455,6 +527,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* sched_full = reinterpret_cast<uint64_t*>(smem + L::SCHED_OFFSET);
+    uint64_t* sched_empty = sched_full + SCHED_D;
+    volatile int* sched_tile = reinterpret_cast<volatile int*>(sched_empty + SCHED_D);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -479,6 +554,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         mbar_init(&tmem_full[1], 1);
         mbar_init(&tmem_empty[0], 8 * CL);
         mbar_init(&tmem_empty[1], 8 * CL);
+#pragma unroll
+        for (int d = 0; d < SCHED_D; ++d) {
+            mbar_init(&sched_full[d], 1);
+            mbar_init(&sched_empty[d], CL == 2 ? 19 : 10);     // producer + MMA issuer + 8 epilogue warps (+ the peer's producer and 8 epilogue warps)
+        }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -498,10 +578,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     pdl_wait();        // everything above is private set-up; from here on the kernel reads what its predecessor wrote
     pdl_trigger();
 
-    if (warp == 0) {
+    TileIter<CL> tiles;
+    tiles.cur = first_tile; tiles.step = tile_step; tiles.num = num_tiles;
+    tiles.dyn = sched != nullptr; tiles.s_tile = sched_tile; tiles.sf = sched_full; tiles.se = sched_empty;
+    tiles.slot = 0; tiles.par = 0; tiles.cta_rank = cta_rank;
+
+    if (warp == 3) {
+        if (sched != nullptr && cta_rank == 0) {
+            // ------------------------------------------------------------------ tile scheduler
+            uint32_t slot = 0, par = 0;
+            for (;;) {
+                mbar_wait(&sched_empty[slot], par ^ 1);
+                int t = 0;
+                if (lane == 0) {
+                    t = atomicAdd(&sched[0], 1);
+                    if (t >= num_tiles) t = -1;
+                    sched_tile[slot] = t;
+                    if (CL == 2) {
+                        st_cluster_u32(mapa_u32(smem_u32(const_cast<int*>(&sched_tile[slot])), 1), static_cast<uint32_t>(t));
+                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                        mbar_arrive_release_cluster(mapa_u32(smem_u32(&sched_full[slot]), 1));
+                    }
+                    mbar_arrive(&sched_full[slot]);
+                }
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t < 0) break;
+                if (++slot == SCHED_D) { slot = 0; par ^= 1; }
+            }
+            // every cluster draws exactly one sentinel; the last one to do so puts the counter pair back to zero
+            if (lane == 0) {
+                const int clusters = gridDim.x / CL;
+                if (atomicAdd(&sched[1], 1) == clusters - 1) {
+                    sched[1] = 0;
+                    __threadfence();
+                    sched[0] = 0;
+                }
+            }
+        }
+    } else if (warp == 0) {
         {
             uint32_t stage = 0, phase = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            for (int tile = tiles.next(); tile >= 0; tile = tiles.next()) {
                 const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -532,7 +649,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc(BM * CL, BN, TF32 ? 2u : 1u);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+            for (int tile = tiles.next(); tile >= 0; tile = tiles.next()) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -578,7 +695,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int ew = (warp - 4) & 3;     // TMEM lane quarter = warp % 4
         const int grp = (warp - 4) >> 2;   // 0 / 1
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        for (int tile = tiles.next(); tile >= 0; tile = tiles.next()) {
             const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -687,6 +804,24 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
     return 0;
 }
 
+// counter pairs {next tile, clusters done} of the dynamic tile scheduler: zero at module load, self-resetting (see the
+// kernel), handed out round-robin - a pair is reused 4096 scheduled launches later, long after its kernel has finished
+constexpr int SCHED_SLOTS = 4096;
+__device__ int g_sched[2 * SCHED_SLOTS];
+
+static int* sched_slot() {
+    static int* base[64] = {};
+    static unsigned seq = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!base[dev]) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_sched) != cudaSuccess) return nullptr;
+        base[dev] = static_cast<int*>(p);
+    }
+    return base[dev] + 2 * (seq++ % SCHED_SLOTS);
+}
+
 template <int BN, int STAGES, bool TF32, int CL>
 static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES, CL>;
@@ -702,7 +837,18 @@ static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaSt
     const int tiles = (((a.M + BM - 1) / BM + CL - 1) / CL) * ((a.N + BN - 1) / BN);
     const int max_clusters = sm_count() / CL;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    TVS_CUDA(launch_pdl(kern, dim3(clusters * CL), dim3(GEMM_THREADS), L::TOTAL, stream, CL, ta, tw, a.M, a.N, a.K, ep));
+    // TVS_GEMM_SCHED: "static" round-robin tiles; "cl1" / "cl2" dynamic only for single-CTA / pair kernels; "memset" also zeroes the
+    // counter pair in the stream before every launch (debug switches)
+    // Default: static.  Measured on the B = 32 step (same-box pairs): dynamic for single-CTA kernels only 10.03 ms vs 9.95 ms static, dynamic
+    // for the pair kernels 10.50 ms (nine remote arrivals per tile and peer) - the interference from the text-tower stream is not a
+    // late-start tail, so the scheduler buys nothing; and a pair cluster that draws NO tile (forced with "force" + TVS_GEMM_CLUSTER=2)
+    // hangs at exit.  Kept as an experiment switch ("dyn", "cl1") - never the default.
+    static const char mode = [] { const char* e = getenv("TVS_GEMM_SCHED"); return e ? (e[0] == 'c' ? e[2] : e[0]) : 's'; }();
+    const bool dyn_ok = mode == 'd' || mode == 'm' || mode == 'f' || (mode == '1' && CL == 1) || (mode == '2' && CL == 2);
+    int* sched = (dyn_ok && (tiles > clusters || mode == 'f')) ? sched_slot() : nullptr;      // one tile per cluster needs no scheduler
+    const int launch_clusters = mode == 'f' ? max_clusters : clusters;      // "force": every SM gets a CTA, most of them draw no tile at all (test switch)
+    if (sched && mode == 'm') TVS_CUDA(cudaMemsetAsync(sched, 0, 2 * sizeof(int), stream));
+    TVS_CUDA(launch_pdl(kern, dim3(launch_clusters * CL), dim3(GEMM_THREADS), L::TOTAL, stream, CL, ta, tw, a.M, a.N, a.K, ep, sched));
     return check_launch("gemm_bf16_tcgen05_kernel");
 }
 

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 from abc import ABC, abstractmethod
 
+import os
+
 import torch
 from torch import nn
 
@@ -99,6 +101,8 @@ class BaseCLIPSeg(HFCLIPSegWrapper, ABC):
         return engine.TextTowerFn.apply(emb, deep, key_mask, pool, pk, n)
 
     def _text_stream(self) -> torch.cuda.Stream:
+        if os.environ.get("TVS_TEXT_STREAM", "1") == "0":      # A/B switch: text tower in line with the vision tower
+            return torch.cuda.current_stream()
         st = getattr(self, "_tvs_text_stream", None)
         if st is None or st.device != torch.cuda.current_stream().device:
             st = torch.cuda.Stream()
