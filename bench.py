@@ -391,8 +391,19 @@ def main():
     # Hold the stream back (~75 ms of device-side spinning) while the host enqueues the whole step: otherwise every kernel
     # that follows a short one is timed together with the host's ~25 us submission gap (measured: the QKV and fc1 GEMMs,
     # which follow a 17 us LayerNorm, looked 30-50 % slower than they run inside the captured graph).
+    # The text tower is run in line for this one pass (TVS_TEXT_STREAM=0): on its own stream its ~250 small kernels share the
+    # SMs with whatever is being timed (the same GEMM reads 103 us instead of 89 us), which says nothing about the kernel.
+    # The ncu launch list (serialised by construction) agrees with the in-line numbers (profiles/r01b_ncu_launches_summary.md).
     torch.cuda._sleep(150_000_000)
-    step_eager()
+    prev = os.environ.get("TVS_TEXT_STREAM")
+    os.environ["TVS_TEXT_STREAM"] = "0"
+    try:
+        step_eager()
+    finally:
+        if prev is None:
+            os.environ.pop("TVS_TEXT_STREAM", None)
+        else:
+            os.environ["TVS_TEXT_STREAM"] = prev
     torch.cuda.synchronize()
     abi.set_profiler(None)
     if rank == 0:
@@ -420,6 +431,7 @@ def main():
         roof = {"bound": "tensor", "kernel": k, "achieved": round(achieved, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / pk["tf_sustained"], 4), "traffic": traffic, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                 "launches_per_step": c, "avg_launch_us": round(1e3 * t / c, 1), "share_of_step": round(t / total, 3),
+                "timing": "CUDA events around every launch of one eager step, text tower in line, host enqueued ahead of the device",
                 "family_share_of_step": round(fam_t / total, 3)}
 
     cpu = None

@@ -224,12 +224,12 @@ __global__ void film_fwd_kernel(const float* __restrict__ x, const float* __rest
     }
 }
 
-// one block (256 threads) per sample: thread (grp, d) sums rows s = grp, grp + ngrp, ... of channel d, then a
+// one block (1024 threads) per sample: thread (grp, d) sums rows s = grp, grp + ngrp, ... of channel d, then a
 // shared-memory reduction over the groups.  dmul[b,d] = sum_s dy*x ; dadd[b,d] = sum_s dy ; dx = mul * dy
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 film_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mul, int S, int D,
                 float* __restrict__ dx, float* __restrict__ dmul, float* __restrict__ dadd) {
-    __shared__ float sm_m[256], sm_a[256];
+    __shared__ float sm_m[1024], sm_a[1024];
     const int b = blockIdx.x;
     const int ngrp = max(1, static_cast<int>(blockDim.x) / D);
     for (int d0 = 0; d0 < D; d0 += blockDim.x) {
@@ -282,7 +282,7 @@ constexpr int HEAD_MAXK = 7;   // ksize <= 7
 // pixel then needs 2*ks shared-memory reads instead of 4*ks*ks (the first version was LDS/ALU bound at 187 us; the
 // kernel's traffic - tconv in, logits (+ add_out) out - is worth ~10 us).
 constexpr int HEAD_THREADS = 512;     // upper bound; the launch uses the image width rounded up to a warp
-__global__ void __launch_bounds__(HEAD_THREADS)
+__global__ void __launch_bounds__(HEAD_THREADS, 2)
 head_fwd_kernel(const float* __restrict__ tconv, long long ld_t, const float* __restrict__ addmap, long long ld_a, const float* __restrict__ bias_t,
                 const float* __restrict__ bias_a, const float* __restrict__ ratio, int blend, int G, int P, int ks, float* __restrict__ logits,
                 float* __restrict__ add_out) {
@@ -290,8 +290,8 @@ head_fwd_kernel(const float* __restrict__ tconv, long long ld_t, const float* __
     const int gy = blockIdx.x, b = blockIdx.y;
     const int KK = ks * ks, W = G * P, half = (ks - 1) / 2;
     float* s_add = s_head;                          // [3][G][KK]  addmap rows gy-1 .. gy+1 (clamped)
-    float* s_T = s_add + 3 * G * KK;                // [2][G][ks]  double-buffered per pixel row
-    int* s_y0 = reinterpret_cast<int*>(s_T + 2 * G * ks);       // [P][ks] row taps relative to gy-1
+    float* s_T = s_add + 3 * G * KK;                // [P][G][ks]  the y-interpolated, ky-contracted additive map of every pixel row
+    int* s_y0 = reinterpret_cast<int*>(s_T + P * G * ks);       // [P][ks] row taps relative to gy-1
     int* s_y1 = s_y0 + P * ks;
     float* s_wy = reinterpret_cast<float*>(s_y1 + P * ks);
     float wa = 1.f, wb = 0.f;
@@ -325,25 +325,55 @@ head_fwd_kernel(const float* __restrict__ tconv, long long ld_t, const float* __
             if (kx < ks) bilin(min(max(X + kx - half, 0), W - 1), P, G, x0[kx], x1[kx], wx[kx]);
     }
     const int gx = X / P, px = X - gx * P;
+    // this thread's column of the transposed-convolution patch row: all P loads in flight before anything waits on them
+    constexpr int PMAX = 16;
+    float tv[PMAX];
+    const float* trow = tconv + (static_cast<long long>(b) * G * G + gy * G + gx) * ld_t + px;
+    if (X < W && P <= PMAX) {
+#pragma unroll
+        for (int py = 0; py < PMAX; ++py)
+            if (py < P) tv[py] = trow[py * P];
+    }
     __syncthreads();
-    for (int py = 0; py < P; ++py) {
-        const int Y = gy * P + py;
-        float* T = s_T + (py & 1) * G * ks;
-        if (blend != 0) {
-            for (int i = threadIdx.x; i < G * ks; i += blockDim.x) {
-                const int xi = i / ks, kx = i - xi * ks;
-                float acc = 0.f;
-                for (int ky = 0; ky < ks; ++ky) {
-                    const float lo = s_add[(s_y0[py * ks + ky] * G + xi) * KK + ky * ks + kx];
-                    const float hi = s_add[(s_y1[py * ks + ky] * G + xi) * KK + ky * ks + kx];
-                    acc += lo + s_wy[py * ks + ky] * (hi - lo);
-                }
-                T[i] = acc;
+    if (blend != 0) {
+        // T[py][xi][kx] for every pixel row of the patch row at once (one barrier instead of one per row)
+        for (int i = threadIdx.x; i < P * G * ks; i += blockDim.x) {
+            const int py = i / (G * ks), r = i - py * (G * ks);
+            const int xi = r / ks, kx = r - xi * ks;
+            float acc = 0.f;
+            for (int ky = 0; ky < ks; ++ky) {
+                const float lo = s_add[(s_y0[py * ks + ky] * G + xi) * KK + ky * ks + kx];
+                const float hi = s_add[(s_y1[py * ks + ky] * G + xi) * KK + ky * ks + kx];
+                acc += lo + s_wy[py * ks + ky] * (hi - lo);
             }
-            __syncthreads();      // T of this row is complete; the other buffer is free for the next row
+            s_T[i] = acc;
         }
-        if (X < W) {
-            float v = wa * (tconv[(static_cast<long long>(b) * G * G + gy * G + gx) * ld_t + py * P + px] + bt);
+        __syncthreads();
+    }
+    if (X < W) {
+#pragma unroll
+        for (int py = 0; py < PMAX; ++py) {
+            if (py >= P) break;
+            const int Y = gy * P + py;
+            const float* T = s_T + py * G * ks;
+            float v = wa * ((P <= PMAX ? tv[py] : trow[py * P]) + bt);
+            if (blend != 0) {
+                float acc = ba;
+#pragma unroll
+                for (int kx = 0; kx < HEAD_MAXK; ++kx)
+                    if (kx < ks) {
+                        const float lo = T[x0[kx] * ks + kx], hi = T[x1[kx] * ks + kx];
+                        acc += lo + wx[kx] * (hi - lo);
+                    }
+                if (add_out) add_out[(static_cast<long long>(b) * W + Y) * W + X] = acc;
+                v += wb * acc;
+            }
+            logits[(static_cast<long long>(b) * W + Y) * W + X] = v;
+        }
+        for (int py = PMAX; py < P; ++py) {        // patch sizes above 16 (not a CLIPSeg / CRIS geometry): plain loop
+            const int Y = gy * P + py;
+            const float* T = s_T + py * G * ks;
+            float v = wa * (trow[py * P] + bt);
             if (blend != 0) {
                 float acc = ba;
 #pragma unroll
@@ -576,7 +606,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_film_fwd(const float* 
 extern "C" __attribute__((visibility("default"))) int tvs_film_bwd(const float* dy, const float* x, const float* mul, int32_t B, int32_t S, int32_t D, float* dx, float* dmul,
                             float* dadd, void* stream) {
     TVS_REQUIRE(dy && x && mul && dx && dmul && dadd, "tvs_film_bwd: null pointer");
-    film_bwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, x, mul, S, D, dx, dmul, dadd);
+    film_bwd_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(dy, x, mul, S, D, dx, dmul, dadd);     // one block per sample: 1024 threads = 16 row groups at D = 64
     return check_launch("film_bwd_kernel");
 }
 
@@ -588,7 +618,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_head_fwd(const float* 
     TVS_REQUIRE(blend == 0 || (addmap && ksize >= 1 && ksize <= HEAD_MAXK && (ksize & 1)), "tvs_head_fwd: additive branch needs addmap and odd ksize <= %d", HEAD_MAXK);
     TVS_REQUIRE(blend != 1 || ratio, "tvs_head_fwd: ratio required for blend=1");
     TVS_REQUIRE(G * P <= HEAD_THREADS, "tvs_head_fwd: image width %d exceeds the %d columns one block covers", G * P, HEAD_THREADS);
-    const size_t sh = blend ? (static_cast<size_t>(3) * G * ksize * ksize + 2 * G * ksize + 3 * P * ksize) * sizeof(float) : 0;
+    const size_t sh = blend ? (static_cast<size_t>(3) * G * ksize * ksize + static_cast<size_t>(P) * G * ksize + 3 * P * ksize) * sizeof(float) : 0;
     TVS_REQUIRE(sh <= 48 * 1024, "tvs_head_fwd: grid too large for the shared-memory neighbourhood");
     const int threads = max(128, (G * P + 31) / 32 * 32);
     head_fwd_kernel<<<dim3(G, B), threads, sh, static_cast<cudaStream_t>(stream)>>>(tconv, ld_tconv, addmap, ld_addmap, bias_t, bias_a, ratio, blend, G, P,

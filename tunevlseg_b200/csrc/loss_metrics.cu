@@ -20,7 +20,7 @@ namespace tvs {
 constexpr int LOSS_THREADS = 256;
 
 static int loss_blocks_per_sample(int B, long long N) {
-    long long want = (4LL * sm_count() + B - 1) / B;
+    long long want = (16LL * sm_count() + B - 1) / B;     // ~8 resident blocks per SM: the kernels are latency bound on their two loads per pixel quad
     long long cap = (N + 4 * LOSS_THREADS - 1) / (4 * LOSS_THREADS);
     long long n = want < cap ? want : cap;
     return static_cast<int>(n < 1 ? 1 : n);
@@ -38,13 +38,16 @@ __device__ __forceinline__ void pixel(float x, float y, float thr, PixelStats& s
     if (PROBS) {
         p = x;   // the caller already holds probabilities (metric(preds, target) API): threshold them as they are
     } else {
-        float e = __expf(-x);
-        p = __fdiv_rn(1.0f, 1.0f + e);
-        if (fabsf(p - thr) < 1e-4f) {
-            e = static_cast<float>(exp(-static_cast<double>(x)));
+        // fast path: one MUFU.EX2, one MUFU.RCP, one MUFU.LG2 per pixel (an IEEE division plus log1pf had made this HBM-sized
+        // kernel instruction bound).  t = exp(-|x|) in (0, 1]; sigmoid(x) = 1 / (1 + t) for x >= 0, t / (1 + t) otherwise.
+        const float t = __expf(-fabsf(x));
+        const float r = __fdividef(1.0f, 1.0f + t);
+        p = x >= 0.f ? r : t * r;
+        if (fabsf(p - thr) < 1e-4f) {      // the integer counters must match fl32(1 / fl32(1 + fl32(exp(-x)))) exactly
+            const float e = static_cast<float>(exp(-static_cast<double>(x)));
             p = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
         }
-        s.bce += fmaxf(x, 0.f) - x * y + log1pf(__expf(-fabsf(x)));
+        s.bce += fmaxf(x, 0.f) - x * y + __logf(1.0f + t);
     }
     s.I += p * y;
     s.P += p;
@@ -117,28 +120,43 @@ dicebce_partial_kernel(const float* __restrict__ logits, const float* __restrict
     }
 }
 
-__global__ void dicebce_finalize_kernel(const double* __restrict__ part_in, const long long* __restrict__ cnt_in, int B, int nblk, long long N,
-                                        float lambda_dice, float lambda_ce, double* __restrict__ parts, long long* __restrict__ counts,
-                                        long long* __restrict__ confmat, float* __restrict__ loss) {
+// one warp per sample: lanes stride over the blocks of that sample, then a fixed-order butterfly - deterministic, and the
+// nblk * 11 loads of a sample are in flight together (the first version walked them serially in one thread per sample: 33 us)
+__global__ void __launch_bounds__(256)
+dicebce_finalize_kernel(const double* __restrict__ part_in, const long long* __restrict__ cnt_in, int B, int nblk, long long N,
+                        float lambda_dice, float lambda_ce, double* __restrict__ parts, long long* __restrict__ counts,
+                        long long* __restrict__ confmat, float* __restrict__ loss) {
     extern __shared__ double sh[];  // [B] dice term, [B] bce sum, then 4*B int64 conf
     double* s_dice = sh;
     double* s_bce = sh + B;
     long long* s_conf = reinterpret_cast<long long*>(sh + 2 * B);
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int b = warp; b < B; b += nwarp) {
         double p[4] = {0, 0, 0, 0};
         long long c[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int k = 0; k < nblk; ++k) {
+        for (int k = lane; k < nblk; k += 32) {
             const long long slot = static_cast<long long>(b) * nblk + k;
+#pragma unroll
             for (int j = 0; j < 4; ++j) p[j] += part_in[slot * 4 + j];
+#pragma unroll
             for (int j = 0; j < 7; ++j) c[j] += cnt_in[slot * 7 + j];
         }
-        if (parts)
-            for (int j = 0; j < 4; ++j) parts[b * 4 + j] = p[j];
-        if (counts)
-            for (int j = 0; j < 3; ++j) counts[b * 3 + j] = c[j];
-        for (int j = 0; j < 4; ++j) s_conf[b * 4 + j] = c[3 + j];
-        s_dice[b] = 1.0 - (2.0 * p[0] + 1e-5) / (p[1] + p[2] + 1e-5);
-        s_bce[b] = p[3];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) c[j] += __shfl_xor_sync(0xffffffffu, c[j], o);
+        }
+        if (lane == 0) {
+            if (parts)
+                for (int j = 0; j < 4; ++j) parts[b * 4 + j] = p[j];
+            if (counts)
+                for (int j = 0; j < 3; ++j) counts[b * 3 + j] = c[j];
+            for (int j = 0; j < 4; ++j) s_conf[b * 4 + j] = c[3 + j];
+            s_dice[b] = 1.0 - (2.0 * p[0] + 1e-5) / (p[1] + p[2] + 1e-5);
+            s_bce[b] = p[3];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -172,7 +190,9 @@ dicebce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ m
     const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
     auto f = [&](float xv, float yv) {
-        const float p = sigmoidf_fast(xv);
+        const float t = __expf(-fabsf(xv));
+        const float r = __fdividef(1.0f, 1.0f + t);
+        const float p = xv >= 0.f ? r : t * r;
         return (a * yv + c) * p * (1.0f - p) + w * (p - yv);
     };
     if (vec) {
