@@ -44,6 +44,17 @@ __device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2, flushes
 // inner tile rows: 64 per step, so that the TMEM footprint is 128 columns in the forward (S + O: three CTAs per SM,
 // bounded by registers) and 256 in the backward kernels (S + dP + accumulators: two CTAs per SM).  Co-resident CTAs
 // overlap one CTA's exp stage, prologue and epilogue with another CTA's MMAs.
+__device__ __forceinline__ void store_row_bf16_32(__nv_bfloat16* dst, const uint32_t (&a)[32]) {
+    // 32 fp32 accumulators -> 32 bf16 = 64 bytes = 2 x 256-bit stores
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(a[16 * q + 2 * i]), __uint_as_float(a[16 * q + 2 * i + 1]));
+        st_global_256(dst + 16 * q, w);
+    }
+}
+
 template <int MODE>
 struct AtcSmem {
     static constexpr int TI = 64;
@@ -72,8 +83,14 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
     }
 }
 
+// Backward modes run EIGHT element-wise warps: two per TMEM lane quarter, each owning 32 of the 64 score columns of a step
+// (no row-wise reduction is needed in the backward: p and dS are element-wise given lse and delta).  With one warp per
+// scheduler and CTA the TMEM load -> exp -> pack -> TMEM store chain of a step was exposed; four warps per scheduler
+// (two CTAs per SM) hide each other's latencies.  Each warp writes its packed P / dS into the first 16 columns of the 32
+// columns it has just read itself, so no store can land on a column another warp still has to load.
+constexpr int ATC_THREADS_BWD = 320;
 template <int MODE>
-__global__ void __launch_bounds__(ATC_THREADS, MODE == MODE_FWD ? 3 : 2)
+__global__ void __launch_bounds__(MODE == MODE_FWD ? ATC_THREADS : ATC_THREADS_BWD, MODE == MODE_FWD ? 3 : 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                const __grid_constant__ CUtensorMap map_qkv_in, const __grid_constant__ CUtensorMap map_do_in, int S, int H,
                __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out,
@@ -97,6 +114,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     const int ot = blockIdx.x + ot0, h = blockIdx.y, b = blockIdx.z;     // ot0 > 0: only the outer tiles from ot0 on (tvs_attn_bwd_tail)
     const int E = H * AHD;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int EW_WARPS = MODE == MODE_FWD ? 4 : 8;       // element-wise warps; then the TMA producer, then the MMA issuer
+    constexpr int W_TMA = EW_WARPS, W_MMA = EW_WARPS + 1;
     constexpr int TI = L::TI, ITILE = L::ITILE;
     const int n_in = (S + TI - 1) / TI;
     const int n_it = MODE == MODE_FWD ? 2 * n_in : n_in;
@@ -115,11 +134,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             mbar_init(&in_empty[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(ew_done, 128);
+        mbar_init(ew_done, EW_WARPS * 32);
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -127,7 +146,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     pdl_wait();        // set-up above is private; q / k / v (and dO, lse, delta) come from the preceding kernels
     pdl_trigger();
 
-    if (warp == 4) {
+    if (warp == W_TMA) {
         // ------------------------------------------------------------------ TMA producer
         const int cq = h * AHD, ck = E + h * AHD, cv = 2 * E + h * AHD;
         if (elect_one()) {
@@ -179,11 +198,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             }
             __syncwarp();
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
         {
             constexpr uint32_t idesc_s = umma_idesc_bf16(AT, TI, 0, 0);
             constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
+            // backward: the packed A operand of K-step k (16 inner rows = 8 columns) - the two element-wise halves leave their
+            // 16 packed columns at offsets 0 and 32 of the 64-column block they read
+            auto PK = [](int k) -> uint32_t { return k < 2 ? 8u * k : 32u + 8u * (k - 2); };
             mbar_wait(outer_full, 0);
             tc_fence_after();
             const uint64_t a0 = umma_desc_sw128(smem_u32(s_outer0));
@@ -233,15 +255,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                     if (elect_one()) {
                         if (MODE == MODE_DQ) {
 #pragma unroll
-                            for (int k = 0; k < TI / 16; ++k)   // dQ += dS K_j
-                                umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < TI / 16; ++k)   // dQ += dS K_j   (dS: packed columns [0,16) and [32,48) of the S block)
+                                umma_ts(tb + C_ACC0, tb + C_S + PK(k), b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
                         } else {
 #pragma unroll
                             for (int k = 0; k < TI / 16; ++k)   // dV += P^T dO_i
-                                umma_ts(tb + C_ACC0, tb + C_S + 8 * k, b1 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                                umma_ts(tb + C_ACC0, tb + C_S + PK(k), b1 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
                             for (int k = 0; k < TI / 16; ++k)   // dK += dS^T Q_i
-                                umma_ts(tb + C_ACC1, tb + C_DP + 8 * k, b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                                umma_ts(tb + C_ACC1, tb + C_DP + PK(k), b0 + 128 * k, idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit(&in_empty[stage]);
                         if (last) umma_commit(acc_full);
@@ -251,9 +273,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             }
         }
     } else {
-        // ------------------------------------------------------------------ element-wise stage (thread = TMEM lane = row)
-        const int tid = threadIdx.x;
-        const uint32_t tl = tb + (static_cast<uint32_t>(warp * 32) << 16);
+        // ------------------------------------------------------------------ element-wise stage (thread = TMEM lane = row;
+        // backward: two warps per lane quarter, `half` selects the 32-column half of every 64-column block)
+        const int quarter = warp & 3, half = warp >> 2;          // half is 0 in the forward (four warps)
+        const int tid = quarter * 32 + lane;
+        const uint32_t tl = tb + (static_cast<uint32_t>(quarter * 32) << 16);
         const int row = ot * AT + tid;
         const bool row_ok = row < S;
         if (MODE == MODE_FWD) {
@@ -336,55 +360,48 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 lse_out[bh * S + row] = (m == -INFINITY ? 0.f : m) + logf(fmaxf(l, 1e-30f));
             }
         } else {
-            // backward: rows are queries (DQ) or keys (DKV)
+            // backward: rows are queries (DQ) or keys (DKV); this thread owns columns [32 half, 32 half + 32) of S and dP
             const float my_lse = (MODE == MODE_DQ && row_ok) ? lse_in[bh * S + row] * L2E : INFINITY;
             const float my_del = (MODE == MODE_DQ && row_ok) ? delta_in[bh * S + row] : 0.f;
+            const uint32_t tS = tl + C_S + 32 * half, tD = tl + C_DP + 32 * half;
             for (int it = 0; it < n_it; ++it) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                const int c0 = it * TI;                      // first inner row (key for DQ, query for DKV)
-                const float* v_lse = s_vec + (it & 1) * 2 * TI;
+                const int c0 = it * TI + 32 * half;          // first inner row of this half (key for DQ, query for DKV)
+                const float* v_lse = s_vec + (it & 1) * 2 * TI + 32 * half;
                 const float* v_del = v_lse + TI;
-                // software pipeline over the two 32-column chunks: chunk 1's TMEM loads fly while chunk 0 is processed
-                uint32_t sA[32], dA[32], sB[32], dB[32];
-                tmem_ld32(tl + C_S, sA);
-                tmem_ld32(tl + C_DP, dA);
+                uint32_t sA[32], dA[32];
+                tmem_ld32(tS, sA);
+                tmem_ld32(tD, dA);
                 tmem_ld_wait();
-                tmem_ld32(tl + C_S + 32, sB);
-                tmem_ld32(tl + C_DP + 32, dB);
+                uint32_t pkp[16], pks[16];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {                // 32 score columns -> 16 packed bf16x2 columns
-                    uint32_t pkp[16], pks[16];
-                    if (c == 1) tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float s0 = __uint_as_float(c == 0 ? sA[i] : sB[i]), s1 = __uint_as_float(c == 0 ? sA[i + 1] : sB[i + 1]);
-                        const float g0 = __uint_as_float(c == 0 ? dA[i] : dB[i]), g1 = __uint_as_float(c == 0 ? dA[i + 1] : dB[i + 1]);
-                        float p0, p1, d0, d1;
-                        if (MODE == MODE_DQ) {
-                            p0 = (c0 + 32 * c + i < S) ? fast_exp2(fmaf(s0, L2E, -my_lse)) : 0.f;
-                            p1 = (c0 + 32 * c + i + 1 < S) ? fast_exp2(fmaf(s1, L2E, -my_lse)) : 0.f;
-                            d0 = p0 * (g0 - my_del);
-                            d1 = p1 * (g1 - my_del);
-                        } else {
-                            const int q = 32 * c + i;      // lse = +inf for queries past the end -> p = 0
-                            p0 = row_ok ? fast_exp2(fmaf(s0, L2E, -v_lse[q])) : 0.f;
-                            p1 = row_ok ? fast_exp2(fmaf(s1, L2E, -v_lse[q + 1])) : 0.f;
-                            d0 = p0 * (g0 - v_del[q]);
-                            d1 = p1 * (g1 - v_del[q + 1]);
-                        }
-                        pks[i / 2] = pack_bf16x2(d0, d1);
-                        if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
-                    }
-                    // the packed values overwrite the first half of the columns just consumed (chunk c -> columns 16c..);
-                    // all four loads have completed before the first store (c == 0 stores touch columns 0..15 only, which
-                    // belong to chunk 0, already in registers)
+                for (int i = 0; i < 32; i += 2) {
+                    const float s0 = __uint_as_float(sA[i]), s1 = __uint_as_float(sA[i + 1]);
+                    const float g0 = __uint_as_float(dA[i]), g1 = __uint_as_float(dA[i + 1]);
+                    float p0, p1, d0, d1;
                     if (MODE == MODE_DQ) {
-                        tmem_st16(tl + C_S + 16 * c, pks);        // dS
+                        p0 = (c0 + i < S) ? fast_exp2(fmaf(s0, L2E, -my_lse)) : 0.f;
+                        p1 = (c0 + i + 1 < S) ? fast_exp2(fmaf(s1, L2E, -my_lse)) : 0.f;
+                        d0 = p0 * (g0 - my_del);
+                        d1 = p1 * (g1 - my_del);
                     } else {
-                        tmem_st16(tl + C_S + 16 * c, pkp);        // P^T
-                        tmem_st16(tl + C_DP + 16 * c, pks);       // dS^T
+                        const float2 l2 = *reinterpret_cast<const float2*>(v_lse + i);      // lse = +inf for queries past the end -> p = 0
+                        const float2 e2 = *reinterpret_cast<const float2*>(v_del + i);
+                        p0 = row_ok ? fast_exp2(fmaf(s0, L2E, -l2.x)) : 0.f;
+                        p1 = row_ok ? fast_exp2(fmaf(s1, L2E, -l2.y)) : 0.f;
+                        d0 = p0 * (g0 - e2.x);
+                        d1 = p1 * (g1 - e2.y);
                     }
+                    pks[i / 2] = pack_bf16x2(d0, d1);
+                    if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
+                }
+                // the packed values overwrite the first 16 of the 32 columns this thread has just read (both loads completed)
+                if (MODE == MODE_DQ) {
+                    tmem_st16(tS, pks);          // dS
+                } else {
+                    tmem_st16(tS, pkp);          // P^T
+                    tmem_st16(tD, pks);          // dS^T
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -392,27 +409,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             }
             mbar_wait(acc_full, 0);
             tc_fence_after();
-            uint32_t a0[32], a1[32];
-            tmem_ld32(tl + C_ACC0, a0);
-            tmem_ld32(tl + C_ACC0 + 32, a1);
+            uint32_t a0[32];
+            tmem_ld32(tl + C_ACC0 + 32 * half, a0);
             tmem_ld_wait();
             const long long tok = static_cast<long long>(b) * S + row;
-            __nv_bfloat16* drow = dqkv + tok * 3 * E + h * AHD;
+            __nv_bfloat16* drow = dqkv + tok * 3 * E + h * AHD + 32 * half;
             if (MODE == MODE_DQ) {
-                if (row_ok) store_row_bf16_64(drow, a0, a1, 1.0f);
+                if (row_ok) store_row_bf16_32(drow, a0);
             } else {
-                if (row_ok) store_row_bf16_64(drow + 2 * E, a0, a1, 1.0f);     // dV
-                tmem_ld32(tl + C_ACC1, a0);
-                tmem_ld32(tl + C_ACC1 + 32, a1);
+                if (row_ok) store_row_bf16_32(drow + 2 * E, a0);     // dV
+                tmem_ld32(tl + C_ACC1 + 32 * half, a0);
                 tmem_ld_wait();
-                if (row_ok) store_row_bf16_64(drow + E, a0, a1, 1.0f);         // dK
+                if (row_ok) store_row_bf16_32(drow + E, a0);         // dK
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tb, TMEM_COLS);
     }
@@ -890,7 +905,7 @@ static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, const CUtens
         attr_set = true;
     }
     dim3 grid((S + AT - 1) / AT - ot0, H, B);
-    TVS_CUDA(launch_pdl(kern, grid, dim3(ATC_THREADS), L::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv, ot0));
+    TVS_CUDA(launch_pdl(kern, grid, dim3(MODE == MODE_FWD ? ATC_THREADS : ATC_THREADS_BWD), L::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv, ot0));
     return check_launch(MODE == MODE_FWD ? "attn_tc_kernel<fwd>" : (MODE == MODE_DQ ? "attn_tc_kernel<dq>" : "attn_tc_kernel<dkv>"));
 }
 
