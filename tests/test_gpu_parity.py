@@ -117,3 +117,37 @@ def test_eval_counters_large_batch():
     _, c2 = engine.DiceBceFn.apply(perfect, mask, 0.5, 1.0, 0.2, conf2)
     assert int(c2[:, 1].sum()) == 0 and int(c2[:, 2].sum()) == 0 and int(conf2[1] + conf2[2]) == 0
     assert torch.isfinite(loss)
+
+
+@pytest.mark.parametrize("case", ["maple", "vpt"])
+def test_bottom_block_pruning_matches_full_backward(case, monkeypatch):
+    """Below the first block only the prompt rows carry a gradient (the patch / class embeddings are frozen), so the
+    engine runs that block's attention backward, QKV dgrad and LayerNorm backward on those rows only
+    (tvs_attn_bwd_tail).  Row-wise arithmetic is unchanged up to the tile shape of the small QKV dgrad GEMM (its fp32
+    accumulation order may differ in the last bit before the bf16 rounding), so every learner gradient must agree with the
+    full-row backward to ~1e-3 of its largest entry - a dropped row or tile would show up as an O(1) difference."""
+    from tunevlseg_b200 import engine
+    from tunevlseg_b200.losses import DiceCELoss
+
+    if case not in LEARNER_CASES:
+        pytest.skip(f"{case} not among the learner cases")
+    spec, B, L = FULL, 2, 8
+    weights = OC.init_weights(spec, seed=7)
+    img, ids, am, mask = make_batch(spec, B, L, 11)
+    grads = []
+    for prune in (True, False):
+        monkeypatch.setattr(engine, "TAIL_PRUNE", prune)
+        net = build_net(case, spec, weights, seed=3).cuda()
+        logits = net(text_input={"input_ids": ids.cuda(), "attention_mask": am.cuda()}, image_input=img.cuda())
+        loss = DiceCELoss(sigmoid=True, lambda_dice=1, lambda_ce=0.2)(logits, mask.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        grads.append({k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 0
+    worst = 0.0
+    for k in grads[0]:
+        scale = grads[1][k].abs().max().item()
+        diff = (grads[0][k] - grads[1][k]).abs().max().item()
+        worst = max(worst, diff / max(scale, 1e-30))
+        assert diff <= 2e-3 * scale + 1e-12, f"{case}: {k} differs between pruned and full bottom-block backward ({diff:.3e} of {scale:.3e})"
+    print(f"PARITY pruning {case}: worst relative difference {worst:.2e}")
