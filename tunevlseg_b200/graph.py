@@ -6,6 +6,8 @@ The reference drives ~25 ATen launches per layer from Python with no graph (SURV
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 
@@ -32,7 +34,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # TVS_MAIN_PRIORITY=1 (experiment switch): capture the main chain on a high-priority stream, so that its thread
+        # blocks are placed before those of the text-tower stream whenever both have blocks pending
+        prio = os.environ.get("TVS_MAIN_PRIORITY", "0") == "1"
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=-1) if prio else None):
             self.loss = self._eager_step()
 
     def _eager_step(self) -> torch.Tensor:
