@@ -488,10 +488,12 @@ __global__ void __launch_bounds__(XA_MAXK * 4) cross_attn_bwd_dkv_kernel(const f
                 gv[d] = g.x; gv[d + 1] = g.y; gv[d + 2] = g.z; gv[d + 3] = g.w;
             }
             float s = 0.f, dp = 0.f;
+            if (live) {
 #pragma unroll
-            for (int d = 0; d < 16; ++d) {
-                s = fmaf(qv[d], kr[d], s);
-                dp = fmaf(gv[d], vr[d], dp);
+                for (int d = 0; d < 16; ++d) {
+                    s = fmaf(qv[d], kr[d], s);
+                    dp = fmaf(gv[d], vr[d], dp);
+                }
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -499,10 +501,12 @@ __global__ void __launch_bounds__(XA_MAXK * 4) cross_attn_bwd_dkv_kernel(const f
             dp += __shfl_xor_sync(0xffffffffu, dp, 2);
             const float p = (attend && (!causal || j <= i0 + ii)) ? __expf(s - sl[ii]) : 0.f;
             const float ds = p * (dp - sd[ii]);
+            if (live) {
 #pragma unroll
-            for (int d = 0; d < 16; ++d) {
-                ak[d] = fmaf(ds, qv[d], ak[d]);
-                av[d] = fmaf(p, gv[d], av[d]);
+                for (int d = 0; d < 16; ++d) {
+                    ak[d] = fmaf(ds, qv[d], ak[d]);
+                    av[d] = fmaf(p, gv[d], av[d]);
+                }
             }
         }
     }
@@ -879,7 +883,7 @@ TVS_API int tvs_cross_attn_bwd(const float* q, int64_t ld_q, const float* k, con
     cross_attn_bwd_dq_kernel<<<dim3((Sq + XA_QPB - 1) / XA_QPB, H, B), XA_THREADS, 0, st>>>(q, ld_q, k, v, ld_kv, key_mask, out, dout, ld_o,
                                                                                                      lse, Sq, Sk, causal, dq, ld_dq, delta);
     if (check_launch("cross_attn_bwd_dq_kernel")) return -3;
-    const int dkv_threads = std::max(128, (Sk * 4 + 31) / 32 * 32);       // 4 lanes per key; idle warps only burn issue slots
+    const int dkv_threads = (Sk * 4 + 31) / 32 * 32;       // 4 lanes per key; the kernel is issue bound, so no warp without a key is launched
     const int nsplit = std::min(8, std::max(1, Sq / 64));       // cluster of query splits; 1 for the text encoder's own attention (Sq <= 77)
     TVS_CUDA(launch_pdl(cross_attn_bwd_dkv_kernel, dim3(nsplit, H, B), dim3(dkv_threads), 0, st, nsplit, q, ld_q, k, v, ld_kv, key_mask, dout, ld_o, lse,
                         delta, Sq, Sk, causal, dk, dv, ld_dkv));
