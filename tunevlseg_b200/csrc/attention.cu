@@ -9,6 +9,8 @@
 // the saved log-sum-exp.  [A tcgen05/TMEM version of these kernels is the planned replacement.]
 //
 // layout: qkv bf16 [B*S, 3*E], E = H*HD, columns Q | K | V, head h at columns h*HD .. h*HD+HD-1 of each part.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tvs_b200.h"
 
@@ -575,7 +577,8 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
 // tcgen05 / TMEM kernels for head dim 64 without masks (attention_sm100.cu)
 bool attn_tc_enabled();
 int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st);
-int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st, int row_begin);
+int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const float* lse, float* delta, int B, int S, int H, void* dqkv, cudaStream_t st,
+                int row_begin);
 
 }  // namespace tvs
 
@@ -600,11 +603,14 @@ extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd_tail(const vo
     TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_bwd_tail: bad shape B=%d S=%d H=%d", B, S, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (hd == 64 && !causal && !key_mask && attn_tc_enabled()) {
+        static const bool fused_delta = [] { const char* e = getenv("TVS_ATTN_DELTA"); return !(e && e[0] == 'k'); }();   // TVS_ATTN_DELTA=kernel: separate pass
+        if (row_begin < 128 && fused_delta) return attn_tc_bwd(qkv, out, dout, lse, delta, B, S, H, dqkv, st, row_begin);   // delta comes out of the dQ kernel
+        // tail-only backward: dK / dV of the last tile still need delta of EVERY query row
         const long long rows = static_cast<long long>(B) * S;
         attn_delta_kernel<64><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
                                                                                       static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta);
         if (int rc = check_launch("attn_delta_kernel")) return rc;
-        return attn_tc_bwd(qkv, dout, lse, delta, B, S, H, dqkv, st, row_begin);
+        return attn_tc_bwd(qkv, nullptr, dout, lse, delta, B, S, H, dqkv, st, row_begin);
     }
     if (hd == 64) return attn_bwd_launch<64>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);
     if (hd == 16) return attn_bwd_launch<16>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);

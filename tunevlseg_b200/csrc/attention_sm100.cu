@@ -362,7 +362,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         } else {
             // backward: rows are queries (DQ) or keys (DKV); this thread owns columns [32 half, 32 half + 32) of S and dP
             const float my_lse = (MODE == MODE_DQ && row_ok) ? lse_in[bh * S + row] * L2E : INFINITY;
-            const float my_del = (MODE == MODE_DQ && row_ok) ? delta_in[bh * S + row] : 0.f;
+            float my_del = 0.f;
+            if (MODE == MODE_DQ) {
+                if (out != nullptr) {
+                    // delta = rowsum(dO o O) computed here (the separate delta kernel and its launch gap disappear): this
+                    // thread's half of the dO row comes from the swizzled outer tile the MMAs use, its half of the O row
+                    // from global memory; the two halves meet through shared memory (s_vec is unused in this mode)
+                    mbar_wait(outer_full, 0);
+                    float part = 0.f;
+                    const long long tok = static_cast<long long>(b) * S + (row_ok ? row : 0);
+                    const uint4* orow = reinterpret_cast<const uint4*>(out + tok * E + h * AHD + 32 * half);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int chunk = 4 * half + c;       // 16-byte chunk of the 128-byte row; stored at chunk ^ (row & 7)
+                        const uint4 g = *reinterpret_cast<const uint4*>(s_outer1 + tid * 128 + ((chunk ^ (tid & 7)) << 4));
+                        const uint4 o = row_ok ? orow[c] : make_uint4(0u, 0u, 0u, 0u);
+                        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 a = unpack_bf16x2(gw[i]), bb = unpack_bf16x2(ow[i]);
+                            part = fmaf(a.x, bb.x, part);
+                            part = fmaf(a.y, bb.y, part);
+                        }
+                    }
+                    s_vec[half * AT + tid] = part;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    my_del = s_vec[tid] + s_vec[AT + tid];
+                    if (half == 0 && row_ok) out32[bh * S + row] = my_del;      // the dK / dV kernel that follows reads it
+                } else if (row_ok) {
+                    my_del = delta_in[bh * S + row];
+                }
+            }
             const uint32_t tS = tl + C_S + 32 * half, tD = tl + C_DP + 32 * half;
             for (int it = 0; it < n_it; ++it) {
                 mbar_wait(s_full, it & 1);
@@ -938,13 +968,22 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
 
 // delta must already hold rowsum(dO o O)
 // row_begin > 0: dqkv is produced only for the 128-row tiles that contain rows >= row_begin (queries for dQ, keys for dK / dV)
-int attn_tc_bwd(const void* qkv, const void* dout, const float* lse, const float* delta, int B, int S, int H, void* dqkv, cudaStream_t st, int row_begin) {
+// out_o != nullptr (whole-sequence backward only): delta is computed by the dQ kernel from O and dO and written for the dK / dV kernel
+int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const float* lse, float* delta, int B, int S, int H, void* dqkv, cudaStream_t st,
+                int row_begin) {
     const int ot0 = row_begin / AT;
     CUtensorMap mq, md, mqi, mdi;      // 128-row boxes for the outer tiles, 64-row boxes for the inner ones
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&md, dout, H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, 64)) return rc;
     if (int rc = make_tmap3(&mdi, dout, H * AHD, S, B, 64)) return rc;
+    if (out_o != nullptr && ot0 == 0) {
+        // dQ first: it produces delta on the way; dK / dV (disjoint columns of dqkv) follow in the stream
+        if (int rc = launch_atc<MODE_DQ>(mq, md, mqi, mdi, B, S, H, static_cast<__nv_bfloat16*>(const_cast<void*>(out_o)), delta, nullptr, lse, delta,
+                                         static_cast<__nv_bfloat16*>(dqkv), st, 0))
+            return rc;
+        return launch_atc<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st, 0);
+    }
     if (int rc = launch_atc<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st, ot0)) return rc;
     return launch_atc<MODE_DQ>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st, ot0);
 }

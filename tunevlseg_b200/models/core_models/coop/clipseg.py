@@ -105,7 +105,9 @@ class BaseCLIPSeg(HFCLIPSegWrapper, ABC):
             return torch.cuda.current_stream()
         st = getattr(self, "_tvs_text_stream", None)
         if st is None or st.device != torch.cuda.current_stream().device:
-            st = torch.cuda.Stream()
+            # TVS_TEXT_PRIORITY=1 (experiment switch) gives the text tower's blocks precedence whenever both streams have
+            # blocks pending; measured 10.24 vs 10.04 ms per step: the vision chain is the critical one, default priority stays
+            st = torch.cuda.Stream(priority=-1 if os.environ.get("TVS_TEXT_PRIORITY", "0") == "1" else 0)
             object.__setattr__(self, "_tvs_text_stream", st)
         return st
 
