@@ -299,3 +299,44 @@ def test_predict_tail_tables_and_metric_formulas():
     assert abs(m["dice"] - 100 * 60 / 90) < 1e-9 and abs(m["iou"] - 50.0) < 1e-9
     assert abs(m["ones_dice_diff"] - (100 * 60 / 90 - 100 * 100 / 250)) < 1e-9
     assert metrics_from_counts(0, 0, 0, 0, 100)["dice"] == 100.0 and metrics_from_counts(0, 5, 0, 0, 100)["iou"] == 0.0
+
+
+def test_stacked_parameter_gradients_go_straight_into_preallocated_buffers():
+    """``_StackParams`` (the per-depth projector parameters stacked for the batched projection) must leave exactly the
+    gradients ordinary autograd leaves: into preallocated ``.grad`` views of a flat buffer (FusedAdamW's layout) with
+    accumulation semantics, through ordinary AccumulateGrad when there is no buffer, and through ordinary autograd when
+    a unified projector lists the same parameter once per depth."""
+    import copy
+
+    from torch import nn
+
+    from tunevlseg_b200.models.core_models.coop.context_learner.learners import _batched_projection
+
+    torch.manual_seed(0)
+
+    def mk():
+        return nn.Sequential(nn.Linear(8, 4), nn.ReLU(), nn.Linear(4, 6, bias=False), nn.LayerNorm(6))
+
+    x = torch.randn(3, 5, 8)
+    plain = nn.ModuleList(mk() for _ in range(3))
+    direct = copy.deepcopy(plain)
+    (_batched_projection(plain, x) ** 2).sum().backward()           # no .grad yet: falls back to AccumulateGrad
+    flat = torch.zeros(sum(p.numel() for p in direct.parameters()))
+    o = 0
+    for p in direct.parameters():
+        p.grad = flat[o:o + p.numel()].view_as(p)
+        o += p.numel()
+    for rep in (1, 2):
+        (_batched_projection(direct, x) ** 2).sum().backward()
+        for a, b in zip(direct.parameters(), plain.parameters()):
+            assert a.grad.data_ptr() >= flat.data_ptr() and torch.allclose(a.grad, rep * b.grad, rtol=1e-6, atol=1e-7)
+    assert flat.abs().sum() > 0
+
+    shared = mk()
+    shared_ref = copy.deepcopy(shared)
+    for p in shared.parameters():
+        p.grad = torch.zeros_like(p)
+    (_batched_projection(nn.ModuleList((shared,) * 3), x) ** 2).sum().backward()
+    (torch.stack([shared_ref(x[i]) for i in range(3)]) ** 2).sum().backward()
+    for a, b in zip(shared.parameters(), shared_ref.parameters()):
+        assert torch.allclose(a.grad, b.grad, rtol=2e-2, atol=1e-5)

@@ -18,6 +18,8 @@ import itertools
 from abc import ABC, abstractmethod
 from collections.abc import Iterable
 
+import os
+
 import torch
 from torch import nn
 
@@ -162,6 +164,35 @@ class BaseProjectorLearner(CoOpContextLearner):
         return layers
 
 
+_STACK_DIRECT = os.environ.get("TVS_STACK_DIRECT", "1") != "0"      # A/B switch
+
+
+class _StackParams(torch.autograd.Function):
+    """``torch.stack`` of per-depth parameters whose backward adds the stacked gradient straight into the parameters'
+    preallocated ``.grad`` buffers with ONE multi-tensor launch.
+
+    With ``FusedAdamW`` every ``.grad`` is a view of the flat gradient buffer, so autograd's AccumulateGrad turns the
+    backward of a plain ``torch.stack`` into one tiny ``add_`` launch per depth and parameter (~45 launches for MaPLe,
+    all of them at the very end of the step's critical path, in front of the all-reduce).  Falls back to ordinary
+    autograd behaviour when a gradient buffer is missing or a parameter is listed twice (unified projectors)."""
+
+    @staticmethod
+    def forward(ctx, *params):
+        ctx.params = params
+        return torch.stack([p.detach() for p in params])
+
+    @staticmethod
+    def backward(ctx, g):
+        params = ctx.params
+        slices = g.unbind(0)
+        direct = (_STACK_DIRECT and len({id(p) for p in params}) == len(params)
+                  and all(p.grad is not None and p.grad.dtype == g.dtype and p.grad.device == g.device for p in params))
+        if direct:
+            torch._foreach_add_([p.grad for p in params], list(slices))
+            return (None,) * len(params)
+        return tuple(slices)
+
+
 def _batched_projection(layers, x: torch.Tensor):
     """Apply `len(layers)` structurally identical projectors to x[i] in a handful of batched launches.
 
@@ -185,7 +216,7 @@ def _batched_projection(layers, x: torch.Tensor):
         ts = [getattr(m, attr) for m in ms]
         if any(t is None for t in ts):
             return None
-        return torch.stack(ts)
+        return _StackParams.apply(*ts) if all(t.requires_grad for t in ts) else torch.stack(ts)
 
     def lin(ms, inp):
         w, b = stk(ms, "weight"), stk(ms, "bias")
