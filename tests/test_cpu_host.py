@@ -340,3 +340,35 @@ def test_stacked_parameter_gradients_go_straight_into_preallocated_buffers():
     (torch.stack([shared_ref(x[i]) for i in range(3)]) ** 2).sum().backward()
     for a, b in zip(shared.parameters(), shared_ref.parameters()):
         assert torch.allclose(a.grad, b.grad, rtol=2e-2, atol=1e-5)
+
+
+def test_lightning_checkpoint_shaped_state_dict_round_trip():
+    """a reference Lightning checkpoint stores ``state_dict`` keys ``net.model.clip.*``,
+    ``net.model.decoder.*``, ``net.context_learner.*``, ``net.additive_decoder_layer.*`` and ``net.residual_ratio``
+    (callbacks/default.yaml:9-15 saves the LightningModule, whose only sub-module is ``net``).  The product module must
+    produce exactly that key space and load it strictly, so that reference runs drop onto the kernels."""
+    from oracle import clipseg as OC
+    from tests.golden_cases import TINY
+    from tests.helpers import build_net
+    from tunevlseg_b200.losses import DiceCELoss
+    from tunevlseg_b200.models.image_text_mask_module import ImageTextMaskModule
+
+    def module(seed):
+        net = build_net("maple", TINY, OC.init_weights(TINY, seed=7), seed=seed)
+        return ImageTextMaskModule(net=net, loss_fn=DiceCELoss(sigmoid=True, lambda_dice=1, lambda_ce=0.2),
+                                   optimizer=partial(torch.optim.AdamW, lr=2e-4), scheduler=None, compile=False, task="binary",
+                                   threshold=0.5, weight_decay=0.01)
+
+    src, dst = module(1), module(2)
+    sd = src.state_dict()
+    prefixes = ("net.model.clip.", "net.model.decoder.", "net.context_learner.", "net.additive_decoder_layer.", "net.residual_ratio")
+    assert all(k.startswith(prefixes) for k in sd), [k for k in sd if not k.startswith(prefixes)][:5]
+    for p in prefixes:
+        assert any(k.startswith(p) for k in sd), p
+    assert "net.context_learner.context_vectors" in sd and "net.additive_decoder_layer.1.weight" in sd
+    assert not torch.equal(dst.state_dict()["net.context_learner.context_vectors"], sd["net.context_learner.context_vectors"])
+    ckpt = {"state_dict": {k: v.clone() for k, v in sd.items()}}            # what torch.load(<lightning .ckpt>) returns
+    res = dst.load_state_dict(ckpt["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, sd[k]), k
