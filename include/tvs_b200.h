@@ -309,6 +309,23 @@ int tvs_ffn64_fwd(const float* x, const void* w1_hi, const void* w1_lo, const vo
 int tvs_ffn64_bwd(const float* x, const float* g, const void* w1_hi, const void* w1_lo, const void* w2t_hi,
                   const void* w2t_lo, const float* b1, int64_t M, int32_t D, int32_t F, float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Eval input transforms on the device (configs/experiment/coop/clipseg.yaml:113-127 `_eval_transforms`, applied by
+ * src/data/core_datasets/image_text_mask_dataset.py:52-84): cv2.resize(INTER_CUBIC) of the uint8 HWC image in OpenCV's
+ * 8-bit fixed-point arithmetic (four int taps scaled by 2048 per output column / row, replicated borders,
+ * (v + 2^21) >> 22, saturation) + albumentations.Normalize + ToTensorV2 in one kernel; cv2.INTER_NEAREST for the mask.
+ * img: device uint8 [Hi, Wi, 3] rows of ld_bytes; xofs / yofs int32 [Wo] / [Ho] first-tap source index + 1 (tap k reads
+ * clamp(ofs + k - 1)); xcoef / ycoef int32 [Wo, 4] / [Ho, 4]; mean255 / inv_std255: HOST pointers to 3 floats
+ * (255 mean, 1 / (255 std)).  out_chw f32 [3, Ho, Wo] and / or out_u8_hwc uint8 [Ho, Wo, 3] (the resized image itself).
+ * tvs_resize_nearest_f32: in f32 [Hi, Wi] rows of ld floats; xofs / yofs int32 source indices; out f32 [Ho, Wo].
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_preproc_image_u8(const uint8_t* img, int32_t Hi, int32_t Wi, int64_t ld_bytes, const int32_t* xofs,
+                         const int32_t* xcoef, const int32_t* yofs, const int32_t* ycoef, const float* mean255,
+                         const float* inv_std255, int32_t Ho, int32_t Wo, float* out_chw, uint8_t* out_u8_hwc,
+                         void* stream);
+int tvs_resize_nearest_f32(const float* in, int32_t Hi, int32_t Wi, int64_t ld, const int32_t* xofs,
+                           const int32_t* yofs, int32_t Ho, int32_t Wo, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,8 @@ def load():
         "tvs_dynconv_bwd": [P, P, P, I64, I32, I32, I32, I32, P, P, I32, P],
         "tvs_ffn64_fwd": [P, P, P, P, P, P, P, I64, I32, I32, P, P],
         "tvs_ffn64_bwd": [P, P, P, P, P, P, P, I64, I32, I32, P, P],
+        "tvs_preproc_image_u8": [P, I32, I32, I64, P, P, P, P, P, P, I32, I32, P, P, P],
+        "tvs_resize_nearest_f32": [P, I32, I32, I64, P, P, I32, I32, P, P],
         "tvs_resample2d_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, I32, P, P],
         "tvs_resample2d_u8": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, P, P],
         "tvs_resample2d_bwd": [P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, I32, I32, P, P],
@@ -660,3 +662,45 @@ def resample2d_bwd(dout, B, Hi, Wi, Ho, Wo, tab, tile, din):
 for _n in ("round_tf32", "pad_nhwc", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd", "cross_attn_fwd",
            "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd", "resample2d_u8"):
     globals()[_n] = _wrap(globals()[_n], _n)
+
+
+# ---- eval input transforms (preprocess.cu) ---------------------------------------------------------------------------------
+def preproc_image_u8(img_u8, xofs, xcoef, yofs, ycoef, mean255, inv_std255, out_chw=None, out_u8=None):
+    """img_u8: CUDA uint8 [Hi, Wi, 3] (row stride allowed); tables: CUDA int32; mean255 / inv_std255: sequences of 3 floats.
+    out_chw: CUDA f32 [3, Ho, Wo]; out_u8: CUDA uint8 [Ho, Wo, 3] (the resized image before Normalize)."""
+    require_device()
+    if not (img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.shape[2] == 3 and img_u8.stride(2) == 1
+            and img_u8.stride(1) == 3):
+        raise TvsError(f"preproc_image_u8: image must be a CUDA uint8 HWC tensor with packed pixels, got {tuple(img_u8.shape)} {img_u8.dtype}")
+    for t in (xofs, xcoef, yofs, ycoef):
+        _chk(t, torch.int32, "tap table")
+    Ho, Wo = yofs.numel(), xofs.numel()
+    if xcoef.numel() != 4 * Wo or ycoef.numel() != 4 * Ho:
+        raise TvsError("preproc_image_u8: coefficient tables must be [n_out, 4]")
+    if out_chw is not None:
+        _chk(out_chw, torch.float32, "out_chw")
+        if tuple(out_chw.shape) != (3, Ho, Wo):
+            raise TvsError(f"preproc_image_u8: out_chw must be {(3, Ho, Wo)}, got {tuple(out_chw.shape)}")
+    if out_u8 is not None:
+        _chk(out_u8, torch.uint8, "out_u8")
+        if tuple(out_u8.shape) != (Ho, Wo, 3):
+            raise TvsError(f"preproc_image_u8: out_u8 must be {(Ho, Wo, 3)}, got {tuple(out_u8.shape)}")
+    m = (c_float * 3)(*[float(v) for v in mean255])
+    d = (c_float * 3)(*[float(v) for v in inv_std255])
+    Hi, Wi, _ = img_u8.shape
+    _ck(load().tvs_preproc_image_u8(img_u8.data_ptr(), Hi, Wi, img_u8.stride(0), xofs.data_ptr(), xcoef.data_ptr(), yofs.data_ptr(),
+                                    ycoef.data_ptr(), ctypes.cast(m, c_void_p), ctypes.cast(d, c_void_p), Ho, Wo, _p(out_chw), _p(out_u8),
+                                    _stream()), "tvs_preproc_image_u8")
+
+
+def resize_nearest_f32(x, xofs, yofs, out):
+    """x: CUDA f32 [Hi, Wi] (row stride allowed) -> out CUDA f32 [Ho, Wo] = x[yofs][:, xofs]."""
+    require_device()
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1):
+        raise TvsError("resize_nearest_f32: x must be a CUDA f32 [H, W] tensor with unit inner stride")
+    _chk(xofs, torch.int32, "xofs"); _chk(yofs, torch.int32, "yofs"); _chk(out, torch.float32, "out")
+    Ho, Wo = yofs.numel(), xofs.numel()
+    if tuple(out.shape) != (Ho, Wo):
+        raise TvsError(f"resize_nearest_f32: out must be {(Ho, Wo)}")
+    _ck(load().tvs_resize_nearest_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), xofs.data_ptr(), yofs.data_ptr(), Ho, Wo,
+                                      out.data_ptr(), _stream()), "tvs_resize_nearest_f32")

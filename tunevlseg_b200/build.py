@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(OUT_DIR, "libtvs_b200.so")
-SOURCES = ["api.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "layernorm.cu", "loss_metrics.cu", "elementwise.cu", "conv_ops.cu", "ffn_sm100.cu"]
+SOURCES = ["api.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "layernorm.cu", "loss_metrics.cu", "elementwise.cu", "conv_ops.cu", "ffn_sm100.cu", "preprocess.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
