@@ -459,7 +459,8 @@ head_bwd_addmap_kernel(const float* __restrict__ dlogits, const float* __restric
     float* s_T = s_hb;                                          // [NRmax][G][ks]
     const int NRmax = 2 * P + ks + 2;
     float* s_w = s_T + NRmax * G * ks;                          // [G][TW]
-    float* s_dl = s_w + G * TW;                                 // [HB_CHUNK][W]
+    float* s_dl = s_w + G * TW;                                 // [HB_CHUNK][WP]
+    const int WP = W + G;                                       // padded row: one extra word per patch
     float wb = 1.f;
     if (blend == 1) wb = *ratio;
     for (int i = threadIdx.x; i < G * TW; i += blockDim.x) {
@@ -474,7 +475,12 @@ head_bwd_addmap_kernel(const float* __restrict__ dlogits, const float* __restric
     for (int r0 = 0; r0 < NR; r0 += HB_CHUNK) {
         const int nr = min(HB_CHUNK, NR - r0);
         __syncthreads();                                         // table ready / previous chunk consumed
-        for (int i = threadIdx.x; i < nr * W; i += blockDim.x) s_dl[i] = dl[static_cast<long long>(Ylo + r0) * W + i];
+        // one padding word per P columns: the tasks of a warp read row[xi * P + j] for consecutive xi, a stride of P = 16
+        // words (16-way bank conflicts); with stride P + 1 they fall into distinct banks
+        for (int i = threadIdx.x; i < nr * W; i += blockDim.x) {
+            const int yr = i / W, X = i - yr * W;
+            s_dl[yr * WP + X + X / P] = dl[static_cast<long long>(Ylo + r0) * W + i];
+        }
         __syncthreads();
         for (int task = threadIdx.x; task < nr * G; task += blockDim.x) {
             const int yr = task / G, xi = task - yr * G;
@@ -483,10 +489,13 @@ head_bwd_addmap_kernel(const float* __restrict__ dlogits, const float* __restric
             float acc[HEAD_MAXK];
 #pragma unroll
             for (int kx = 0; kx < HEAD_MAXK; ++kx) acc[kx] = 0.f;
-            const float* row = s_dl + yr * W;
+            const float* row = s_dl + yr * WP;
             const float* wt = s_w + xi * TW;
+            int Xp = Xlo + Xlo / P, rem = Xlo % P;             // padded index of X, kept without a division per step
             for (int X = Xlo; X <= Xhi; ++X) {
-                const float g = row[X];
+                const float g = row[Xp];
+                ++Xp;
+                if (++rem == P) { rem = 0; ++Xp; }
 #pragma unroll
                 for (int kx = 0; kx < HEAD_MAXK; ++kx)
                     if (kx < ks) {
@@ -639,7 +648,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_head_bwd(const float* 
     if (blend != 0 && daddmap) {
         TVS_REQUIRE(ksize >= 1 && ksize <= HEAD_MAXK && (ksize & 1), "tvs_head_bwd: odd ksize <= %d", HEAD_MAXK);
         const int nr = 2 * P + ksize + 2;
-        const size_t sh = (static_cast<size_t>(nr) * G * ksize + static_cast<size_t>(G) * (2 * P + 2) + static_cast<size_t>(HB_CHUNK) * G * P) * sizeof(float);
+        const size_t sh = (static_cast<size_t>(nr) * G * ksize + static_cast<size_t>(G) * (2 * P + 2) + static_cast<size_t>(HB_CHUNK) * (G * P + G)) * sizeof(float);
         TVS_REQUIRE(sh <= 48 * 1024, "tvs_head_bwd: shared-memory tile too large");
         head_bwd_addmap_kernel<<<dim3(G, B), 256, sh, st>>>(dlogits, ratio, blend, G, P, ksize, daddmap, ld_daddmap);
         return check_launch("head_bwd_addmap_kernel");
