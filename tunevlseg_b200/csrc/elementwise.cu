@@ -482,8 +482,7 @@ head_bwd_addmap_kernel(const float* __restrict__ dlogits, const float* __restric
             s_dl[yr * WP + X + X / P] = dl[static_cast<long long>(Ylo + r0) * W + i];
         }
         __syncthreads();
-        for (int task = threadIdx.x; task < nr * G; task += blockDim.x) {
-            const int yr = task / G, xi = task - yr * G;
+        auto do_task = [&](int yr, int xi) {
             const int base = xi * P - P / 2 - 1;
             const int Xlo = max(base - half, 0), Xhi = min(base + TW - 1 + half, W - 1);
             float acc[HEAD_MAXK];
@@ -509,7 +508,7 @@ head_bwd_addmap_kernel(const float* __restrict__ dlogits, const float* __restric
                 }
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) s_T[((r0 + yr) * G + xi) * ks + kx] = acc[kx];
-                continue;
+                return;
             }
             int Xp = Xlo + Xlo / P, rem = Xlo % P;             // padded index of X, kept without a division per step
             for (int X = Xlo; X <= Xhi; ++X) {
@@ -526,7 +525,15 @@ head_bwd_addmap_kernel(const float* __restrict__ dlogits, const float* __restric
 #pragma unroll
             for (int kx = 0; kx < HEAD_MAXK; ++kx)
                 if (kx < ks) s_T[((r0 + yr) * G + xi) * ks + kx] = acc[kx];
-        }
+        };
+        // interior patch columns first, the two border columns (whose clamps need the general loop) last: a warp that holds
+        // both kinds of task pays for both paths, so the border tasks are packed into the last warp
+        const int n_mid = G > 2 ? G - 2 : 0;
+        for (int task = threadIdx.x; task < nr * n_mid; task += blockDim.x) do_task(task / n_mid, 1 + task % n_mid);
+        const int n_edge = G > 1 ? 2 : 1;
+        // ... of the block, which has no interior task (nr * n_mid <= 8 * 20 < 224), so both kinds run side by side
+        for (int task = static_cast<int>(threadIdx.x) - (static_cast<int>(blockDim.x) - 32); task >= 0 && task < nr * n_edge; task += 32)
+            do_task(task / n_edge, (task % n_edge) ? G - 1 : 0);
     }
     __syncthreads();
     const int ybase = yi * P - P / 2 - 1;
