@@ -126,12 +126,15 @@ def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse, out_f32=None):
         out_f32.copy_(_tf32_rn(o))
 
 
-def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv):
+def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv, row_begin=0):
     q = qkv.float().requires_grad_(True)
     with torch.enable_grad():
         o, _ = _attn_ref(q, B, S, H, hd, causal, key_mask)
     (g,) = torch.autograd.grad(o, q, dout.float())
     dqkv.copy_(g)
+    if row_begin:       # tvs_attn_bwd_tail: rows below the 128-row tile of row_begin are NOT produced - poison them
+        first = (row_begin // 128) * 128
+        dqkv.view(B, S, -1)[:, :first] = float("nan")
 
 
 def prompt_overwrite(x, row0, n, ctx, x_bf16=None):
@@ -328,11 +331,73 @@ def head_bwd(dlogits, tconv, add_out, bias_t, ratio, blend, B, G, P, ksize, dtco
         dratio += outs[3]
 
 
+# ---- CLIPSeg-only entries -------------------------------------------------------------------------------------------------
+def im2col_patches(image, P, out_bf16):
+    B, C, H, W = image.shape
+    g = H // P
+    cols = image.view(B, C, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, C * P * P)      # column order (c, py, px)
+    out_bf16.copy_(cols)
+
+
+def vision_assemble(patches, cls, pos, ctx, B, G2, n, D, h):
+    hv = h.view(B, 1 + G2 + n, D)
+    hv[:, 0] = cls.view(-1) + pos[0]
+    hv[:, 1:1 + G2] = patches.view(B, G2, D) + pos[1:1 + G2]
+    if n:
+        hv[:, 1 + G2:] = ctx                      # (n, D) shared or (B, n, D) per sample; no position embedding on prompts
+
+
+def slice_rows(x, row0, nrows, y_f32=None, y_bf16=None):
+    if y_f32 is not None:
+        y_f32.copy_(x[:, row0:row0 + nrows])
+    if y_bf16 is not None:
+        y_bf16.copy_(x[:, row0:row0 + nrows])
+
+
+def unslice_rows(dy, S, row0, dx):
+    dx.zero_()
+    dx.view(dy.shape[0], S, -1)[:, row0:row0 + dy.shape[1]] = dy
+
+
+def add_f32(y, x):
+    y += x
+
+
+def film_fwd(x, mul, add, y=None, y_bf16=None):
+    o = mul.unsqueeze(1) * x + add.unsqueeze(1)
+    if y is not None:
+        y.copy_(o)
+    if y_bf16 is not None:
+        y_bf16.copy_(o)
+
+
+def film_bwd(dy, x, mul, dx, dmul, dadd):
+    dx.copy_(mul.unsqueeze(1) * dy)
+    dmul.copy_((dy * x).sum(1))
+    dadd.copy_(dy.sum(1))
+
+
+def _ffn_w(pair):
+    hi, lo = pair
+    return hi.float() if lo is None else hi.float() + lo.float()
+
+
+def ffn64_fwd(x, w1, w2t, b1, b2, out):
+    assert x.shape[1] == 64 and w1[0].shape == w2t[0].shape and w1[0].dtype == BF16
+    out.copy_(x + torch.relu(x @ _ffn_w(w1).t() + b1) @ _ffn_w(w2t) + b2)
+
+
+def ffn64_bwd(x, g, w1, w2t, b1, dx):
+    mask = (x @ _ffn_w(w1).t() + b1) > 0
+    dx.copy_(g + ((g @ _ffn_w(w2t).t()) * mask) @ _ffn_w(w1))
+
+
 def install(monkeypatch):
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "prompt_overwrite", "prompt_grad", "wgrad_small",
                  "cast_bf16", "round_tf32", "pad_nhwc", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd",
                  "cross_attn_fwd", "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd", "head_fwd",
-                 "head_bwd"):
+                 "head_bwd", "im2col_patches", "vision_assemble", "slice_rows", "unslice_rows", "add_f32", "film_fwd", "film_bwd", "ffn64_fwd",
+                 "ffn64_bwd"):
         monkeypatch.setattr(abi, name, globals()[name])
     monkeypatch.setattr(abi, "require_device", lambda: None)
     monkeypatch.setattr(abi, "check_cuda_input", lambda t: None)

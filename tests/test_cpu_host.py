@@ -372,3 +372,55 @@ def test_lightning_checkpoint_shaped_state_dict_round_trip():
     assert not res.missing_keys and not res.unexpected_keys
     for k, v in dst.state_dict().items():
         assert torch.equal(v, sd[k]), k
+
+
+@pytest.mark.parametrize("case", ["maple", "vpt", "coop", "coop_deep", "cocoop", "shared_attn", "shared_separate"])
+def test_clipseg_engine_composition_against_oracle(case, monkeypatch):
+    """The host-side composition of the CLIPSeg engine - operand packing (fused QKV, folded scale, split-bf16 FFN
+    weights), layouts, flags, the prompt table overwrite / gradient routing, the bottom-block backward restricted to the
+    prompt rows (``tvs_attn_bwd_tail`` leaves the other rows unwritten: the emulation poisons them with NaN), the
+    stacked-parameter gradient accumulation and the autograd wiring of the three nodes - run over a CPU emulation of the
+    C ABI (tests/fake_abi.py) must reproduce the oracle: logits to the emulated operand precision, every learner / head
+    gradient, and exactly-zero gradients for the parameters the reference never uses."""
+    import contextlib
+
+    from oracle import clipseg as OC
+    from tests import fake_abi
+    from tests.helpers import SMALL, build_net, make_batch, oracle_head, oracle_state
+
+    fake_abi.install(monkeypatch)
+
+    class _NoStream:                                  # there is no CUDA here: both towers run in line
+        def wait_stream(self, other): ...
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    monkeypatch.setenv("TVS_TEXT_STREAM", "0")
+
+    weights = OC.init_weights(SMALL, seed=7)
+    net = build_net(case, SMALL, weights, seed=5)
+    st, head = oracle_state(case, net, SMALL), oracle_head(net)
+    img, ids, am, mask = make_batch(SMALL, 2, 8, 9)
+    logits = net(text_input={"input_ids": ids, "attention_mask": am}, image_input=img)
+    ref = OC.net_forward(weights, SMALL, st, head, ids, am, img)
+    assert logits.shape == ref.shape
+    assert (logits - ref).abs().max().item() < 2e-2, (logits - ref).abs().max().item()
+    gw = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    (logits * gw).sum().backward()
+    (ref * gw).sum().backward()
+    named = dict(net.named_parameters())
+    checked = 0
+    for k, p_ref in list(st.params.items()) + list(head.items()):
+        pk = k if k in head else f"context_learner.{k}"
+        if pk not in named:
+            continue
+        g, g_ref = named[pk].grad, p_ref.grad
+        if g_ref is None or g_ref.abs().max() == 0:
+            assert g is None or g.abs().max().item() == 0, pk
+            continue
+        assert g is not None and torch.isfinite(g).all(), pk
+        err = ((g - g_ref).norm() / g_ref.norm()).item()
+        assert err < 5e-2, f"{pk}: {err}"
+        checked += 1
+    assert checked > 0

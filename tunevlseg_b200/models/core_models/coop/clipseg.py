@@ -72,8 +72,7 @@ class BaseCLIPSeg(HFCLIPSegWrapper, ABC):
             raise ValueError("Invalid conditional, should be either provided as `input_ids` or `conditional_pixel_values`")
         if len(input_ids) != pixel_values.shape[0]:
             raise ValueError("Make sure to pass as many prompt texts as there are query images")
-        if not pixel_values.is_cuda:
-            raise abi.TvsError("tunevlseg_b200 runs on a CUDA (sm_100a) device only; inputs must be CUDA tensors")
+        abi.check_cuda_input(pixel_values)      # TvsError for host tensors: there is no CPU path
 
     def _text_condition(self, input_ids, attention_mask, learner, image_features=None):
         """Conditional embedding (B, projection_dim).  ``learner`` None = stock HF text path (no prompts)."""
