@@ -392,12 +392,64 @@ def ffn64_bwd(x, g, w1, w2t, b1, dx):
     dx.copy_(g + ((g @ _ffn_w(w2t).t()) * mask) @ _ffn_w(w1))
 
 
+# ---- loss + metric counters (loss_metrics.cu) -------------------------------------------------------------------------------
+def dicebce_scratch_bytes(B, N):
+    return 16
+
+
+def _counts(p, y, thr):
+    t = y.long() & 1
+    ge, gt = (p >= thr).long(), (p > thr).long()
+    counts = torch.stack(((ge * t).sum(1), (ge * (1 - t)).sum(1), ((1 - ge) * t).sum(1)), dim=1)
+    conf = torch.stack((((1 - t) * (1 - gt)).sum(), ((1 - t) * gt).sum(), (t * (1 - gt)).sum(), (t * gt).sum()))
+    return counts, conf
+
+
+def dicebce_metrics_fwd(logits, mask, threshold, lambda_dice, lambda_ce, parts, counts, confmat, loss, scratch):
+    B = logits.shape[0]
+    x, y = logits.reshape(B, -1).float(), mask.reshape(B, -1).float()
+    p = 1.0 / (1.0 + torch.exp(-x))            # fl32(1 / fl32(1 + fl32(exp(-x)))): the definition the counters are bit-exact against
+    bce = torch.clamp(x, min=0) - x * y + torch.log1p(torch.exp(-x.abs()))
+    pr = torch.stack(((p * y).sum(1), p.sum(1), y.sum(1), bce.sum(1)), dim=1).double()
+    if parts is not None:
+        parts.copy_(pr)
+    c, cf = _counts(p, y, threshold)
+    if counts is not None:
+        counts.copy_(c)
+    if confmat is not None:
+        confmat += cf
+    if loss is not None:
+        dice = 1.0 - (2.0 * pr[:, 0] + 1e-5) / (pr[:, 1] + pr[:, 2] + 1e-5)
+        loss.fill_(float(lambda_dice * dice.mean() + lambda_ce * pr[:, 3].sum() / (B * x.shape[1])))
+
+
+def dicebce_bwd(logits, mask, parts, gscale, lambda_dice, lambda_ce, dlogits):
+    B = logits.shape[0]
+    x, y = logits.reshape(B, -1).float(), mask.reshape(B, -1).float()
+    N = x.shape[1]
+    p = torch.sigmoid(x)
+    I, P, G = (parts[:, k].unsqueeze(1) for k in range(3))
+    den = P + G + 1e-5
+    ddice = (-(2.0 * y * den - (2.0 * I + 1e-5)) / den ** 2).float()
+    gs = 1.0 if gscale is None else float(gscale)
+    dlogits.copy_((gs * (lambda_dice / B * ddice * p * (1 - p) + lambda_ce / (B * N) * (p - y))).view_as(dlogits))
+
+
+def metrics_from_probs(preds, mask, threshold, counts, confmat, scratch):
+    B = preds.shape[0]
+    c, cf = _counts(preds.reshape(B, -1).float(), mask.reshape(B, -1).float(), threshold)
+    if counts is not None:
+        counts.copy_(c)
+    if confmat is not None:
+        confmat += cf
+
+
 def install(monkeypatch):
     for name in ("gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "prompt_overwrite", "prompt_grad", "wgrad_small",
                  "cast_bf16", "round_tf32", "pad_nhwc", "im2col_nhwc", "col2im_nhwc", "relu_mask", "avgpool2_nhwc", "upsample2x_fwd", "upsample2x_bwd",
                  "cross_attn_fwd", "cross_attn_bwd", "dynconv_fwd", "dynconv_bwd", "resample2d_fwd", "resample2d_bwd", "head_fwd",
                  "head_bwd", "im2col_patches", "vision_assemble", "slice_rows", "unslice_rows", "add_f32", "film_fwd", "film_bwd", "ffn64_fwd",
-                 "ffn64_bwd"):
+                 "ffn64_bwd", "dicebce_scratch_bytes", "dicebce_metrics_fwd", "dicebce_bwd", "metrics_from_probs"):
         monkeypatch.setattr(abi, name, globals()[name])
     monkeypatch.setattr(abi, "require_device", lambda: None)
     monkeypatch.setattr(abi, "check_cuda_input", lambda t: None)

@@ -424,3 +424,67 @@ def test_clipseg_engine_composition_against_oracle(case, monkeypatch):
         assert err < 5e-2, f"{pk}: {err}"
         checked += 1
     assert checked > 0
+
+
+def test_module_training_and_eval_steps_over_cpu_abi_emulation(monkeypatch):
+    """``ImageTextMaskModule`` end to end on the CPU ABI emulation: ``training_step`` (fused loss + counters, backward,
+    torch AdamW on the learner parameters), ``validation_step`` / ``test_step`` metric accumulation and ``predict_step``,
+    against the oracle's loss, Dice (average="samples", >=) and IoU (global confusion matrix, >) on the same logits."""
+    import contextlib
+
+    from oracle import clipseg as OC
+    from oracle import loss_metrics as OLM
+    from tests import fake_abi
+    from tests.helpers import SMALL, build_net, make_batch, oracle_head, oracle_state
+    from tunevlseg_b200.losses import DiceCELoss
+    from tunevlseg_b200.models.image_text_mask_module import ImageTextMaskModule
+
+    fake_abi.install(monkeypatch)
+
+    class _NoStream:
+        def wait_stream(self, other): ...
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    monkeypatch.setenv("TVS_TEXT_STREAM", "0")
+
+    weights = OC.init_weights(SMALL, seed=7)
+    net = build_net("maple", SMALL, weights, seed=5)
+    st, head = oracle_state("maple", net, SMALL), oracle_head(net)
+    module = ImageTextMaskModule(net=net, loss_fn=DiceCELoss(sigmoid=True, lambda_dice=1, lambda_ce=0.2),
+                                 optimizer=partial(torch.optim.AdamW, lr=1e-3), scheduler=None, compile=False, task="binary",
+                                 threshold=0.5, weight_decay=0.01)
+    module.setup("fit")
+    module.setup("test")
+    opt = module.configure_optimizers()["optimizer"]
+    img, ids, am, mask = make_batch(SMALL, 3, 8, 21)
+    batch = {"image": img, "mask": mask, "input_ids": ids, "attention_mask": am, "mask_name": ["a", "b", "c"],
+             "mask_shape": torch.tensor([[64, 64]] * 3)}
+
+    ref = OC.net_forward(weights, SMALL, st, head, ids, am, img)
+    ref_loss = OLM.dice_ce_loss(ref, mask)
+    loss = module.training_step(batch, 0)
+    assert abs(loss.item() - ref_loss.item()) < 5e-3
+    before = {k: p.detach().clone() for k, p in net.named_parameters() if p.requires_grad}
+    loss.backward()
+    opt.step()
+    moved = [k for k, p in net.named_parameters() if p.requires_grad and p.grad is not None and not torch.equal(p, before[k])]
+    assert any(k.startswith("context_learner.") for k in moved) and "residual_ratio" in moved
+
+    # metric accumulation: counters of the batch == the oracle's counters on the module's own logits
+    module.test_dice.reset(); module.test_iou.reset()
+    with torch.no_grad():
+        logits = module.get_logits(batch)
+        module.test_step(batch, 0)
+    _, c_counts, c_conf = OLM.c_dicebce_metrics(logits, mask)
+    tp, fp, fn = (c_counts[:, k].double() for k in range(3))
+    dice_ref = torch.where(2 * tp + fp + fn > 0, 2 * tp / (2 * tp + fp + fn), torch.ones_like(tp)).mean()
+    tn_, fp_, fn_, tp_ = (c_conf.view(-1)[k].double() for k in range(4))
+    iou_ref = tp_ / (tp_ + fp_ + fn_) if (tp_ + fp_ + fn_) > 0 else torch.tensor(1.0)
+    assert abs(module.test_dice.compute().item() - dice_ref.item()) < 1e-6
+    assert abs(module.test_iou.compute().item() - iou_ref.item()) < 1e-6
+    with torch.no_grad():
+        out = module.predict_step(batch, 0)
+    assert out["preds"].shape == (3, 1, SMALL.image_size, SMALL.image_size) and out["mask_name"] == ["a", "b", "c"]
+    assert float(out["preds"].min()) >= 0.0 and float(out["preds"].max()) <= 1.0
