@@ -488,3 +488,31 @@ def test_module_training_and_eval_steps_over_cpu_abi_emulation(monkeypatch):
         out = module.predict_step(batch, 0)
     assert out["preds"].shape == (3, 1, SMALL.image_size, SMALL.image_size) and out["mask_name"] == ["a", "b", "c"]
     assert float(out["preds"].min()) >= 0.0 and float(out["preds"].max()) <= 1.0
+
+
+def test_cris_distributed_checkpoint_conversion_and_strict_load(tmp_path):
+    """scripts/process_cris_checkpoint.py (reference :5-25) -> ``CRIS(cris_pretrain=...)`` strict load (reference
+    cris_model/__init__.py:64-69): a DDP-saved ``{"state_dict": {"module.<key>": ...}}`` file becomes the single-process
+    state dict and restores every CRIS tensor."""
+    from oracle import cris as OCR
+    from tests.helpers import CRIS_SMALL, cris_model_cfg
+    from tunevlseg_b200.models.components.cris_model import CRIS
+    from tunevlseg_b200.scripts import process_cris_checkpoint as P
+
+    w = OCR.init_weights(CRIS_SMALL, seed=11)
+    src = CRIS(**cris_model_cfg(CRIS_SMALL, w))
+    with torch.no_grad():
+        for p in src.neck.parameters():
+            p.add_(0.25)
+    ddp_path, single_path = tmp_path / "cris_best.pth", tmp_path / "cris_best_single.pth"
+    torch.save({"state_dict": {"module." + k: v for k, v in src.state_dict().items()}, "epoch": 3}, ddp_path)
+    P.main(ddp_path, single_path, prefix="model.", pickle_protocol=5)
+    from tunevlseg_b200.models.components.cris_model import load_checkpoint
+
+    converted = load_checkpoint(single_path)             # protocol-5 file: the weights-only unpickler alone rejects it
+    assert set(converted) == set(src.state_dict())
+    dst = CRIS(**dict(cris_model_cfg(CRIS_SMALL, OCR.init_weights(CRIS_SMALL, seed=12)), cris_pretrain=str(single_path)))
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    with pytest.raises(ValueError):
+        P.convert({"short": torch.zeros(1)})

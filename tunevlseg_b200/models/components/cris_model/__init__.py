@@ -189,6 +189,19 @@ class Projector(_Holder):
         self.txt = nn.Linear(word_dim, in_dim * kernel_size * kernel_size + 1)
 
 
+def load_checkpoint(path):
+    """``torch.load(path, map_location="cpu")`` as the reference calls it (cris_model/__init__.py:66).  The reference's
+    conversion script writes with ``pickle_protocol=5`` (scripts/process_cris_checkpoint.py:22), whose framing opcodes the
+    weights-only unpickler of current torch rejects, so a file the reference itself produced would not load with the new
+    default; such files (the user's own, exactly what the reference always unpickled) are retried the reference's way."""
+    import pickle
+
+    try:
+        return torch.load(path, map_location="cpu")
+    except pickle.UnpicklingError:
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
 class CRIS(nn.Module):
     """cris_model/__init__.py:20-132.  ``clip_pretrain`` is the TorchScript ``RN50.pt`` path as in the reference, or a
     CLIP ``state_dict`` mapping (tests / benchmarks hand over random weights: there is no checkpoint in this image)."""
@@ -207,7 +220,7 @@ class CRIS(nn.Module):
         self.proj = Projector(word_dim, vis_dim // 2, 3)
         if cris_pretrain is not None:
             print("Loading CRIS pre-trained model from:", cris_pretrain)
-            self.load_state_dict(torch.load(cris_pretrain, map_location="cpu"), strict=True)
+            self.load_state_dict(load_checkpoint(cris_pretrain), strict=True)
         self.word_dim = word_dim
 
     @staticmethod
