@@ -11,7 +11,7 @@ import torch
 
 from oracle import learners as OL
 from oracle import loss_metrics as OLM
-from tests.golden_cases import CASES, TINY, learner_state, load_case
+from tests.golden_cases import TINY, learner_state, load_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

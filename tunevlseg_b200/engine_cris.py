@@ -15,7 +15,6 @@ the positional tables, the 13x13 ``f5 * state`` product) stays in torch.
 """
 from __future__ import annotations
 
-import math
 from types import SimpleNamespace
 
 import torch

@@ -12,7 +12,7 @@ from types import SimpleNamespace
 from typing import Any
 
 import torch
-from torch import nn, optim
+from torch import nn
 
 from ..losses import DiceCELoss
 from ..metrics import Dice, JaccardIndex
