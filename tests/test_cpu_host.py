@@ -516,3 +516,73 @@ def test_cris_distributed_checkpoint_conversion_and_strict_load(tmp_path):
         assert torch.equal(dst.state_dict()[k], v), k
     with pytest.raises(ValueError):
         P.convert({"short": torch.zeros(1)})
+
+
+# ---- round-2 drop-in fixes -------------------------------------------------------------------------------------------
+def test_epoch_metrics_are_computed_over_the_accumulated_state_and_reset():
+    """The reference logs the torchmetrics objects (image_text_mask_module.py:118-125,144-170): Lightning reports
+    ``compute()`` over the epoch's accumulated state and resets afterwards.  Two unequal batches: the epoch IoU is the IoU
+    of the SUMMED confusion matrix (not a mean of per-batch IoUs), Dice the mean over all 5 samples; the next epoch starts
+    from an empty state."""
+    from tunevlseg_b200.losses import DiceCELoss
+    from tunevlseg_b200.metrics import Dice, JaccardIndex
+    from tunevlseg_b200.models.image_text_mask_module import ImageTextMaskModule
+
+    module = ImageTextMaskModule(net=torch.nn.Linear(1, 1), loss_fn=DiceCELoss(sigmoid=True, lambda_dice=1, lambda_ce=0.2),
+                                 optimizer=None, scheduler=None, compile=False, task="binary", threshold=0.5)
+    module.setup("fit")
+    c1 = torch.tensor([[10, 2, 3], [0, 0, 0], [5, 5, 5]])
+    c2 = torch.tensor([[1, 9, 0], [7, 0, 1]])
+    f1, f2 = torch.tensor([100, 7, 8, 15]), torch.tensor([10, 9, 1, 8])
+    for stage, keys in (("val", ("val_dice", "val_iou")), ("train", ("train_dice_epoch", "train_iou_epoch"))):
+        dice, iou = getattr(module, f"{stage}_dice"), getattr(module, f"{stage}_iou")
+        for c, f in ((c1, f1), (c2, f2)):
+            dice.update_from_counts(c)
+            iou.update_from_confmat(f)
+        getattr(module, f"on_{'validation' if stage == 'val' else stage}_epoch_end")()
+        want_dice = Dice.score(torch.cat((c1, c2)), 1.0)
+        want_iou = JaccardIndex.score(f1 + f2, 1.0)
+        assert abs(float(module.logged[keys[0]]) - float(want_dice)) < 1e-6
+        assert abs(float(module.logged[keys[1]]) - float(want_iou)) < 1e-6
+        mean_of_batches = (JaccardIndex.score(f1, 1.0) + JaccardIndex.score(f2, 1.0)) / 2
+        assert abs(float(want_iou) - float(mean_of_batches)) > 1e-3          # the two notions really differ on this data
+        assert not dice.has_updates and int(iou.confmat.sum()) == 0          # reset for the next epoch
+        module.logged.clear()
+        getattr(module, f"on_{'validation' if stage == 'val' else stage}_epoch_end")()   # nothing accumulated: logs nothing, no error
+        assert not module.logged
+
+
+def test_install_as_src_aliases_monai_dice_ce_loss():
+    """configs/model/maple_clipseg.yaml:29-33 ``_target_: monai.losses.DiceCELoss`` must resolve to the fused loss, so the
+    module takes the one-pass loss + counters branch with the stock YAML."""
+    import importlib
+
+    import tunevlseg_b200
+    from tunevlseg_b200.losses import DiceCELoss
+
+    tunevlseg_b200.install_as_src()
+    cls = getattr(importlib.import_module("monai.losses"), "DiceCELoss")
+    assert cls is DiceCELoss
+    loss = cls(sigmoid=True, lambda_dice=1, lambda_ce=0.2)       # the reference's kwargs
+    assert isinstance(loss, DiceCELoss)
+
+
+def test_load_checkpoint_rejects_pickles_that_name_foreign_globals(tmp_path, monkeypatch):
+    """A protocol-5 checkpoint is re-read with an unpickler restricted to torch's weights-only allow-list; a file that
+    references any other callable (the malicious case) must fail instead of being fully unpickled."""
+    import pickle
+
+    from tunevlseg_b200.models.components.cris_model import load_checkpoint
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("arbitrary code ran",))
+
+    good, bad = tmp_path / "good.pth", tmp_path / "bad.pth"
+    torch.save({"w": torch.arange(6.0).view(2, 3)}, good, pickle_protocol=5)
+    torch.save({"w": Evil()}, bad, pickle_protocol=5)
+    assert torch.equal(load_checkpoint(good)["w"], torch.arange(6.0).view(2, 3))
+    monkeypatch.delenv("TVS_ALLOW_UNSAFE_PICKLE", raising=False)
+    with pytest.raises(pickle.UnpicklingError):
+        load_checkpoint(bad)
+    assert load_checkpoint(bad, allow_unsafe_pickle=True)["w"] is None      # explicit opt-in: print(...) ran and returned None

@@ -1,5 +1,5 @@
 """World-size-2 checks on the CPU (gloo): the N > 1 host logic that does not need a GPU -
-metric state synchronisation (confusion matrix: sum-reduce; per-sample Dice counts: gather) and the reference arm's
+metric state synchronisation (confusion matrix: sum-reduce; per-sample Dice scores: sum + count, unequal per-rank sample counts) and the reference arm's
 rank protocol under torchrun (rank 0 measures and prints one JSON line, other ranks exit 0 silently)."""
 import json
 import os
@@ -13,17 +13,24 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _updates(rank):
+    """UNEQUAL per-rank sample counts (the last validation batch is not dropped, image_text_mask_datamodule.py:40-47):
+    rank 0 sees 3 batches of 4, rank 1 sees 2 batches of 4 and one of 1."""
+    g = torch.Generator().manual_seed(100 + rank)
+    for k in range(3):
+        n = 1 if (rank == 1 and k == 2) else 4
+        counts = torch.randint(0, 100, (n, 3), generator=g)
+        counts[0] = 0                                    # an empty sample: zero_division -> 1
+        yield counts, torch.randint(0, 1000, (4,), generator=g)
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tunevlseg_b200.metrics import Dice, JaccardIndex
 
-    g = torch.Generator().manual_seed(100 + rank)
     dice, iou = Dice(threshold=0.5, zero_division=1, average="samples"), JaccardIndex(task="binary", threshold=0.5, zero_division=1)
-    for _ in range(3):
-        counts = torch.randint(0, 100, (4, 3), generator=g)
-        counts[0] = 0                                    # an empty sample: zero_division -> 1
-        conf = torch.randint(0, 1000, (4,), generator=g)
+    for counts, conf in _updates(rank):
         dice.update_from_counts(counts)
         iou.update_from_confmat(conf)
     d, i = dice.compute(), iou.compute()
@@ -41,11 +48,7 @@ def test_metric_sync_world2(tmp_path):
     # single-process reference over the union of both ranks' updates
     dice, iou = Dice(threshold=0.5, zero_division=1, average="samples"), JaccardIndex(task="binary", threshold=0.5, zero_division=1)
     for rank in range(2):
-        g = torch.Generator().manual_seed(100 + rank)
-        for _ in range(3):
-            counts = torch.randint(0, 100, (4, 3), generator=g)
-            counts[0] = 0
-            conf = torch.randint(0, 1000, (4,), generator=g)
+        for counts, conf in _updates(rank):
             dice.update_from_counts(counts)
             iou.update_from_confmat(conf)
     assert torch.allclose(got["dice"], dice.compute(), atol=1e-6)

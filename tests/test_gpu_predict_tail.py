@@ -19,9 +19,15 @@ def test_resize_quantise_matches_torchvision(src, dst):
     ours = resize_to_png_array(pred, dst).cpu()
     ref = TF.resize(pred.cpu().float(), size=list(dst), interpolation=TF.InterpolationMode.BICUBIC, antialias=False)
     ref_u8 = ref.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8)[0]            # torchvision.utils.save_image
+    assert ours.shape == ref_u8.shape
+    # byte work: bit-exact against the oracle (pinned to ATen's CPU kernel in tests/test_oracle_resize_u8.py) ...
+    from oracle import resize_u8 as OR
+
+    want = torch.from_numpy(OR.resize_to_png_array(pred.cpu().numpy(), dst))
+    assert torch.equal(ours, want), f"{(ours != want).sum().item()} bytes differ from the oracle"
+    # ... and against torchvision on the host, which is what the reference's save_predictions runs
     diff = (ours.int() - ref_u8.int()).abs()
-    assert ours.shape == ref_u8.shape and diff.max().item() <= 1                 # a tie at x.5 may round either way in fp32
-    assert (diff == 0).float().mean().item() > 0.999
+    assert diff.max().item() == 0, f"{(diff != 0).sum().item()} bytes differ from torchvision"
 
 
 def test_save_predictions_and_eval_script(tmp_path):

@@ -46,13 +46,135 @@ def test_fused_adamw_matches_torch(wd):
             gr = torch.randn(p.shape, device="cuda", generator=g) * (0.1 + step)
             p.grad.copy_(gr)
             q.grad = gr.clone()
-        if step == 3:       # a scheduler changing the group lr must reach the kernel
+        if step == 3:       # a scheduler changing the group lr must reach the kernel - param_groups is all it touches
             a.param_groups[0]["lr"] = b.param_groups[0]["lr"] = 1e-3
-            a.sync_lr()
         a.step()
         b.step()
     for p, q in zip(ours, theirs):
         assert torch.allclose(p, q, rtol=2e-6, atol=2e-7), (p - q).abs().max().item()
+
+
+def _twin_params(shapes, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    return ours, [torch.nn.Parameter(p.detach().clone()) for p in ours], g
+
+
+def _drive(opts, params, g, steps, scale0=0):
+    for step in range(steps):
+        grads = [torch.randn(p.shape, device="cuda", generator=g) * (0.1 + scale0 + step) for p in params[0]]
+        for opt, ps in zip(opts, params):
+            opt.zero_grad()
+            for p, gr in zip(ps, grads):
+                if p.grad is None:
+                    p.grad = gr.clone()
+                else:
+                    p.grad.copy_(gr)
+            opt.step()
+
+
+def test_fused_adamw_follows_reduce_lr_on_plateau():
+    """The reference's default scheduler (maple_clipseg.yaml:50-55) only edits ``param_groups[i]["lr"]``; the kernel reads
+    a device scalar.  Driving a REAL ReduceLROnPlateau on both optimizers (no sync_lr call anywhere) must keep them equal."""
+    from tunevlseg_b200.optim import FusedAdamW
+
+    ours, theirs, g = _twin_params([(9, 4, 64), (33,), (1,)])
+    a = FusedAdamW(ours, lr=5e-3, weight_decay=0.01)
+    b = torch.optim.AdamW(theirs, lr=5e-3, weight_decay=0.01)
+    sa = torch.optim.lr_scheduler.ReduceLROnPlateau(a, mode="min", factor=0.1, patience=0)
+    sb = torch.optim.lr_scheduler.ReduceLROnPlateau(b, mode="min", factor=0.1, patience=0)
+    for epoch, val_loss in enumerate([1.0, 1.1, 1.2, 0.5, 0.6]):      # two plateaus -> lr 5e-3 -> 5e-4 -> 5e-5 -> ...
+        _drive([a, b], [ours, theirs], g, 2, scale0=epoch)
+        sa.step(val_loss)
+        sb.step(val_loss)
+    assert a.param_groups[0]["lr"] == b.param_groups[0]["lr"] < 5e-3
+    _drive([a, b], [ours, theirs], g, 2)
+    for p, q in zip(ours, theirs):
+        assert torch.allclose(p, q, rtol=2e-6, atol=2e-7), (p - q).abs().max().item()
+
+
+def test_fused_adamw_state_dict_round_trip_and_torch_interchange():
+    """Lightning checkpoints ``optimizer.state_dict()``: moments and step count must be in it (torch.optim.AdamW layout),
+    a resumed optimizer must continue bit for bit, and a torch.optim.AdamW state dict must load."""
+    from tunevlseg_b200.optim import FusedAdamW
+
+    shapes = [(9, 4, 64), (33,), (5, 5, 3)]
+    ours, theirs, g = _twin_params(shapes)
+    a = FusedAdamW(ours, lr=3e-3, weight_decay=0.02)
+    b = torch.optim.AdamW(theirs, lr=3e-3, weight_decay=0.02)
+    _drive([a, b], [ours, theirs], g, 3)
+    sd = a.state_dict()
+    sd_t = b.state_dict()
+    assert set(sd["state"]) == set(sd_t["state"]) == {0, 1, 2}
+    for i in range(3):
+        assert float(sd["state"][i]["step"]) == float(sd_t["state"][i]["step"]) == 3.0
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert sd["state"][i][k].shape == sd_t["state"][i][k].shape
+            assert torch.allclose(sd["state"][i][k], sd_t["state"][i][k], rtol=1e-5, atol=1e-9)
+    # resume into a fresh optimizer over copies of the parameters, with a DIFFERENT constructor lr: the checkpoint wins
+    resumed = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    a2 = FusedAdamW(resumed, lr=1.0, weight_decay=0.02)
+    a2.load_state_dict(sd)
+    assert a2.param_groups[0]["lr"] == 3e-3
+    # and a torch.optim.AdamW state dict into a third one
+    from_torch = [torch.nn.Parameter(q.detach().clone()) for q in theirs]
+    a3 = FusedAdamW(from_torch, lr=3e-3, weight_decay=0.02)
+    a3.load_state_dict(sd_t)
+    g2 = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(3):
+        grads = [torch.randn(s, device="cuda", generator=g2) for s in shapes]
+        for opt, ps in ((a, ours), (a2, resumed), (a3, from_torch), (b, theirs)):
+            opt.zero_grad()
+            for p, gr in zip(ps, grads):
+                if p.grad is None:
+                    p.grad = gr.clone()
+                else:
+                    p.grad.copy_(gr)
+            opt.step()
+    for p, r, t, q in zip(ours, resumed, from_torch, theirs):
+        assert torch.equal(p, r), "resumed FusedAdamW diverged from the uninterrupted one"
+        assert torch.allclose(t, q, rtol=2e-6, atol=2e-7)
+    assert float(a2.state_dict()["state"][0]["step"]) == 6.0
+
+
+def test_fused_adamw_rejects_parameters_moved_off_the_flat_buffer():
+    from tunevlseg_b200.abi import TvsError
+    from tunevlseg_b200.optim import FusedAdamW
+
+    lin = torch.nn.Linear(8, 8).cuda()
+    opt = FusedAdamW(lin.parameters(), lr=1e-3)
+    lin.weight.data = lin.weight.data.clone()          # what model.to()/float() does: new storage
+    with pytest.raises(TvsError, match="storage no longer aliases"):
+        opt.step()
+
+
+def test_graph_replay_sees_scheduler_lr_changes():
+    """Inside a captured step the kernel reads the lr from a device scalar; GraphedTrainStep refreshes it from
+    param_groups before every replay, so a scheduler step between replays takes effect (and equals the eager run)."""
+    from tunevlseg_b200.graph import GraphedTrainStep
+
+    batch = _batch()
+    m_e, o_e = _module()
+    m_g, o_g = _module()
+    step = GraphedTrainStep(m_g, o_g, batch, warmup=3)
+    for _ in range(3):
+        o_e.zero_grad()
+        m_e.training_step(batch, 0).backward()
+        o_e.step()
+    for opt in (o_e, o_g):
+        for grp in opt.param_groups:
+            grp["lr"] = grp["lr"] * 0.05
+    o_e.zero_grad()
+    le = m_e.training_step(batch, 0)
+    le.backward()
+    o_e.step()
+    lg = step(batch)
+    assert abs(le.item() - lg.item()) <= 1e-5
+    pe, pg = dict(m_e.named_parameters()), dict(m_g.named_parameters())
+    for k, p in pe.items():
+        if p.requires_grad:
+            assert torch.allclose(p, pg[k], rtol=1e-5, atol=1e-6), f"{k}: {(p - pg[k]).abs().max().item()}"
+    assert m_g.train_dice.streaming        # GraphedTrainStep switched the Dice metrics to device-side accumulation
 
 
 def test_fused_adamw_rejects_detached_grads():

@@ -35,3 +35,24 @@ def install_as_src() -> None:
         mod = importlib.import_module(f"{__name__}.{n}")
         sys.modules[f"src.{n}"] = mod
     setattr(sys.modules["src"], "models", sys.modules["src.models"])
+    _alias_monai_loss()
+
+
+def _alias_monai_loss() -> None:
+    """``_target_: monai.losses.DiceCELoss`` (configs/model/maple_clipseg.yaml:29-33) -> ``tunevlseg_b200.losses.DiceCELoss``.
+    When monai is importable its module object is kept and only the ``DiceCELoss`` attribute is re-pointed (the fused
+    class raises ``NotImplementedError`` for any configuration it does not cover, so nothing is silently different);
+    when it is absent, stand-in ``monai`` / ``monai.losses`` modules holding just that class are registered."""
+    import types
+
+    from .losses import DiceCELoss
+
+    try:
+        losses = importlib.import_module("monai.losses")
+    except Exception:  # noqa: BLE001 - monai absent (or broken): register the stand-in
+        monai = sys.modules.get("monai") or types.ModuleType("monai")
+        losses = types.ModuleType("monai.losses")
+        monai.losses = losses
+        monai.__dict__.setdefault("__tvs_stand_in__", True)
+        sys.modules["monai"], sys.modules["monai.losses"] = monai, losses
+    losses.DiceCELoss = DiceCELoss

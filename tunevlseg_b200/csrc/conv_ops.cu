@@ -704,15 +704,33 @@ __global__ void __launch_bounds__(256) resample2d_fwd_kernel(const float* __rest
         const int r = static_cast<int>(idx - b * Ho * Wo);
         const int y = r / Wo, x = r - y * Wo;
         float acc = 0.f;
-        for (int a = 0; a < NT; ++a) {
-            const float* row = in + (b * Hi + iy[y * NT + a]) * Wi;
-            float s = 0.f;
-            for (int c = 0; c < NT; ++c) s = fmaf(wx[x * NT + c], row[ix[x * NT + c]], s);
-            acc = fmaf(wy[y * NT + a], s, acc);
+        if (U8 && NT == 4) {
+            // Byte-exact against the reference's host-side TF.resize (ATen UpSampleKernel.cpp Interpolate<2,...,4>, x86 build
+            // with FMA contraction; restated and pinned in oracle/resize_u8.py): every 4-tap sum is
+            // fma(v3, w3, fma(v2, w2, fma(v0, w0, fl(v1 * w1)))), x taps inside, y taps outside.
+            float t[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float* row = in + (b * Hi + iy[y * 4 + a]) * Wi;
+                float s = __fmaf_rn(row[ix[x * 4 + 0]], wx[x * 4 + 0], __fmul_rn(row[ix[x * 4 + 1]], wx[x * 4 + 1]));
+                s = __fmaf_rn(row[ix[x * 4 + 2]], wx[x * 4 + 2], s);
+                t[a] = __fmaf_rn(row[ix[x * 4 + 3]], wx[x * 4 + 3], s);
+            }
+            acc = __fmaf_rn(t[0], wy[y * 4 + 0], __fmul_rn(t[1], wy[y * 4 + 1]));
+            acc = __fmaf_rn(t[2], wy[y * 4 + 2], acc);
+            acc = __fmaf_rn(t[3], wy[y * 4 + 3], acc);
+        } else {
+            for (int a = 0; a < NT; ++a) {
+                const float* row = in + (b * Hi + iy[y * NT + a]) * Wi;
+                float s = 0.f;
+                for (int c = 0; c < NT; ++c) s = fmaf(wx[x * NT + c], row[ix[x * NT + c]], s);
+                acc = fmaf(wy[y * NT + a], s, acc);
+            }
         }
         if (U8) {
-            // torchvision.utils.save_image: mul(255).add(0.5).clamp(0, 255).to(uint8)
-            static_cast<uint8_t*>(out)[idx] = static_cast<uint8_t>(fminf(fmaxf(fmaf(acc, 255.f, 0.5f), 0.f), 255.f));
+            // torchvision.utils.save_image: mul(255).add_(0.5).clamp_(0, 255).to(uint8) - two roundings, then truncation
+            const float q = __fadd_rn(__fmul_rn(acc, 255.f), 0.5f);
+            static_cast<uint8_t*>(out)[idx] = static_cast<uint8_t>(fminf(fmaxf(q, 0.f), 255.f));
         } else {
             static_cast<float*>(out)[tiled_index(b, y, x, Ho, Wo, tile)] = acc;
         }

@@ -208,6 +208,20 @@ dicebce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ m
     }
 }
 
+// B * 48 bytes of dynamic shared memory: above 48 KB (B > 1024, up to the 4096 the entry points accept = 192 KB) the kernel
+// needs the opt-in attribute, otherwise the launch fails
+static int finalize_smem_opt_in(size_t sh) {
+    static size_t granted = 48 * 1024;
+    if (sh <= granted) return 0;
+    cudaError_t e = cudaFuncSetAttribute(dicebce_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sh));
+    if (e != cudaSuccess) {
+        set_error("dicebce_finalize_kernel: cannot opt in to %zu bytes of shared memory: %s", sh, cudaGetErrorString(e));
+        return -2;
+    }
+    granted = sh;
+    return 0;
+}
+
 }  // namespace tvs
 
 extern "C" __attribute__((visibility("default"))) int64_t tvs_dicebce_scratch_bytes(int32_t B, int64_t N) {
@@ -228,6 +242,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_dicebce_metrics_fwd(co
     dicebce_partial_kernel<false><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(logits, mask, N, threshold, part, cnt);
     if (int rc = check_launch("dicebce_partial_kernel")) return rc;
     const size_t sh = static_cast<size_t>(B) * (2 * sizeof(double) + 4 * sizeof(long long));
+    if (int rc = finalize_smem_opt_in(sh)) return rc;
     dicebce_finalize_kernel<<<1, 256, sh, st>>>(part, cnt, B, nblk, N, lambda_dice, lambda_ce, parts, reinterpret_cast<long long*>(counts),
                                                 reinterpret_cast<long long*>(confmat), loss);
     return check_launch("dicebce_finalize_kernel");
@@ -257,6 +272,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_metrics_from_probs(con
     dicebce_partial_kernel<true><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(preds, mask, N, threshold, part, cnt);
     if (int rc = check_launch("dicebce_partial_kernel")) return rc;
     const size_t sh = static_cast<size_t>(B) * (2 * sizeof(double) + 4 * sizeof(long long));
+    if (int rc = finalize_smem_opt_in(sh)) return rc;
     dicebce_finalize_kernel<<<1, 256, sh, st>>>(part, cnt, B, nblk, N, 0.f, 0.f, nullptr, reinterpret_cast<long long*>(counts),
                                                 reinterpret_cast<long long*>(confmat), nullptr);
     return check_launch("dicebce_finalize_kernel");

@@ -105,11 +105,28 @@ def _mha_ops(sd, prefix, heads):
     return SimpleNamespace(q=q, k=k, v=v, qk=qk, o=o, heads=heads, hd=D // heads, D=D)
 
 
-def _bicubic_tables(n_in: int, n_out: int, device, align_corners: bool = True):
+def _fma32(a, b, c):
+    """fl32(a * b + c) with ONE rounding (x86 / CUDA fma), evaluated exactly with rationals."""
+    import numpy as np
+    from fractions import Fraction
+
+    exact = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+    guess = np.float32(float(exact))
+    cands = [np.nextafter(guess, np.float32(-np.inf)), guess, np.nextafter(guess, np.float32(np.inf))]
+    best = min(cands, key=lambda v: (abs(Fraction(float(v)) - exact), int(np.float32(v).view(np.uint32)) & 1))
+    return np.float32(best)
+
+
+def _bicubic_tables(n_in: int, n_out: int, device, align_corners: bool = True, aten_cpu: bool = False):
     """Per-output taps of torch's bicubic (A = -0.75) with border clamping - and their transpose.  align_corners=True:
     src = o (n_in - 1) / (n_out - 1); False: src = (o + 0.5) n_in / n_out - 0.5 (aten upsample_bicubic2d).  The source
-    index and the cubic coefficients are evaluated in fp32, operation for operation as aten does, so the tables
-    reproduce F.interpolate to the last bit of the weights."""
+    index and the cubic coefficients are evaluated in fp32, operation for operation as aten does.
+
+    ``aten_cpu``: the predict tail's reference is ``TF.resize`` on CPU tensors (Lightning moves predictions to the host,
+    src/utils/save_utils.py:74-104).  ATen's x86 CPU kernel (UpSampleKernel.cpp, built with FMA contraction) evaluates
+    ``src = fma(scale, o + 0.5, -0.5)``, ``conv1(x) = fl(fl(fma(1.25, x, -2.25) * x) * x) + 1`` and
+    ``conv2(x) = fl(fma(fma(-0.75, x, 3.75), x, -6) * x) + 3``; pinned against ``F.interpolate`` itself in
+    tests/test_oracle_resize_u8.py, these tables reproduce its weights to the last bit."""
     import numpy as np
 
     f = np.float32
@@ -121,17 +138,30 @@ def _bicubic_tables(n_in: int, n_out: int, device, align_corners: bool = True):
     idx = torch.zeros((n_out, 4), dtype=torch.int32)
     wt = torch.zeros((n_out, 4), dtype=torch.float32)
 
-    def c1(x):          # cubic_convolution1
-        return ((A + f(2)) * x - (A + f(3))) * x * x + f(1)
+    if aten_cpu:
+        def c1(x):
+            return f(f(f(_fma32(f(1.25), x, f(-2.25)) * x) * x) + f(1))
 
-    def c2(x):          # cubic_convolution2
-        return ((A * x - f(5) * A) * x + f(8) * A) * x - f(4) * A
+        def c2(x):
+            return f(f(_fma32(_fma32(A, x, f(3.75)), x, f(-6)) * x) + f(3))
+    else:
+        def c1(x):          # cubic_convolution1
+            return ((A + f(2)) * x - (A + f(3))) * x * x + f(1)
+
+        def c2(x):          # cubic_convolution2
+            return ((A * x - f(5) * A) * x + f(8) * A) * x - f(4) * A
 
     for o in range(n_out):
-        src = scale * f(o) if align_corners else scale * (f(o) + f(0.5)) - f(0.5)
+        if align_corners:
+            src = scale * f(o)
+        elif aten_cpu:
+            src = _fma32(scale, f(o) + f(0.5), f(-0.5))
+        else:
+            src = scale * (f(o) + f(0.5)) - f(0.5)
         fl = int(np.floor(src))
         t = f(src - f(fl))
-        ws = (c2(t + f(1)), c1(t), c1(f(1) - t), c2(f(2) - t))
+        t = min(max(t, f(0)), f(1))
+        ws = (c2(f(t + f(1))), c1(t), c1(f(f(1) - t)), c2(f(f(f(1) - t) + f(1))))
         for a in range(4):
             idx[o, a] = min(max(fl - 1 + a, 0), n_in - 1)
             wt[o, a] = float(ws[a])
@@ -150,9 +180,9 @@ def _bicubic_tables(n_in: int, n_out: int, device, align_corners: bool = True):
     return idx.to(device), wt.to(device), t_idx.to(device), t_w.to(device), cnt.to(device), mt
 
 
-def resample_tables(hi, wi, ho, wo, device, align_corners: bool = True):
-    iy, wy, ty, twy, cy, mty = _bicubic_tables(hi, ho, device, align_corners)
-    ix, wx, tx, twx, cx, mtx = _bicubic_tables(wi, wo, device, align_corners)
+def resample_tables(hi, wi, ho, wo, device, align_corners: bool = True, aten_cpu: bool = False):
+    iy, wy, ty, twy, cy, mty = _bicubic_tables(hi, ho, device, align_corners, aten_cpu)
+    ix, wx, tx, twx, cx, mtx = _bicubic_tables(wi, wo, device, align_corners, aten_cpu)
     mt = max(mty, mtx)
 
     def padto(t):

@@ -22,6 +22,12 @@ class GraphedTrainStep:
 
     def __init__(self, module, optimizer, example_batch: dict, warmup: int = 3) -> None:
         self.module, self.optimizer = module, optimizer
+        # a replayed graph cannot grow a Python list: every Dice metric of the module accumulates on the device instead
+        # (same value as the cat-reduced per-sample lists; metrics.Dice.streaming)
+        for name in getattr(module, "registered_metric_names", []):
+            metric = getattr(module, name, None)
+            if hasattr(metric, "streaming"):
+                metric.streaming = True
         self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
         for v in self.static.values():
             if torch.is_tensor(v) and not v.is_cuda:
@@ -75,11 +81,17 @@ class GraphedTrainStep:
         for k, v in self._staging.items():
             self.static[k].copy_(v, non_blocking=True)
         self._consumed.record()
-        self.graph.replay()
+        self._replay()
         return self.loss
+
+    def _replay(self) -> None:
+        refresh = getattr(self.optimizer, "refresh_lr", None)
+        if refresh is not None:        # a scheduler changed param_groups[i]["lr"]: update the device scalar the graph reads
+            refresh()
+        self.graph.replay()
 
     def __call__(self, batch: dict | None = None) -> torch.Tensor:
         if batch is not None:
             self.load(batch)
-        self.graph.replay()
+        self._replay()
         return self.loss

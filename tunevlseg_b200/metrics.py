@@ -75,20 +75,27 @@ class Dice(_Metric):
             raise ValueError("preds and target must have the same shape")
         return self.update_from_counts(_counts_from_probs(preds, target, self.threshold)[0])
 
+    @property
+    def has_updates(self) -> bool:
+        return bool(self._counts) or (self.streaming and int(self._n) > 0)
+
     def compute(self) -> torch.Tensor:
-        if self.streaming:
-            tot = torch.stack((self._score_sum, self._n.to(torch.float64)))
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-            return (tot[0] / tot[1]).to(torch.float32)
-        if not self._counts:
-            raise RuntimeError("Dice.compute() called before any update")
-        counts = torch.cat(self._counts)
+        """Mean of the per-sample scores over every sample seen (on all ranks).  The cross-rank reduction is a SUM of
+        (score sum, sample count): ranks may hold different numbers of samples (last validation batch not dropped,
+        image_text_mask_datamodule.py:40-47), which a fixed-shape all_gather of the count lists cannot express."""
+        tot = torch.stack((self._score_sum, self._n.to(torch.float64)))        # streaming part (graph replays)
+        if self._counts:
+            counts = torch.cat(self._counts)
+            tp, fp, fn = (counts[:, i].to(torch.float32) for i in range(3))
+            num, den = 2 * tp, 2 * tp + fp + fn
+            zero = den == 0
+            scores = torch.where(zero, torch.full_like(num, self.zero_division), num) / torch.where(zero, torch.ones_like(den), den)
+            tot = tot + torch.stack((scores.to(torch.float64).sum(), torch.tensor(float(counts.shape[0]), dtype=torch.float64, device=scores.device))).to(tot.device)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            gathered = [torch.empty_like(counts) for _ in range(dist.get_world_size())]
-            dist.all_gather(gathered, counts)           # equal per-rank batch counts (DDP with drop_last) assumed
-            counts = torch.cat(gathered)
-        return self.score(counts, self.zero_division)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        if float(tot[1]) == 0:
+            raise RuntimeError("Dice.compute() called before any update")
+        return (tot[0] / tot[1]).to(torch.float32)
 
 
 class JaccardIndex(_Metric):
@@ -103,6 +110,10 @@ class JaccardIndex(_Metric):
 
     def reset(self) -> None:
         self.confmat.zero_()
+
+    @property
+    def has_updates(self) -> bool:
+        return int(self.confmat.sum()) > 0
 
     @staticmethod
     def score(conf: torch.Tensor, zero_division: float) -> torch.Tensor:

@@ -189,17 +189,39 @@ class Projector(_Holder):
         self.txt = nn.Linear(word_dim, in_dim * kernel_size * kernel_size + 1)
 
 
-def load_checkpoint(path):
+def load_checkpoint(path, allow_unsafe_pickle: bool | None = None):
     """``torch.load(path, map_location="cpu")`` as the reference calls it (cris_model/__init__.py:66).  The reference's
-    conversion script writes with ``pickle_protocol=5`` (scripts/process_cris_checkpoint.py:22), whose framing opcodes the
-    weights-only unpickler of current torch rejects, so a file the reference itself produced would not load with the new
-    default; such files (the user's own, exactly what the reference always unpickled) are retried the reference's way."""
+    conversion script writes with ``pickle_protocol=5`` (scripts/process_cris_checkpoint.py:22), whose FRAME opcode torch's
+    weights-only unpickler rejects.  Such files are re-read with Python's own (all-protocol) unpickler **restricted to
+    torch's weights-only allow-list of globals** - tensors, storages, dtypes, ``OrderedDict`` - so a checkpoint that names
+    any other callable (the malicious case) still fails.  Full, arbitrary-code unpickling happens only on explicit
+    opt-in: ``allow_unsafe_pickle=True`` or the environment variable ``TVS_ALLOW_UNSAFE_PICKLE=1``."""
+    import os
     import pickle
+    import types
 
     try:
         return torch.load(path, map_location="cpu")
-    except pickle.UnpicklingError:
-        return torch.load(path, map_location="cpu", weights_only=False)
+    except pickle.UnpicklingError as first:
+        from torch._weights_only_unpickler import _get_allowed_globals
+
+        class _Restricted(pickle.Unpickler):
+            def find_class(self, module, name):
+                allowed = _get_allowed_globals()
+                key = f"{module}.{name}"
+                if key not in allowed:
+                    raise pickle.UnpicklingError(f"{path}: global {key} is not on the weights-only allow-list")
+                return allowed[key]
+
+        mod = types.SimpleNamespace(Unpickler=_Restricted, load=lambda f, **kw: _Restricted(f, **kw).load(), __name__="tvs_restricted_pickle")
+        try:
+            return torch.load(path, map_location="cpu", weights_only=False, pickle_module=mod)
+        except pickle.UnpicklingError:
+            if allow_unsafe_pickle is None:
+                allow_unsafe_pickle = os.environ.get("TVS_ALLOW_UNSAFE_PICKLE", "0") == "1"
+            if not allow_unsafe_pickle:
+                raise first
+            return torch.load(path, map_location="cpu", weights_only=False)
 
 
 class CRIS(nn.Module):

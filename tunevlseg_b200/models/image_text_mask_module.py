@@ -109,15 +109,39 @@ class ImageTextMaskModule(_Base):
                  logger=True, batch_size=n)
         return loss
 
+    # ---- epoch-level metric values ----------------------------------------------------------------------------------
+    # The reference logs the torchmetrics objects themselves (image_text_mask_module.py:118-125,144-148,162-170):
+    # Lightning then reports ``metric.compute()`` over the state ACCUMULATED during the epoch and resets the metric
+    # afterwards.  The metric objects here are filled by the fused kernel and are not ``torchmetrics.Metric``s, so
+    # the same semantics are spelled out: per-step batch values for the training progress bar, and at every epoch end
+    # the accumulated value is logged under the reference's key and the state is reset.
+    def _log_epoch_metrics(self, stage: str, dice_key: str, iou_key: str) -> None:
+        dice, iou = getattr(self, f"{stage}_dice", None), getattr(self, f"{stage}_iou", None)
+        if dice is None or iou is None:
+            return
+        try:       # every rank takes part in the reductions inside compute(); "no update anywhere" is decided after them
+            self.log_dict({dice_key: dice.compute(), iou_key: iou.compute()}, prog_bar=True)
+        except RuntimeError as e:
+            if "before any update" not in str(e):
+                raise
+        dice.reset()
+        iou.reset()
+
     def on_train_epoch_end(self) -> None:
-        self.log_dict({"train_dice_epoch": self.train_dice.compute(), "train_iou_epoch": self.train_iou.compute()})
+        self._log_epoch_metrics("train", "train_dice_epoch", "train_iou_epoch")
+
+    def on_validation_epoch_end(self) -> None:
+        self._log_epoch_metrics("val", "val_dice", "val_iou")
+
+    def on_test_epoch_end(self) -> None:
+        self._log_epoch_metrics("test", "test_dice", "test_iou")
 
     def validation_step(self, batch, batch_idx: int) -> None:
         want_images = self.logger is not None and (self.global_step == 0 or batch_idx == 0)
         loss, preds, targets = self.model_step(batch, materialize=want_images)
         d, i = self._update_metrics(self.val_dice, self.val_iou, preds, targets)
-        self.log_dict({"val_dice": d, "val_iou": i, "val_loss": torch.nan_to_num(loss.detach(), nan=float("inf"))},
-                      prog_bar=True, batch_size=len(batch["mask"]))
+        # val_dice / val_iou are epoch values: logged from the accumulated state in on_validation_epoch_end
+        self.log_dict({"val_loss": torch.nan_to_num(loss.detach(), nan=float("inf"))}, prog_bar=True, batch_size=len(batch["mask"]))
         if want_images and hasattr(self.logger, "log_image"):   # wandb tables/images: host-side glue, unchanged semantics
             k = self.hparams.log_image_num
             self.logger.log_image("val_pred", [p for p in preds[:k].float().cpu()])
@@ -125,8 +149,7 @@ class ImageTextMaskModule(_Base):
     def test_step(self, batch, batch_idx: int = 0) -> None:
         loss, preds, targets = self.model_step(batch)
         d, i = self._update_metrics(self.test_dice, self.test_iou, preds, targets)
-        self.log_dict({"test_dice": d, "test_iou": i, "test_loss": torch.nan_to_num(loss.detach(), nan=float("inf"))},
-                      prog_bar=True, batch_size=len(batch["mask"]))
+        self.log_dict({"test_loss": torch.nan_to_num(loss.detach(), nan=float("inf"))}, prog_bar=True, batch_size=len(batch["mask"]))
 
     def predict_step(self, batch, batch_idx: int = 0):
         logits = self.get_logits(batch)

@@ -4,7 +4,9 @@ The reference does, per sample, ``TF.resize(pred.float(), mask_shape, BICUBIC, a
 ``torchvision.utils.save_image`` (``mul(255).add(0.5).clamp(0, 255).to(uint8)``, one grey value replicated to RGB).
 Here the resize and the quantisation are ONE sm_100a kernel per sample (``tvs_resample2d_u8``: table-driven separable
 bicubic, the probabilities are read once and only the u8 image leaves the GPU - 1 byte per output pixel instead of a
-4-byte float map); PNG encoding stays on the host (PIL).
+4-byte float map); PNG encoding stays on the host (PIL).  The bytes are IDENTICAL to the reference's: weights and
+accumulation order follow ATen's CPU kernel operation for operation (``engine_cris._bicubic_tables(aten_cpu=True)``,
+``oracle/resize_u8.py``), since Lightning hands ``save_predictions`` host tensors.
 """
 from __future__ import annotations
 
@@ -23,7 +25,7 @@ def _tables(hi, wi, ho, wo, device):
     if key not in _TABLES:
         if len(_TABLES) > 256:
             _TABLES.clear()
-        _TABLES[key] = resample_tables(hi, wi, ho, wo, device, align_corners=False)
+        _TABLES[key] = resample_tables(hi, wi, ho, wo, device, align_corners=False, aten_cpu=True)
     return _TABLES[key]
 
 
