@@ -31,6 +31,10 @@ const char* tvs_last_error(void);
 int64_t tvs_launch_count(void);
 /* 0 when the current device is sm_100 and the library can run on it */
 int tvs_device_check(void);
+/* template instance chosen by the calling thread's last tvs_gemm_bf16 launch:
+ * (tile_n << 16) | (pipeline stages << 8) | (tf32 << 4) | cta_group (1 = independent CTAs, 2 = cta_group::2 pairs).
+ * Lets tests assert that the benched shapes really run the pair kernel. */
+int32_t tvs_gemm_last_variant(void);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  C[M,N] = epilogue( A[M,K] * W[N,K]^T )  on tcgen05 / TMEM, operands by TMA, fp32 accumulate.

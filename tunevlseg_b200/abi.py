@@ -60,6 +60,7 @@ def load():
         raise TvsError(f"cannot load {_LIB_PATH}: {e}") from e
     lib.tvs_last_error.restype = c_char_p
     lib.tvs_launch_count.restype = c_int64
+    lib.tvs_gemm_last_variant.restype = c_int32
     lib.tvs_dicebce_scratch_bytes.restype = c_int64
     lib.tvs_dicebce_scratch_bytes.argtypes = [c_int32, c_int64]
     lib.tvs_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
@@ -213,6 +214,12 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.reserved = 1 if round_out else 0
     g.conv_h, g.conv_w = conv_hw if conv_hw is not None else (0, 0)
     _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
+
+
+def gemm_last_variant() -> str:
+    """Template instance the calling thread's last ``gemm`` launched, e.g. ``"256x6 bf16 cta_group::2"``."""
+    v = load().tvs_gemm_last_variant()
+    return f"{v >> 16}x{(v >> 8) & 0xFF} {'tf32' if (v >> 4) & 1 else 'bf16'} cta_group::{v & 0xF}"
 
 
 def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None, round_tf32=False):
@@ -489,16 +496,47 @@ def _flops(name, args, kwargs) -> tuple[str, float]:
     return "", 0.0
 
 
+def _bytes(name, args, kwargs) -> float:
+    """Algorithmic HBM bytes of the HBM-bound kernels (each operand read / written once)."""
+    def nb(t):
+        return 0 if t is None else t.numel() * t.element_size()
+
+    if name == "layernorm_fwd":
+        return nb(args[0]) + nb(kwargs.get("y_f32")) + nb(kwargs.get("y_bf16"))
+    if name == "layernorm_bwd":
+        return nb(args[0]) + nb(args[1]) + sum(nb(kwargs.get(k)) for k in ("dx_add", "dx_f32", "dx_bf16"))
+    if name in ("dicebce_metrics_fwd", "metrics_from_probs"):
+        return nb(args[0]) + nb(args[1])
+    if name == "dicebce_bwd":
+        return nb(args[0]) + nb(args[1]) + nb(args[-1])
+    if name == "adamw_flat":
+        return 7.0 * nb(args[0])                    # p, g, m, v read; p, m, v written
+    if name in ("cast_bf16", "add_f32"):
+        return 1.5 * nb(args[0]) if name == "cast_bf16" else 3.0 * nb(args[0])
+    if name == "head_fwd":
+        return nb(args[0]) + nb(args[1]) + nb(args[-2]) + nb(args[-1])
+    if name == "head_bwd":
+        return sum(nb(a) for a in args if torch.is_tensor(a))
+    if name in ("film_fwd", "film_bwd"):
+        return sum(nb(a) for a in args if torch.is_tensor(a))
+    return 0.0
+
+
 def _wrap(fn, name):
     def op(*args, **kwargs):
         if _prof is None:
             return fn(*args, **kwargs)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # inside a stream capture the events become EVENT-RECORD NODES of the graph (cudaEventRecordExternal): every replay
+        # of that (instrumented) graph re-stamps them, which is how bench.py times kernels inside the graph itself
+        ext = torch.cuda.is_current_stream_capturing()
+        e0, e1 = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
         out = fn(*args, **kwargs)
         e1.record()
         key, fl = _flops(name, args, kwargs)
-        _prof.append((name, key, e0, e1, fl))
+        if name == "gemm":
+            key += f"|{gemm_last_variant()}"
+        _prof.append((name, key, e0, e1, fl, _bytes(name, args, kwargs)))
         return out
 
     op.__name__, op.__doc__ = fn.__name__, fn.__doc__

@@ -822,9 +822,12 @@ static int* sched_slot() {
     return base[dev] + 2 * (seq++ % SCHED_SLOTS);
 }
 
+static thread_local int g_last_variant = 0;
+
 template <int BN, int STAGES, bool TF32, int CL>
 static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES, CL>;
+    g_last_variant = (BN << 16) | (STAGES << 8) | ((TF32 ? 1 : 0) << 4) | CL;
     CUtensorMap ta, tw;
     if (int rc = make_tmap(&ta, a.A, a.M, a.conv_h ? a.K / 9 : a.K, a.lda, BM, TF32)) return rc;
     if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN / CL, TF32)) return rc;
@@ -885,6 +888,8 @@ static int pick_tile_n(int M, int N) {
 }
 
 }  // namespace tvs
+
+extern "C" __attribute__((visibility("default"))) int32_t tvs_gemm_last_variant(void) { return tvs::g_last_variant; }
 
 extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream) {
     using namespace tvs;
