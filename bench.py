@@ -408,7 +408,7 @@ def main():
     abi.set_profiler(None)
     if rank == 0:
         agg = {}
-        for name, key, a, b, fl in recs:
+        for name, key, a, b, fl, *_ in recs:
             k = f"{name}:{key}" if key else name
             t, f, c = agg.get(k, (0.0, 0.0, 0))
             agg[k] = (t + a.elapsed_time(b), f + fl, c + 1)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TVS_ABI_VERSION 1
+#define TVS_ABI_VERSION 2
 
 int tvs_version(void);
 const char* tvs_last_error(void);
@@ -54,7 +54,13 @@ int32_t tvs_gemm_last_variant(void);
  * post-ReLU activation for DRELU) - the dgrad-through-activation epilogue.
  * Requirements: K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, A and W 16-byte aligned.
  * ------------------------------------------------------------------------------------------------ */
-enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1 };
+/* operand formats.  kind::f16 MMAs take IEEE fp16 or bf16 per operand (instruction-descriptor fields), same rate:
+ * the vision tower's FORWARD operands (LayerNorm / attention / GELU outputs and the frozen weights) are fp16 - three more
+ * significand bits than bf16 cut the logit error 2.5x (tools/precision_attribution.py) - while
+ * gradients stay bf16 (range).  The 16-bit pointers below are named *_bf16 for history; their format follows these flags. */
+enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1, TVS_AB_F16 = 2 /* A, W fp16 */, TVS_AB_BF16_F16 = 3 /* A bf16, W fp16 */,
+       TVS_AB_F16_BF16 = 4 /* A fp16, W bf16 */ };
+enum { TVS_GEMM_ROUND_OUT_TF32 = 1, TVS_GEMM_OUT16_F16 = 2 };     /* tvs_gemm_args.reserved (flags) */
 enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4, TVS_ACT_RES_RELU = 5 };
 
 typedef struct tvs_gemm_args {
@@ -72,8 +78,9 @@ typedef struct tvs_gemm_args {
     int32_t ab_dtype;                      /* TVS_AB_BF16: A, W are bf16 (kind::f16).  TVS_AB_TF32: A, W are f32 and the
                                               MMA runs kind::tf32 (10-bit mantissa) - used for the small text tower and
                                               decoder, whose rounding dominates the logit error; K, lda, ldw % 4 == 0 */
-    int32_t reserved;                      /* flags; bit 0: round out_f32 to nearest tf32 (cvt.rna) - for outputs that only
-                                              feed further TVS_AB_TF32 GEMMs, whose MMA truncates its operands */
+    int32_t reserved;                      /* flags; TVS_GEMM_ROUND_OUT_TF32: round out_f32 to nearest tf32 (cvt.rna) - for outputs
+                                              that only feed further TVS_AB_TF32 GEMMs, whose MMA truncates its operands;
+                                              TVS_GEMM_OUT16_F16: out_bf16 is written as IEEE fp16 (pre_bf16 stays bf16) */
     int32_t conv_h, conv_w;                /* != 0: implicit-GEMM 3x3 convolution, stride 1, pad 1 (cris_model/layers.py:14-26,
                                               clip.py:26-27).  A = zero-bordered channels-last image [B, H+2, W+2, C] (from
                                               tvs_pad_nhwc), lda = C, M = B*(H+2)*(W+2), K = 9*C, W = [N, 9*C] with K ordered
@@ -93,9 +100,11 @@ int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);
  *      dx_out_f32 = dx (+ dx_add_f32) ; dx_out_bf16 = same, rounded.  dy is bf16 (dy_bf16) or f32 (dy_f32).
  * D % 4 == 0, D <= 2048 (2048: the CRIS decoder FFN norm, layers.py:303-309).
  * ------------------------------------------------------------------------------------------------ */
+enum { TVS_LN_ROUND_TF32 = 1, TVS_LN_Y16_F16 = 2 };
 int tvs_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t M, int32_t D,
                       float* y_f32, void* y_bf16, float* mean, float* rstd, int32_t round_tf32, void* stream);
-/* round_tf32 != 0: y_f32 is rounded to nearest tf32 - it feeds a TVS_AB_TF32 GEMM, whose MMA truncates its operands.
+/* round_tf32 (flags): bit 0 (TVS_LN_ROUND_TF32): y_f32 is rounded to nearest tf32 - it feeds a TVS_AB_TF32 GEMM, whose MMA
+ * truncates its operands; bit 1 (TVS_LN_Y16_F16): the 16-bit output y_bf16 is written as IEEE fp16.
  * (tvs_attn_fwd's out_f32 and tvs_cross_attn_fwd's out are always rounded that way: they only feed such GEMMs.) */
 int tvs_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dx_add_f32, int64_t M, int32_t D,
@@ -110,19 +119,22 @@ int tvs_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, 
  * key_mask: u8 [B,S] 1 = attend, 0 = padding, or NULL (base_multimodal_clipseg.py:212-222).
  * hd is 64 (towers) or 16 (decoder).  bwd writes dqkv (same layout as qkv); delta is f32 [B,H,S] scratch.
  * ------------------------------------------------------------------------------------------------ */
+/* flags: TVS_ATTN_O_F16 - `out` (written by fwd, read by bwd for delta = rowsum(dO o O)) is IEEE fp16 instead of bf16: it is
+ * the A operand of the out-projection GEMM (TVS_AB_F16).  tcgen05 path only (hd = 64, no masks); qkv, dout, dqkv stay bf16. */
+enum { TVS_ATTN_O_F16 = 1 };
 int tvs_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t hd, int32_t causal,
                  const uint8_t* key_mask, void* out, float* out_f32 /* optional f32 copy of out */, float* lse,
-                 void* stream);
+                 int32_t flags, void* stream);
 int tvs_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
                  int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv,
-                 void* stream);
+                 int32_t flags, void* stream);
 /* Bottom block of a prompted tower: below it only the prompt rows (the last n of every sample) still carry a gradient
  * (base_visual_learner.py:18-23 appends them last; the patch / class embeddings are frozen), so dqkv is only needed for
  * rows >= row_begin.  Rows of dqkv below the 128-row tile that contains row_begin are left untouched (hd = 64 without
  * masks); other configurations compute every row like tvs_attn_bwd. */
 int tvs_attn_bwd_tail(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S,
                       int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv,
-                      int32_t row_begin, void* stream);
+                      int32_t row_begin, int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Vision embedding pieces (hf::196-212 CLIPSegVisionEmbeddings.forward; base_multimodal_clipseg.py:449-465)
@@ -131,7 +143,7 @@ int tvs_attn_bwd_tail(const void* qkv, const void* out, const void* dout, const 
  *           (ctx_batch_stride = 0 for a shared prompt, n*D for per-sample prompts); n may be 0.
  * ------------------------------------------------------------------------------------------------ */
 int tvs_im2col_patches(const float* image, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, void* out_bf16,
-                       void* stream);
+                       int32_t out_f16 /* != 0: IEEE fp16 columns (TVS_AB_F16 patch-embedding GEMM) */, void* stream);
 int tvs_vision_assemble(const float* patches, const float* cls, const float* pos, const float* ctx,
                         int64_t ctx_batch_stride, int32_t B, int32_t G2, int32_t n, int32_t D, float* h,
                         void* stream);

@@ -39,13 +39,15 @@ def round_tf32(x, y):
 
 
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False, conv_hw=None):
-    assert A.dtype == W.dtype and A.dim() == 2 and W.dim() == 2, (A.shape, W.shape, A.dtype, W.dtype)
-    assert A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] % (8 if A.dtype == BF16 else 4) == 0
-    Ar, Wr = (A.float(), W.float()) if A.dtype == BF16 else (_tf32(A), _tf32(W))
+    H16 = (BF16, torch.float16)          # kind::f16 takes bf16 or fp16 per operand; kind::tf32 takes two fp32 operands
+    assert (A.dtype in H16 and W.dtype in H16) or (A.dtype == W.dtype == F32), (A.dtype, W.dtype)
+    assert A.dim() == 2 and W.dim() == 2, (A.shape, W.shape)
+    assert A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] % (8 if A.dtype in H16 else 4) == 0
+    Ar, Wr = (A.float(), W.float()) if A.dtype in H16 else (_tf32(A), _tf32(W))
     if conv_hw is not None:          # implicit-GEMM 3x3 conv: A = zero-bordered image [B*(H+2)*(W+2), C], W = [N, (ky, kx, c)]
         H_, W_ = conv_hw
         C, N = A.shape[1], W.shape[0]
-        assert A.is_contiguous() and W.shape[1] == 9 * C and C % (64 if A.dtype == BF16 else 32) == 0 and N % 32 == 0
+        assert A.is_contiguous() and W.shape[1] == 9 * C and C % (64 if A.dtype in H16 else 32) == 0 and N % 32 == 0
         B_ = A.shape[0] // ((H_ + 2) * (W_ + 2))
         img = Ar.view(B_, H_ + 2, W_ + 2, C)
         assert img[:, 0].abs().max() == 0 and img[:, -1].abs().max() == 0 and img[:, :, 0].abs().max() == 0 and img[:, :, -1].abs().max() == 0
@@ -119,6 +121,7 @@ def _attn_ref(qkv, B, S, H, hd, causal, key_mask):
 
 def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse, out_f32=None):
     assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.shape == (B * S, 3 * H * hd)
+    assert out.dtype == BF16 or (out.dtype == torch.float16 and hd == 64 and not causal and key_mask is None)   # TVS_ATTN_O_F16: tcgen05 path only
     o, l = _attn_ref(qkv.float(), B, S, H, hd, causal, key_mask)
     out.copy_(o)
     lse.copy_(l)

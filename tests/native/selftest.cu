@@ -285,9 +285,9 @@ static void attn_case(int B, int S, int H, int hd, int causal, bool use_mask, bo
     __nv_bfloat16* dDQKV = dev_zero<__nv_bfloat16>((size_t)B * S * 3 * E);
     float* dLse = dev_zero<float>((size_t)B * H * S);
     float* dDelta = dev_zero<float>((size_t)B * H * S);
-    TV(tvs_attn_fwd(dQKV, B, S, H, hd, causal, use_mask ? dMask : nullptr, dOut, nullptr, dLse, nullptr));
+    TV(tvs_attn_fwd(dQKV, B, S, H, hd, causal, use_mask ? dMask : nullptr, dOut, nullptr, dLse, 0, nullptr));
     CK(cudaDeviceSynchronize());
-    TV(tvs_attn_bwd(dQKV, dOut, dDO, dLse, B, S, H, hd, causal, use_mask ? dMask : nullptr, dDelta, dDQKV, nullptr));
+    TV(tvs_attn_bwd(dQKV, dOut, dDO, dLse, B, S, H, hd, causal, use_mask ? dMask : nullptr, dDelta, dDQKV, 0, nullptr));
     CK(cudaDeviceSynchronize());
     auto out = host(dOut, (size_t)B * S * E);
     auto dqkv = host(dDQKV, (size_t)B * S * 3 * E);
@@ -384,9 +384,9 @@ static void attn_timing(int B, int S, int H, int hd) {
     const int it = 10;
     for (int w = 0; w < 2; ++w) {
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < it; ++i) TV(tvs_attn_fwd(dQKV, B, S, H, hd, 0, nullptr, dOut, nullptr, dLse, nullptr));
+        for (int i = 0; i < it; ++i) TV(tvs_attn_fwd(dQKV, B, S, H, hd, 0, nullptr, dOut, nullptr, dLse, 0, nullptr));
         CK(cudaEventRecord(e1));
-        for (int i = 0; i < it; ++i) TV(tvs_attn_bwd(dQKV, dOut, dDO, dLse, B, S, H, hd, 0, nullptr, dDelta, dDQKV, nullptr));
+        for (int i = 0; i < it; ++i) TV(tvs_attn_bwd(dQKV, dOut, dDO, dLse, B, S, H, hd, 0, nullptr, dDelta, dDQKV, 0, nullptr));
         CK(cudaEventRecord(e2));
         CK(cudaEventSynchronize(e2));
     }

@@ -102,29 +102,34 @@ def test_full_geometry_at_bench_batch(case, B, with_grads):
     assert checked > 0
 
 
-# the vision tower's GEMMs at M = 32 * 489 (forward, then the dgrad chain): (name, N, K, epilogue)
+# the vision tower's GEMMs at M = 32 * 489 (forward, then the dgrad chain): (name, N, K, epilogue, operand format).
+# Forward operands are IEEE fp16 (engine.FWD16), gradients and the transposed dgrad weights bf16.
 TOWER_GEMMS = [
-    ("qkv", 2304, 768, "bias"), ("out_proj", 768, 768, "residual"), ("fc1", 3072, 768, "qgelu_pre"), ("fc2", 768, 3072, "residual"),
-    ("d_fc2", 3072, 768, "dqgelu"), ("d_fc1", 768, 3072, "plain"), ("d_out_proj", 768, 768, "plain"), ("d_qkv", 768, 2304, "plain"),
+    ("qkv", 2304, 768, "bias", "f16"), ("out_proj", 768, 768, "residual", "f16"), ("fc1", 3072, 768, "qgelu_pre", "f16"),
+    ("fc2", 768, 3072, "residual", "f16"),
+    ("d_fc2", 3072, 768, "dqgelu", "bf16"), ("d_fc1", 768, 3072, "plain", "bf16"), ("d_out_proj", 768, 768, "plain", "bf16"),
+    ("d_qkv", 768, 2304, "plain", "bf16"),
 ]
 
 
-@pytest.mark.parametrize("name,N,K,epi", TOWER_GEMMS)
+@pytest.mark.parametrize("name,N,K,epi,fmt", TOWER_GEMMS)
 @pytest.mark.parametrize("tile_n", [0, 128, 256])
-def test_tower_gemm_shapes_at_bench_rows(name, N, K, epi, tile_n):
+def test_tower_gemm_shapes_at_bench_rows(name, N, K, epi, fmt, tile_n):
     """``abi.gemm`` at M = 15 648 for the eight tower shapes x their fused epilogues against fp32 ``torch.matmul`` on the
-    same bf16-rounded operands, for the automatic tile choice and both forced widths; asserts WHICH template instance ran
+    same 16-bit-rounded operands, for the automatic tile choice and both forced widths; asserts WHICH template instance ran
     (cta_group::2 pairs for the compute-heavy shapes - the instances bench.py's roofline names)."""
     from tunevlseg_b200 import abi
 
     M = 32 * 489
+    dt = torch.float16 if fmt == "f16" else torch.bfloat16
+    ulp = 2 ** -10 if fmt == "f16" else 2 ** -7           # bound on the rounding of a 16-bit output, relative to the largest entry
     g = torch.Generator(device="cuda").manual_seed(N * 7 + K + tile_n)
-    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
-    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dt)
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(dt)
     bias = torch.randn(N, device="cuda", generator=g) * 0.1
     ref = A.float() @ W.float().t()
     kw, checks = {}, []
-    if epi == "bias":
+    if epi == "bias":                       # QKV projection: fp16 operands, q / k / v leave as bf16 (attention operands)
         out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
         kw = dict(bias=bias, out_bf16=out)
         checks = [(out, ref + bias, 2 ** -7)]
@@ -133,17 +138,17 @@ def test_tower_gemm_shapes_at_bench_rows(name, N, K, epi, tile_n):
         out = torch.empty(M, N, device="cuda")
         kw = dict(bias=bias, residual=res, out_f32=out)
         checks = [(out, ref + bias + res, 1e-3)]
-    elif epi == "qgelu_pre":
-        pre, out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"), torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    elif epi == "qgelu_pre":                # fc1: bf16 pre-activation saved for the backward, fp16 activation for fc2
+        pre, out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"), torch.empty(M, N, dtype=dt, device="cuda")
         kw = dict(bias=bias, pre_bf16=pre, out_bf16=out, act=abi.ACT_QGELU)
         u = ref + bias
-        checks = [(pre, u, 2 ** -7), (out, u * torch.sigmoid(1.702 * u), 2 ** -7)]
+        checks = [(pre, u, 2 ** -7), (out, u * torch.sigmoid(1.702 * u), max(ulp, 2 ** -9))]      # tanh.approx sigmoid: ~2^-11
     elif epi == "dqgelu":
         aux = (torch.randn(M, N, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
         out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
         kw = dict(aux_bf16=aux, out_bf16=out, act=abi.ACT_DQGELU)
-        s = torch.sigmoid(1.702 * aux.float())
-        checks = [(out, ref * (s * (1 + 1.702 * aux.float() * (1 - s))), 2 ** -7)]
+        sg = torch.sigmoid(1.702 * aux.float())
+        checks = [(out, ref * (sg * (1 + 1.702 * aux.float() * (1 - sg))), 2 ** -7)]
     else:
         out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
         kw = dict(out_bf16=out)
@@ -160,7 +165,67 @@ def test_tower_gemm_shapes_at_bench_rows(name, N, K, epi, tile_n):
     if heavy and bn >= 128:      # launch_gemm: pairs when the problem fills the machine and is compute-heavy
         assert variant.endswith("cta_group::2"), f"{name}: expected the pair kernel, got {variant}"
         assert variant.startswith(f"{bn}x"), variant
-    print(f"GEMM {name} M={M} N={N} K={K} tile_n={tile_n}: {variant}")
+    print(f"GEMM {name} M={M} N={N} K={K} {fmt} tile_n={tile_n}: {variant}")
+
+
+@pytest.mark.parametrize("a_dt,w_dt", [(torch.float16, torch.float16), (torch.bfloat16, torch.float16), (torch.float16, torch.bfloat16)])
+@pytest.mark.parametrize("M,tile_n", [(300, 0), (15648, 256)])
+def test_gemm_operand_formats(a_dt, w_dt, M, tile_n):
+    """kind::f16 takes IEEE fp16 and bf16 PER OPERAND (instruction-descriptor fields): values that bf16 cannot represent must
+    come through exactly, for both the single-CTA and the cta_group::2 instances."""
+    from tunevlseg_b200 import abi
+
+    N, K = 768, 1024
+    g = torch.Generator(device="cuda").manual_seed(M + 3)
+    # 11-bit significands: exactly representable in fp16, NOT in bf16 - a wrong format field would change the result by ~2^-9
+    A = ((torch.randint(1024, 2048, (M, K), device="cuda", generator=g).float() / 1024) * (torch.randint(0, 2, (M, K), device="cuda", generator=g) * 2 - 1)).to(a_dt)
+    W = ((torch.randint(1024, 2048, (N, K), device="cuda", generator=g).float() / 1024) * (torch.randint(0, 2, (N, K), device="cuda", generator=g) * 2 - 1) / 32).to(w_dt)
+    out = torch.empty(M, N, device="cuda")
+    abi.gemm(A, W, out_f32=out, tile_n=tile_n)
+    torch.cuda.synchronize()
+    ref = (A.double() @ W.double().t()).float()
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item() + 1e-5, f"{a_dt} x {w_dt} [{abi.gemm_last_variant()}]: {err:.3e}"
+    wrong = (A.to(torch.bfloat16).double() @ W.to(torch.bfloat16).double().t()).float()       # what a bf16 reading of fp16-exact data would give
+    if a_dt == w_dt == torch.float16:
+        assert (wrong - ref).abs().max().item() > 100 * max(err, 1e-6), "the test data does not separate the formats"
+    out16 = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    abi.gemm(A, W, out_bf16=out16)
+    torch.cuda.synchronize()
+    assert (out16.float() - ref).abs().max().item() <= 2 ** -10 * ref.abs().max().item() + 1e-4
+
+
+def test_attention_fp16_output_and_backward():
+    """TVS_ATTN_O_F16: the tcgen05 attention writes its output as fp16 (the out-projection's A operand) and the backward
+    reads it back for delta = rowsum(dO o O).  Against an fp32 torch reference on the same bf16 q / k / v."""
+    from tunevlseg_b200 import abi
+
+    B, S, H, hd = 4, 489, 12, 64
+    D = H * hd
+    g = torch.Generator(device="cuda").manual_seed(9)
+    qkv = (torch.randn(B * S, 3 * D, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
+    dout = (torch.randn(B * S, D, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    res = {}
+    for dt in (torch.float16, torch.bfloat16):
+        out, lse = torch.empty(B * S, D, dtype=dt, device="cuda"), torch.empty(B, H, S, device="cuda")
+        abi.attn_fwd(qkv, B, S, H, hd, False, None, out, lse)
+        delta, dqkv = torch.empty(B, H, S, device="cuda"), torch.empty(B * S, 3 * D, dtype=torch.bfloat16, device="cuda")
+        abi.attn_bwd(qkv, out, dout, lse, B, S, H, hd, False, None, delta, dqkv)
+        torch.cuda.synchronize()
+        res[dt] = (out.float(), dqkv.float(), delta.clone())
+    q = qkv.float().requires_grad_(True)
+    qh, kh, vh = (q[:, i * D:(i + 1) * D].reshape(B, S, H, hd).transpose(1, 2) for i in range(3))
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh).transpose(1, 2).reshape(B * S, D)
+    (gq,) = torch.autograd.grad(ref, q, dout.float())
+    e16 = (res[torch.float16][0] - ref).abs().max().item()
+    eb16 = (res[torch.bfloat16][0] - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"attention out: fp16 err {e16:.3e}, bf16 err {eb16:.3e} (scale {scale:.2f})")
+    assert e16 <= 2 ** -8 * scale and eb16 <= 2 ** -7 * scale and e16 < eb16
+    ref_delta = (dout.float() * ref).view(B, S, H, hd).sum(-1).permute(0, 2, 1)
+    for dt in res:
+        assert (res[dt][2] - ref_delta).abs().max().item() <= 2e-2 * ref_delta.abs().max().item()
+        assert ((res[dt][1] - gq).norm() / gq.norm()).item() <= 2e-2
 
 
 def test_cris_cocoop_full_geometry_at_bench_batch():

@@ -16,6 +16,8 @@ import torch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtvs_b200.so")
 
 ACT_NONE, ACT_QGELU, ACT_RELU, ACT_DQGELU, ACT_DRELU, ACT_RES_RELU = range(6)
+AB_BF16, AB_TF32, AB_F16, AB_BF16_F16, AB_F16_BF16 = range(5)
+H16 = (torch.bfloat16, torch.float16)       # 16-bit activation formats of the kind::f16 MMA (per operand)
 BLEND_NONE, BLEND_RATIO, BLEND_ADD = range(3)
 
 
@@ -68,10 +70,10 @@ def load():
     sig = {
         "tvs_layernorm_fwd": [P, P, P, F, I64, I32, P, P, P, P, I32, P],
         "tvs_layernorm_bwd": [P, P, P, P, P, P, P, I64, I32, P, P, P],
-        "tvs_attn_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, P],
-        "tvs_attn_bwd": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, P],
-        "tvs_attn_bwd_tail": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, I32, P],
-        "tvs_im2col_patches": [P, I32, I32, I32, I32, I32, P, P],
+        "tvs_attn_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, P],
+        "tvs_attn_bwd": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, I32, P],
+        "tvs_attn_bwd_tail": [P, P, P, P, I32, I32, I32, I32, I32, P, P, P, I32, I32, P],
+        "tvs_im2col_patches": [P, I32, I32, I32, I32, I32, P, I32, P],
         "tvs_vision_assemble": [P, P, P, P, I64, I32, I32, I32, I32, P, P],
         "tvs_prompt_overwrite": [P, P, I32, I32, I32, I32, I32, P, I64, P],
         "tvs_prompt_grad": [P, P, I32, I32, I32, I32, I32, P, I64, I32, P],
@@ -161,7 +163,7 @@ def _chk(t: torch.Tensor | None, dtype, name: str, dim2: bool = False) -> None:
         return
     if not t.is_cuda:
         raise TvsError(f"{name} must be a CUDA tensor")
-    if t.dtype != dtype:
+    if t.dtype != dtype and not (isinstance(dtype, tuple) and t.dtype in dtype):
         raise TvsError(f"{name} must be {dtype}, got {t.dtype}")
     if dim2:
         if t.dim() != 2 or t.stride(1) != 1:
@@ -178,11 +180,13 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     ``conv_hw=(H, W)``: implicit-GEMM 3x3 convolution - A is the zero-bordered image [B*(H+2)*(W+2), C] from ``pad_nhwc``,
     W is [N, 9*C]; outputs / residual are unpadded [B*H*W, N]."""
     require_device()
-    if A.dtype != W.dtype or A.dtype not in (torch.bfloat16, torch.float32):
-        raise TvsError(f"gemm: A and W must both be bf16 or both f32 (tf32 MMA), got {A.dtype} / {W.dtype}")
+    ab = {(torch.bfloat16, torch.bfloat16): AB_BF16, (torch.float32, torch.float32): AB_TF32, (torch.float16, torch.float16): AB_F16,
+          (torch.bfloat16, torch.float16): AB_BF16_F16, (torch.float16, torch.bfloat16): AB_F16_BF16}.get((A.dtype, W.dtype))
+    if ab is None:
+        raise TvsError(f"gemm: A and W must both be f32 (tf32 MMA) or each bf16 / fp16 (kind::f16 MMA), got {A.dtype} / {W.dtype}")
     _chk(A, A.dtype, "A", True); _chk(W, W.dtype, "W", True)
     _chk(bias, torch.float32, "bias"); _chk(residual, torch.float32, "residual", True)
-    _chk(out_f32, torch.float32, "out_f32", True); _chk(out_bf16, torch.bfloat16, "out_bf16", True)
+    _chk(out_f32, torch.float32, "out_f32", True); _chk(out_bf16, H16, "out_bf16", True)
     _chk(pre_bf16, torch.bfloat16, "pre_bf16", True); _chk(aux_bf16, torch.bfloat16, "aux_bf16", True)
     M, K = A.shape
     N, K2 = W.shape
@@ -210,8 +214,8 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.pre_bf16, g.ldpre = _p(pre_bf16), (pre_bf16.stride(0) if pre_bf16 is not None else 0)
     g.aux_bf16, g.ldaux = _p(aux_bf16), (aux_bf16.stride(0) if aux_bf16 is not None else 0)
     g.act, g.tile_n = act, tile_n
-    g.ab_dtype = 1 if A.dtype == torch.float32 else 0
-    g.reserved = 1 if round_out else 0
+    g.ab_dtype = ab
+    g.reserved = (1 if round_out else 0) | (2 if (out_bf16 is not None and out_bf16.dtype == torch.float16) else 0)
     g.conv_h, g.conv_w = conv_hw if conv_hw is not None else (0, 0)
     _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
 
@@ -225,11 +229,12 @@ def gemm_last_variant() -> str:
 def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None, round_tf32=False):
     require_device()
     _chk(x, torch.float32, "x"); _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
-    _chk(y_f32, torch.float32, "y_f32"); _chk(y_bf16, torch.bfloat16, "y_bf16")
+    _chk(y_f32, torch.float32, "y_f32"); _chk(y_bf16, H16, "y_bf16")
     D = x.shape[-1]
     M = x.numel() // D
+    flags = int(bool(round_tf32)) | (2 if (y_bf16 is not None and y_bf16.dtype == torch.float16) else 0)
     _ck(load().tvs_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, M, D, _p(y_f32), _p(y_bf16),
-                                 _p(mean), _p(rstd), int(round_tf32), _stream()), "tvs_layernorm_fwd")
+                                 _p(mean), _p(rstd), flags, _stream()), "tvs_layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, dx_add=None, dx_f32=None, dx_bf16=None):
@@ -279,31 +284,33 @@ def ffn64_bwd(x, g, w1, w2t, b1, dx):
 
 def attn_fwd(qkv, B, S, H, hd, causal, key_mask, out, lse, out_f32=None):
     require_device()
-    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(lse, torch.float32, "lse")
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, H16, "out"); _chk(lse, torch.float32, "lse")
     _chk(key_mask, torch.uint8, "key_mask"); _chk(out_f32, torch.float32, "out_f32")
     _ck(load().tvs_attn_fwd(qkv.data_ptr(), B, S, H, hd, int(causal), _p(key_mask), out.data_ptr(), _p(out_f32),
-                            lse.data_ptr(), _stream()), "tvs_attn_fwd")
+                            lse.data_ptr(), int(out.dtype == torch.float16), _stream()), "tvs_attn_fwd")
 
 
 def attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv, row_begin=0):
     """``row_begin`` > 0 (tvs_attn_bwd_tail): only rows >= row_begin of dqkv are needed; rows below the 128-row tile of
     row_begin may be left unwritten."""
     require_device()
-    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, torch.bfloat16, "out"); _chk(dout, torch.bfloat16, "dout")
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(out, H16, "out"); _chk(dout, torch.bfloat16, "dout")
     _chk(dqkv, torch.bfloat16, "dqkv"); _chk(lse, torch.float32, "lse"); _chk(delta, torch.float32, "delta")
+    flags = int(out.dtype == torch.float16)
     if row_begin:
         _ck(load().tvs_attn_bwd_tail(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, S, H, hd, int(causal),
-                                     _p(key_mask), delta.data_ptr(), dqkv.data_ptr(), int(row_begin), _stream()), "tvs_attn_bwd_tail")
+                                     _p(key_mask), delta.data_ptr(), dqkv.data_ptr(), int(row_begin), flags, _stream()), "tvs_attn_bwd_tail")
         return
     _ck(load().tvs_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, S, H, hd, int(causal),
-                            _p(key_mask), delta.data_ptr(), dqkv.data_ptr(), _stream()), "tvs_attn_bwd")
+                            _p(key_mask), delta.data_ptr(), dqkv.data_ptr(), flags, _stream()), "tvs_attn_bwd")
 
 
 def im2col_patches(image, P, out_bf16):
     require_device()
-    _chk(image, torch.float32, "image"); _chk(out_bf16, torch.bfloat16, "out")
+    _chk(image, torch.float32, "image"); _chk(out_bf16, H16, "out")
     B, C, H, W = image.shape
-    _ck(load().tvs_im2col_patches(image.data_ptr(), B, C, H, W, P, out_bf16.data_ptr(), _stream()), "tvs_im2col_patches")
+    _ck(load().tvs_im2col_patches(image.data_ptr(), B, C, H, W, P, out_bf16.data_ptr(), int(out_bf16.dtype == torch.float16), _stream()),
+        "tvs_im2col_patches")
 
 
 def vision_assemble(patches, cls, pos, ctx, B, G2, n, D, h):
@@ -474,7 +481,8 @@ def _flops(name, args, kwargs) -> tuple[str, float]:
     if name == "gemm":
         M, (N, K) = args[0].shape[0], args[1].shape
         conv = "conv3x3_" if kwargs.get("conv_hw") is not None else ""
-        return f"{conv}{M}x{N}x{K}{'_tf32' if args[0].dtype == torch.float32 else ''}", 2.0 * M * N * K
+        tag = "_tf32" if args[0].dtype == torch.float32 else ("_f16" if args[0].dtype == torch.float16 else "")
+        return f"{conv}{M}x{N}x{K}{tag}", 2.0 * M * N * K
     if name == "attn_fwd":
         _, B, S, H, hd = args[:5]
         return f"B{B}S{S}H{H}d{hd}", 4.0 * B * H * S * S * hd

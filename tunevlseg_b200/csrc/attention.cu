@@ -263,7 +263,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int H, int causal,
 // ---------------------------------------------------------------------------------------------
 template <int HD>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int S, int H,
-                                  long long rows, float* __restrict__ delta) {
+                                  long long rows, float* __restrict__ delta, int o_f16) {
     constexpr int CH = HD / 8;  // 16-byte chunks (lanes) per head
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -281,7 +281,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const _
             const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                float2 x = unpack_bf16x2(aw[i]), y = unpack_bf16x2(dw[i]);
+                float2 x = o_f16 ? unpack_f16x2(aw[i]) : unpack_bf16x2(aw[i]), y = unpack_bf16x2(dw[i]);
                 acc += x.x * y.x + x.y * y.y;
             }
         }
@@ -559,7 +559,7 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
                            const uint8_t* km, float* delta, void* dqkv, cudaStream_t st) {
     const long long rows = static_cast<long long>(B) * S;
     attn_delta_kernel<HD><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
-                                                                                  static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta);
+                                                                                  static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta, 0);
     if (int rc = check_launch("attn_delta_kernel")) return rc;
     dim3 grid((S + ATT_BM - 1) / ATT_BM, H, B);
     const __nv_bfloat16* q_ = static_cast<const __nv_bfloat16*>(qkv);
@@ -576,19 +576,21 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
 
 // tcgen05 / TMEM kernels for head dim 64 without masks (attention_sm100.cu)
 bool attn_tc_enabled();
-int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st);
+int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st, int o_f16);
 int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const float* lse, float* delta, int B, int S, int H, void* dqkv, cudaStream_t st,
-                int row_begin);
+                int row_begin, int o_f16);
 
 }  // namespace tvs
 
 extern "C" __attribute__((visibility("default"))) int tvs_attn_fwd(const void* qkv, int32_t B, int32_t S, int32_t H, int32_t hd, int32_t causal, const uint8_t* key_mask,
-                            void* out, float* out_f32, float* lse, void* stream) {
+                            void* out, float* out_f32, float* lse, int32_t flags, void* stream) {
     using namespace tvs;
     TVS_REQUIRE(qkv && out && lse, "tvs_attn_fwd: null pointer");
     TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (hd == 64 && !causal && !key_mask && attn_tc_enabled()) return attn_tc_fwd(qkv, B, S, H, out, out_f32, lse, st);
+    const int o_f16 = (flags & TVS_ATTN_O_F16) ? 1 : 0;
+    if (hd == 64 && !causal && !key_mask && attn_tc_enabled()) return attn_tc_fwd(qkv, B, S, H, out, out_f32, lse, st, o_f16);
+    TVS_REQUIRE(!o_f16, "tvs_attn_fwd: TVS_ATTN_O_F16 is implemented by the tcgen05 kernels only (hd = 64, no masks)");
     if (hd == 64) return attn_fwd_launch<64>(qkv, B, S, H, causal, key_mask, out, out_f32, lse, st);
     if (hd == 16) return attn_fwd_launch<16>(qkv, B, S, H, causal, key_mask, out, out_f32, lse, st);
     set_error("tvs_attn_fwd: head dim %d not supported (64 or 16)", hd);
@@ -596,22 +598,24 @@ extern "C" __attribute__((visibility("default"))) int tvs_attn_fwd(const void* q
 }
 
 extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd_tail(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S, int32_t H,
-                            int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv, int32_t row_begin, void* stream) {
+                            int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv, int32_t row_begin, int32_t flags, void* stream) {
     using namespace tvs;
+    const int o_f16 = (flags & TVS_ATTN_O_F16) ? 1 : 0;
     TVS_REQUIRE(row_begin >= 0 && row_begin < S, "tvs_attn_bwd_tail: row_begin %d outside [0, %d)", row_begin, S);
     TVS_REQUIRE(qkv && out && dout && lse && delta && dqkv, "tvs_attn_bwd_tail: null pointer");
     TVS_REQUIRE(B > 0 && S > 0 && H > 0, "tvs_attn_bwd_tail: bad shape B=%d S=%d H=%d", B, S, H);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (hd == 64 && !causal && !key_mask && attn_tc_enabled()) {
         static const bool fused_delta = [] { const char* e = getenv("TVS_ATTN_DELTA"); return !(e && e[0] == 'k'); }();   // TVS_ATTN_DELTA=kernel: separate pass
-        if (row_begin < 128 && fused_delta) return attn_tc_bwd(qkv, out, dout, lse, delta, B, S, H, dqkv, st, row_begin);   // delta comes out of the dQ kernel
+        if (row_begin < 128 && fused_delta) return attn_tc_bwd(qkv, out, dout, lse, delta, B, S, H, dqkv, st, row_begin, o_f16);   // delta comes out of the dQ kernel
         // tail-only backward: dK / dV of the last tile still need delta of EVERY query row
         const long long rows = static_cast<long long>(B) * S;
         attn_delta_kernel<64><<<static_cast<unsigned>((rows + 3) / 4), 128, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
-                                                                                      static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta);
+                                                                                      static_cast<const __nv_bfloat16*>(dout), S, H, rows, delta, o_f16);
         if (int rc = check_launch("attn_delta_kernel")) return rc;
-        return attn_tc_bwd(qkv, nullptr, dout, lse, delta, B, S, H, dqkv, st, row_begin);
+        return attn_tc_bwd(qkv, nullptr, dout, lse, delta, B, S, H, dqkv, st, row_begin, o_f16);
     }
+    TVS_REQUIRE(!o_f16, "tvs_attn_bwd: TVS_ATTN_O_F16 is implemented by the tcgen05 kernels only (hd = 64, no masks)");
     if (hd == 64) return attn_bwd_launch<64>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);
     if (hd == 16) return attn_bwd_launch<16>(qkv, out, dout, lse, B, S, H, causal, key_mask, delta, dqkv, st);
     set_error("tvs_attn_bwd_tail: head dim %d not supported (64 or 16)", hd);
@@ -619,6 +623,6 @@ extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd_tail(const vo
 }
 
 extern "C" __attribute__((visibility("default"))) int tvs_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int32_t B, int32_t S, int32_t H,
-                            int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv, void* stream) {
-    return tvs_attn_bwd_tail(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv, 0, stream);
+                            int32_t hd, int32_t causal, const uint8_t* key_mask, float* delta, void* dqkv, int32_t flags, void* stream) {
+    return tvs_attn_bwd_tail(qkv, out, dout, lse, B, S, H, hd, causal, key_mask, delta, dqkv, 0, flags, stream);
 }

@@ -67,8 +67,8 @@ struct AtcSmem {
     static constexpr int TOTAL = BAR + 16 * 8 + 1024;             // barriers + tmem slot + alignment slack
 };
 
-__device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float scale) {
-    // 64 fp32 accumulators (two 32-column TMEM loads) -> 64 bf16 = 128 bytes = 4 x 256-bit stores
+__device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], float scale, int f16) {
+    // 64 fp32 accumulators (two 32-column TMEM loads) -> 64 bf16 (or IEEE fp16: TVS_ATTN_O_F16) = 128 bytes = 4 x 256-bit stores
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint32_t w[8];
@@ -77,7 +77,7 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
             const int e = 16 * q + 2 * i;
             const float x0 = __uint_as_float(e < 32 ? a[e] : b[e - 32]) * scale;
             const float x1 = __uint_as_float(e + 1 < 32 ? a[e + 1] : b[e + 1 - 32]) * scale;
-            w[i] = pack_bf16x2(x0, x1);
+            w[i] = f16 ? pack_f16x2(x0, x1) : pack_bf16x2(x0, x1);
         }
         st_global_256(dst + 16 * q, w);
     }
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(MODE == MODE_FWD ? ATC_THREADS : ATC_THREADS_B
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                const __grid_constant__ CUtensorMap map_qkv_in, const __grid_constant__ CUtensorMap map_do_in, int S, int H,
                __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out,
-               const float* __restrict__ lse_in, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv, int ot0) {
+               const float* __restrict__ lse_in, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv, int ot0, int o_f16) {
     using L = AtcSmem<MODE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -343,7 +343,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             if (row_ok) {
                 const float inv = l > 0.f ? 1.0f / l : 0.f;
                 const long long tok = static_cast<long long>(b) * S + row;
-                store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv);
+                store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv, o_f16);
                 if (out32) {
                     float* f = out32 + tok * E + h * AHD;
 #pragma unroll
@@ -380,7 +380,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                         const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float2 a = unpack_bf16x2(gw[i]), bb = unpack_bf16x2(ow[i]);
+                            const float2 a = unpack_bf16x2(gw[i]), bb = o_f16 ? unpack_f16x2(ow[i]) : unpack_bf16x2(ow[i]);
                             part = fmaf(a.x, bb.x, part);
                             part = fmaf(a.y, bb.y, part);
                         }
@@ -481,7 +481,7 @@ struct FwdSmem {
 
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_in, int S, int H,
-                   __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out) {
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out, int o_f16) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* s_q = smem + FwdSmem::Q;
@@ -653,7 +653,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (row_ok) {
             const float inv = l > 0.f ? 1.0f / l : 0.f;
             const long long tok = static_cast<long long>(b) * S + row;
-            store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv);
+            store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv, o_f16);
             if (out32) {
                 float* f = out32 + tok * E + h * AHD;
 #pragma unroll
@@ -690,7 +690,7 @@ constexpr float RESCALE_LOG2 = 8.0f;
 
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_in, int S, int H,
-                    __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out) {
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out, int o_f16) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* s_q = smem + FwdSmem::Q;
@@ -866,7 +866,7 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         if (row_ok) {
             const float inv = l > 0.f ? 1.0f / l : 0.f;
             const long long tok = static_cast<long long>(b) * S + row;
-            store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv);
+            store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv, o_f16);
             if (out32) {
                 float* f = out32 + tok * E + h * AHD;
 #pragma unroll
@@ -926,7 +926,7 @@ static int make_tmap3(CUtensorMap* map, const void* ptr, int cols, int S, int B,
 template <int MODE>
 static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mqi, const CUtensorMap& mdi, int B, int S, int H,
                       __nv_bfloat16* out, float* out32, float* lse_out,
-                      const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st, int ot0 = 0) {
+                      const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st, int ot0 = 0, int o_f16 = 0) {
     using L = AtcSmem<MODE>;
     auto kern = attn_tc_kernel<MODE>;
     static bool attr_set = false;
@@ -935,7 +935,7 @@ static int launch_atc(const CUtensorMap& mq, const CUtensorMap& md, const CUtens
         attr_set = true;
     }
     dim3 grid((S + AT - 1) / AT - ot0, H, B);
-    TVS_CUDA(launch_pdl(kern, grid, dim3(MODE == MODE_FWD ? ATC_THREADS : ATC_THREADS_BWD), L::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv, ot0));
+    TVS_CUDA(launch_pdl(kern, grid, dim3(MODE == MODE_FWD ? ATC_THREADS : ATC_THREADS_BWD), L::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, out32, lse_out, lse_in, delta_in, dqkv, ot0, o_f16));
     return check_launch(MODE == MODE_FWD ? "attn_tc_kernel<fwd>" : (MODE == MODE_DQ ? "attn_tc_kernel<dq>" : "attn_tc_kernel<dkv>"));
 }
 
@@ -944,12 +944,12 @@ bool attn_tc_enabled() {
     return !off;
 }
 
-int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st) {
+int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, float* lse, cudaStream_t st, int o_f16) {
     CUtensorMap mq, mqi;
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, 64)) return rc;
     static const bool legacy = [] { const char* e = getenv("TVS_ATTN_FWD"); return e && e[0] == '1'; }();   // TVS_ATTN_FWD=1: single-buffer variant
-    if (legacy) return launch_atc<MODE_FWD>(mq, mq, mqi, mqi, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st);
+    if (legacy) return launch_atc<MODE_FWD>(mq, mq, mqi, mqi, B, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, nullptr, nullptr, nullptr, st, 0, o_f16);
     static const bool two_pass = [] { const char* e = getenv("TVS_ATTN_FWD"); return e && e[0] == '2'; }();   // TVS_ATTN_FWD=2: two-pass pipelined variant
     static bool attr_set = false;
     if (!attr_set) {
@@ -959,10 +959,10 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
     }
     dim3 grid((S + AT - 1) / AT, H, B);
     if (!two_pass) {
-        TVS_CUDA(launch_pdl(attn_tc_fwd1_kernel, grid, dim3(ATC_THREADS), FwdSmem::TOTAL, st, 1, mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse));
+        TVS_CUDA(launch_pdl(attn_tc_fwd1_kernel, grid, dim3(ATC_THREADS), FwdSmem::TOTAL, st, 1, mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, o_f16));
         return check_launch("attn_tc_fwd1_kernel");
     }
-    TVS_CUDA(launch_pdl(attn_tc_fwd_kernel, grid, dim3(ATC_THREADS), FwdSmem::TOTAL, st, 1, mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse));
+    TVS_CUDA(launch_pdl(attn_tc_fwd_kernel, grid, dim3(ATC_THREADS), FwdSmem::TOTAL, st, 1, mq, mqi, S, H, static_cast<__nv_bfloat16*>(out), out32, lse, o_f16));
     return check_launch("attn_tc_fwd_kernel");
 }
 
@@ -970,7 +970,7 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
 // row_begin > 0: dqkv is produced only for the 128-row tiles that contain rows >= row_begin (queries for dQ, keys for dK / dV)
 // out_o != nullptr (whole-sequence backward only): delta is computed by the dQ kernel from O and dO and written for the dK / dV kernel
 int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const float* lse, float* delta, int B, int S, int H, void* dqkv, cudaStream_t st,
-                int row_begin) {
+                int row_begin, int o_f16) {
     const int ot0 = row_begin / AT;
     CUtensorMap mq, md, mqi, mdi;      // 128-row boxes for the outer tiles, 64-row boxes for the inner ones
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
@@ -980,7 +980,7 @@ int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const floa
     if (out_o != nullptr && ot0 == 0) {
         // dQ first: it produces delta on the way; dK / dV (disjoint columns of dqkv) follow in the stream
         if (int rc = launch_atc<MODE_DQ>(mq, md, mqi, mdi, B, S, H, static_cast<__nv_bfloat16*>(const_cast<void*>(out_o)), delta, nullptr, lse, delta,
-                                         static_cast<__nv_bfloat16*>(dqkv), st, 0))
+                                         static_cast<__nv_bfloat16*>(dqkv), st, 0, o_f16))
             return rc;
         return launch_atc<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, nullptr, lse, delta, static_cast<__nv_bfloat16*>(dqkv), st, 0);
     }

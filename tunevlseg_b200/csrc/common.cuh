@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -82,6 +83,16 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
+}
+// IEEE fp16 pairs: the forward operands of the vision tower (11-bit significand instead of bf16's 8; the values are
+// LayerNorm outputs, attention outputs, GELU outputs and frozen weights, all far inside fp16's range)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+    __half2 t = *reinterpret_cast<__half2*>(&v);
+    return __half22float2(t);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
     __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);

@@ -17,7 +17,7 @@ static inline unsigned blocks_for(long long n, int threads, int max_blocks = 1 <
 // im2col for the stride-P patch embedding (transformers modeling_clipseg.py:141-147, :202-203)
 // out[(b*G + gy)*G + gx][c*P*P + py*P + px] = image[b][c][gy*P+py][gx*P+px]
 // ------------------------------------------------------------------------------------------------
-__global__ void im2col_kernel(const float* __restrict__ img, int B, int C, int H, int W, int P, __nv_bfloat16* __restrict__ out) {
+__global__ void im2col_kernel(const float* __restrict__ img, int B, int C, int H, int W, int P, __nv_bfloat16* __restrict__ out, int f16) {
     const int G = W / P, GH = H / P;
     const long long total4 = static_cast<long long>(B) * C * H * W / 4;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -30,7 +30,8 @@ __global__ void im2col_kernel(const float* __restrict__ img, int B, int C, int H
         const int gy = yh / P, py = yh % P, gx = xw / P, px = xw % P;   // P % 4 == 0 -> the 4 pixels stay in one patch row
         const long long row = (static_cast<long long>(b) * GH + gy) * G + gx;
         const long long col = (static_cast<long long>(c) * P + py) * P + px;
-        *reinterpret_cast<uint2*>(out + row * (static_cast<long long>(C) * P * P) + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        *reinterpret_cast<uint2*>(out + row * (static_cast<long long>(C) * P * P) + col) =
+            f16 ? make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w)) : make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
 
@@ -577,11 +578,11 @@ __global__ void counter_inc_kernel(int* c) { *c += 1; }
 
 using namespace tvs;
 
-extern "C" __attribute__((visibility("default"))) int tvs_im2col_patches(const float* image, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, void* out_bf16, void* stream) {
+extern "C" __attribute__((visibility("default"))) int tvs_im2col_patches(const float* image, int32_t B, int32_t C, int32_t H, int32_t W, int32_t P, void* out_bf16, int32_t out_f16, void* stream) {
     TVS_REQUIRE(image && out_bf16, "tvs_im2col_patches: null pointer");
     TVS_REQUIRE(P % 4 == 0 && H % P == 0 && W % P == 0, "tvs_im2col_patches: P must divide H, W and be a multiple of 4");
     const long long n4 = static_cast<long long>(B) * C * H * W / 4;
-    im2col_kernel<<<blocks_for(n4, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, B, C, H, W, P, static_cast<__nv_bfloat16*>(out_bf16));
+    im2col_kernel<<<blocks_for(n4, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, B, C, H, W, P, static_cast<__nv_bfloat16*>(out_bf16), out_f16);
     return check_launch("im2col_kernel");
 }
 

@@ -42,6 +42,8 @@ struct GemmEpilogue {
     int vec256_ok;   // 32-byte aligned rows for every operand -> direct 256-bit epilogue (the default)
     int staged;      // force the shared-memory staged (coalesced) epilogue
     int round_out;   // out_f32 is rounded to nearest tf32 (cvt.rna): it only feeds further kind::tf32 MMAs, which truncate
+    int fmt_a, fmt_b;   // kind::f16 operand formats of A and W in the instruction descriptor: 0 = IEEE fp16, 1 = bf16 (ignored by kind::tf32)
+    int out16_f16;      // the 16-bit activation output (out_bf16) is written as IEEE fp16 (11-bit significand) instead of bf16
     // implicit-GEMM 3x3 convolution (conv_wp != 0): A is a zero-bordered channels-last image [B, conv_hp, conv_wp, C] seen as
     // a [B*hp*wp, C] matrix; k-block kb belongs to tap kb / conv_kpt and loads the A rows SHIFTED by that tap's offset
     // in the flattened image (the physical zero border makes every interior pixel's 9 taps correct); the epilogue maps
@@ -138,8 +140,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major.
 // fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32, operands are fp32 in shared memory, top 19 bits used)
-__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, uint32_t fmt) {
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, uint32_t fmt_a, uint32_t fmt_b) {
+    return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -230,7 +232,9 @@ __device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, 
     if (ep.out_f32)
         *reinterpret_cast<float4*>(ep.out_f32 + row * ep.ldo32 + col) =
             ep.round_out ? make_float4(rn_tf32f(v.x), rn_tf32f(v.y), rn_tf32f(v.z), rn_tf32f(v.w)) : v;
-    if (ep.out_bf16) *reinterpret_cast<uint2*>(ep.out_bf16 + row * ep.ldo16 + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    if (ep.out_bf16)
+        *reinterpret_cast<uint2*>(ep.out_bf16 + row * ep.ldo16 + col) =
+            ep.out16_f16 ? make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w)) : make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
 // scalar, fully predicated (ragged N such as the 25-tap additive map, or unaligned leading dimensions)
@@ -241,7 +245,10 @@ __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& ep, float x,
     if (ep.residual) x += ep.residual[row * ep.ldr + c];
     if (ep.act == TVS_ACT_RES_RELU) x = fmaxf(x, 0.f);
     if (ep.out_f32) ep.out_f32[row * ep.ldo32 + c] = ep.round_out ? rn_tf32f(x) : x;
-    if (ep.out_bf16) ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
+    if (ep.out_bf16) {
+        if (ep.out16_f16) reinterpret_cast<__half*>(ep.out_bf16)[row * ep.ldo16 + c] = __float2half_rn(x);
+        else ep.out_bf16[row * ep.ldo16 + c] = __float2bfloat16(x);
+    }
 }
 
 // ---- direct epilogue: the thread keeps its TMEM row and moves 32 bytes per instruction (LDG.256 / STG.256, sm_100) ----
@@ -264,6 +271,15 @@ __device__ __forceinline__ void st_bf16_row32(__nv_bfloat16* p, const float (&v)
         uint32_t w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[16 * h + 2 * i], v[16 * h + 2 * i + 1]);
+        st256(p + 16 * h, w);
+    }
+}
+__device__ __forceinline__ void st_f16_row32(__nv_bfloat16* p, const float (&v)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack_f16x2(v[16 * h + 2 * i], v[16 * h + 2 * i + 1]);
         st256(p + 16 * h, w);
     }
 }
@@ -341,7 +357,10 @@ __device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const ui
             st256(ep.out_f32 + row * ep.ldo32 + col0 + 8 * q, o);
         }
     }
-    if (ep.out_bf16) st_bf16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
+    if (ep.out_bf16) {
+        if (ep.out16_f16) st_f16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
+        else st_bf16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
+    }
 }
 
 // one 32x32 chunk: acc = this thread's row (lane) of the chunk; stage = this warp's private staging area
@@ -647,7 +666,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp == 1) {
         if (cta_rank == 0) {
-            constexpr uint32_t idesc = umma_idesc(BM * CL, BN, TF32 ? 2u : 1u);
+            // kind::f16 takes fp16 and bf16 operands, chosen per operand by the descriptor (runtime: no extra template instances)
+            const uint32_t idesc = TF32 ? umma_idesc(BM * CL, BN, 2u, 2u) : umma_idesc(BM * CL, BN, static_cast<uint32_t>(ep.fmt_a), static_cast<uint32_t>(ep.fmt_b));
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = tiles.next(); tile >= 0; tile = tiles.next()) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -896,7 +916,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     TVS_REQUIRE(args != nullptr, "tvs_gemm_bf16: null args");
     const tvs_gemm_args& a = *args;
     TVS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "tvs_gemm_bf16: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
-    TVS_REQUIRE(a.ab_dtype == TVS_AB_BF16 || a.ab_dtype == TVS_AB_TF32, "tvs_gemm_bf16: ab_dtype must be TVS_AB_BF16 or TVS_AB_TF32");
+    TVS_REQUIRE(a.ab_dtype >= TVS_AB_BF16 && a.ab_dtype <= TVS_AB_F16_BF16, "tvs_gemm_bf16: ab_dtype must be one of the TVS_AB_* values (got %d)", a.ab_dtype);
     const int kal = a.ab_dtype == TVS_AB_TF32 ? 4 : 8;   // 16-byte rows for TMA
     TVS_REQUIRE(a.K % kal == 0 && a.lda % kal == 0 && a.ldw % kal == 0, "tvs_gemm_bf16: K, lda, ldw must be multiples of %d (K=%d lda=%lld ldw=%lld)",
                 kal, a.K, (long long)a.lda, (long long)a.ldw);
@@ -921,7 +941,10 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.aux_bf16 = static_cast<const __nv_bfloat16*>(a.aux_bf16);
     ep.ldaux = a.ldaux;
     ep.act = a.act;
-    ep.round_out = a.reserved & 1;
+    ep.round_out = a.reserved & TVS_GEMM_ROUND_OUT_TF32;
+    ep.out16_f16 = (a.reserved & TVS_GEMM_OUT16_F16) ? 1 : 0;
+    ep.fmt_a = (a.ab_dtype == TVS_AB_F16 || a.ab_dtype == TVS_AB_F16_BF16) ? 0 : 1;
+    ep.fmt_b = (a.ab_dtype == TVS_AB_F16 || a.ab_dtype == TVS_AB_BF16_F16) ? 0 : 1;
     ep.conv_wp = ep.conv_hp = ep.conv_kpt = 0;
     ep.vec_ok = vec_ok ? 1 : 0;
     auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };

@@ -62,8 +62,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
             o.w = (v[i].w - mean) * rstd * g.w + b.w;
             if (y32)
                 reinterpret_cast<float4*>(y32 + row * D)[c] =
-                    round_out ? make_float4(round_tf32_rn(o.x), round_tf32_rn(o.y), round_tf32_rn(o.z), round_tf32_rn(o.w)) : o;
-            if (y16) reinterpret_cast<uint2*>(y16 + row * D)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+                    (round_out & 1) ? make_float4(round_tf32_rn(o.x), round_tf32_rn(o.y), round_tf32_rn(o.z), round_tf32_rn(o.w)) : o;
+            if (y16) reinterpret_cast<uint2*>(y16 + row * D)[c] = (round_out & 2) ? make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w)) : make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         }
     }
 }
@@ -282,8 +282,8 @@ layernorm_fwd_wide_kernel(const float* __restrict__ x, const float* __restrict__
             o.w = (v[i].w - mean) * rstd * g.w + b.w;
             if (y32)
                 reinterpret_cast<float4*>(y32 + off)[c] =
-                    round_out ? make_float4(round_tf32_rn(o.x), round_tf32_rn(o.y), round_tf32_rn(o.z), round_tf32_rn(o.w)) : o;
-            if (y16) reinterpret_cast<uint2*>(y16 + off)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+                    (round_out & 1) ? make_float4(round_tf32_rn(o.x), round_tf32_rn(o.y), round_tf32_rn(o.z), round_tf32_rn(o.w)) : o;
+            if (y16) reinterpret_cast<uint2*>(y16 + off)[c] = (round_out & 2) ? make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w)) : make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         }
     }
 }

@@ -29,7 +29,15 @@ import torch
 from . import abi
 
 BF16 = torch.bfloat16
+F16 = torch.float16
 F32 = torch.float32
+
+# Forward operands of the vision tower (LayerNorm / attention / GELU outputs, patch columns and the frozen weights) are IEEE
+# fp16, not bf16: same tcgen05 kind::f16 rate, three more significand bits.  Measured on the device-exact CPU emulation
+# (tools/precision_attribution.py, VPT full geometry): bf16 weights and the D=768 activations were 90 % of the logit
+# error; fp16 takes the rms error from 3.2e-3 to 1.3e-3 (max over B=2: 0.0187 -> 0.0066).  Every such value is far inside
+# fp16's range (|x| < 6.5e4); gradients, whose range is the issue, stay bf16.  TVS_F16=0 restores bf16 (A/B switch).
+FWD16 = F16 if os.environ.get("TVS_F16", "1") != "0" else BF16
 
 
 def _e(shape, dtype, like):
@@ -42,6 +50,10 @@ def _bf(w: torch.Tensor) -> torch.Tensor:
 
 def _f(w: torch.Tensor) -> torch.Tensor:
     return w.detach().to(F32).contiguous()
+
+
+def _h(w: torch.Tensor, dtype) -> torch.Tensor:
+    return w.detach().to(dtype).contiguous()
 
 
 def tf32_rn(w: torch.Tensor) -> torch.Tensor:
@@ -83,8 +95,10 @@ def rn_act(a: torch.Tensor) -> torch.Tensor:
 class PackedLayer:
     """bf16 operands of one transformer block (pre- or post-LN), forward and transposed (dgrad) copies."""
 
-    def __init__(self, layer, heads: int, tf32: bool = False, attn32: bool = False):
-        """``tf32``: also keep fp32 forward operands; the block's forward GEMMs then run kind::tf32 on fp32
+    def __init__(self, layer, heads: int, tf32: bool = False, attn32: bool = False, fwd16=BF16):
+        """``fwd16``: 16-bit format of the FORWARD operands (weights here; the engine allocates LayerNorm / attention / GELU
+        outputs to match): torch.float16 for the vision tower (see FWD16), bf16 otherwise.  dgrad copies (``*_t``) are bf16.
+        ``tf32``: also keep fp32 forward operands; the block's forward GEMMs then run kind::tf32 on fp32
         activations (text tower and decoder: <3 % of the FLOPs but most of the logit rounding error).
         ``attn32`` (needs tf32, head dim 64, S <= 80): q / k / v stay fp32 and the attention runs in the short-key fp32
         kernel (tvs_cross_attn_*) - the CRIS text encoder, whose output steers a dynamic convolution."""
@@ -95,11 +109,12 @@ class PackedLayer:
         wq, bq = sa.q_proj.weight.detach() * scale, sa.q_proj.bias.detach() * scale
         wqkv = torch.cat((wq, sa.k_proj.weight.detach(), sa.v_proj.weight.detach()), dim=0)
         self.D, self.F, self.heads, self.hd = D, mlp.fc1.weight.shape[0], heads, hd
-        self.wqkv = _bf(wqkv)                                   # [3D, D]
+        self.act16 = fwd16
+        self.wqkv = _h(wqkv, fwd16)                             # [3D, D]
         self.bqkv = _f(torch.cat((bq, sa.k_proj.bias.detach(), sa.v_proj.bias.detach())))
-        self.wo, self.bo = _bf(sa.out_proj.weight), _f(sa.out_proj.bias)
-        self.w1, self.b1 = _bf(mlp.fc1.weight), _f(mlp.fc1.bias)
-        self.w2, self.b2 = _bf(mlp.fc2.weight), _f(mlp.fc2.bias)
+        self.wo, self.bo = _h(sa.out_proj.weight, fwd16), _f(sa.out_proj.bias)
+        self.w1, self.b1 = _h(mlp.fc1.weight, fwd16), _f(mlp.fc1.bias)
+        self.w2, self.b2 = _h(mlp.fc2.weight, fwd16), _f(mlp.fc2.bias)
         self.wqkv_t = _bf(wqkv.t())                             # [D, 3D]
         self.wo_t = _bf(sa.out_proj.weight.t())
         self.w1_t = _bf(mlp.fc1.weight.t())                     # [D, F]
@@ -144,12 +159,12 @@ class PackedClipSeg:
             raise abi.TvsError("use_complex_transposed_convolution=True (refined decoder) is outside the supported path")
         # vision embeddings
         emb = vm.embeddings
-        self.w_patch = _bf(emb.patch_embedding.weight.reshape(self.Dv, -1))          # [Dv, 3*P*P]
+        self.w_patch = _h(emb.patch_embedding.weight.reshape(self.Dv, -1), FWD16)    # [Dv, 3*P*P]
         self.cls = _f(emb.class_embedding)
         self.pos_v = _f(emb.position_embedding.weight)                               # [G*G+1, Dv]
         self.pre_g, self.pre_b = _f(vm.pre_layrnorm.weight), _f(vm.pre_layrnorm.bias)
         self.post_g, self.post_b = _f(vm.post_layernorm.weight), _f(vm.post_layernorm.bias)
-        self.v_layers = [PackedLayer(l, self.v_heads) for l in vm.encoder.layers]
+        self.v_layers = [PackedLayer(l, self.v_heads, fwd16=FWD16) for l in vm.encoder.layers]
         self.w_vproj = _bf(model.clip.visual_projection.weight)                      # [proj, Dv]
         # text
         self.t_layers = [PackedLayer(l, self.t_heads, tf32=True) for l in tm.encoder.layers]
@@ -209,7 +224,7 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     """Pre-LN block (modeling_clipseg.py:357-387).  x: f32 [B*S, D] -> f32 [B*S, D]."""
     M, D, F = B * S, pk.D, pk.F
     hi = pk.tf32                       # fp32 activations + kind::tf32 MMAs for the small, precision-critical towers
-    adt = F32 if hi else BF16
+    adt = F32 if hi else pk.act16      # 16-bit forward operands: fp16 in the vision tower (FWD16), q / k / v stay bf16
     ln = _e((M, D), adt, x)
     mean1, rstd1 = _e((M,), F32, x), _e((M,), F32, x)
     abi.layernorm_fwd(x, pk.g1, pk.be1, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean1, rstd=rstd1, round_tf32=hi)
@@ -224,7 +239,7 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     else:
         qkv = _e((M, 3 * D), BF16, x)
         abi.gemm(ln, pk.wqkv32 if hi else pk.wqkv, bias=pk.bqkv, out_bf16=qkv)
-        att = _e((M, D), BF16, x)
+        att = _e((M, D), BF16 if (hi or causal or key_mask is not None or pk.hd != 64) else pk.act16, x)   # fp16 out: tcgen05 kernels only
         att32 = _e((M, D), F32, x) if hi else None
         abi.attn_fwd(qkv, B, S, pk.heads, pk.hd, causal, key_mask, att, lse, out_f32=att32)
     x1 = _e((M, D), F32, x)
@@ -381,7 +396,7 @@ def _vision_embed(pk: PackedClipSeg, image, ctx0):
     G2, D = pk.grid * pk.grid, pk.Dv
     n = 0 if ctx0 is None else ctx0.shape[-2]
     S = 1 + G2 + n
-    cols = _e((B * G2, 3 * pk.patch * pk.patch), BF16, image)
+    cols = _e((B * G2, 3 * pk.patch * pk.patch), pk.w_patch.dtype, image)
     abi.im2col_patches(image.contiguous(), pk.patch, cols)
     pe = _e((B * G2, D), F32, image)
     abi.gemm(cols, pk.w_patch, out_f32=pe)
