@@ -54,12 +54,13 @@ int32_t tvs_gemm_last_variant(void);
  * post-ReLU activation for DRELU) - the dgrad-through-activation epilogue.
  * Requirements: K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, A and W 16-byte aligned.
  * ------------------------------------------------------------------------------------------------ */
-/* operand formats.  kind::f16 MMAs take IEEE fp16 or bf16 per operand (instruction-descriptor fields), same rate:
- * the vision tower's FORWARD operands (LayerNorm / attention / GELU outputs and the frozen weights) are fp16 - three more
- * significand bits than bf16 cut the logit error 2.5x (tools/precision_attribution.py) - while
- * gradients stay bf16 (range).  The 16-bit pointers below are named *_bf16 for history; their format follows these flags. */
-enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1, TVS_AB_F16 = 2 /* A, W fp16 */, TVS_AB_BF16_F16 = 3 /* A bf16, W fp16 */,
-       TVS_AB_F16_BF16 = 4 /* A fp16, W bf16 */ };
+/* operand formats.  kind::f16 MMAs take IEEE fp16 or bf16 operands at the same rate: the vision tower's FORWARD operands
+ * (LayerNorm / attention / GELU outputs and the frozen weights) are fp16 - three more significand bits than bf16 cut the
+ * logit error 2.5x (tools/precision_attribution.py) - while gradients stay bf16 (range).
+ * A and W must have the SAME format: although the instruction descriptor has one format field per operand, a B200 raises
+ * "illegal instruction" for a mixed fp16 x bf16 kind::f16 MMA (measured, round 2).
+ * The 16-bit pointers below are named *_bf16 for history; their format follows these flags. */
+enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1, TVS_AB_F16 = 2 /* A, W IEEE fp16 */ };
 enum { TVS_GEMM_ROUND_OUT_TF32 = 1, TVS_GEMM_OUT16_F16 = 2 };     /* tvs_gemm_args.reserved (flags) */
 enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4, TVS_ACT_RES_RELU = 5 };
 

@@ -39,8 +39,8 @@ def round_tf32(x, y):
 
 
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False, conv_hw=None):
-    H16 = (BF16, torch.float16)          # kind::f16 takes bf16 or fp16 per operand; kind::tf32 takes two fp32 operands
-    assert (A.dtype in H16 and W.dtype in H16) or (A.dtype == W.dtype == F32), (A.dtype, W.dtype)
+    H16 = (BF16, torch.float16)          # kind::f16 takes two bf16 or two fp16 operands (mixing is illegal on sm_100); kind::tf32 two fp32
+    assert A.dtype == W.dtype and A.dtype in (BF16, torch.float16, F32), (A.dtype, W.dtype)
     assert A.dim() == 2 and W.dim() == 2, (A.shape, W.shape)
     assert A.stride(1) == 1 and W.stride(1) == 1 and A.shape[1] % (8 if A.dtype in H16 else 4) == 0
     Ar, Wr = (A.float(), W.float()) if A.dtype in H16 else (_tf32(A), _tf32(W))

@@ -65,4 +65,24 @@ def test_reference_arm_under_torchrun_world2():
     assert len(lines) == 1, res.stdout
     rec = json.loads(lines[0])
     assert rec["impl"] == "reference" and rec["n_gpus"] == 2 and rec["value"] > 0
-    assert rec["cpu_baseline"]["kind"] == "port" and rec["e2e"]["h2d_bytes_per_step"] == 0
+    # "reference+shim": the reference's own MapleCLIPSeg (from /root/reference here, from its byte-compiled build oracle/_ref
+    # on the GPU box); "port": the oracle, when neither is importable
+    assert rec["cpu_baseline"]["kind"] in ("reference+shim", "port") and rec["e2e"]["h2d_bytes_per_step"] == 0
+    assert rec["config"]["workload"].startswith("CLIPSeg ViT-B/16 + MaPLe") and "batch 32/GPU" in rec["config"]["workload"]
+
+
+def test_reference_arm_runs_from_the_byte_compiled_build():
+    """oracle/build_ref.py byte-compiles the reference into oracle/_ref (what travels to the GPU box, where /root/reference
+    does not exist): the reference arm must import the reference's classes from there."""
+    import pytest
+
+    from oracle import build_ref
+
+    if build_ref.build() is None and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "src")):
+        pytest.skip("no /root/reference and no prebuilt oracle/_ref")
+    env = dict(os.environ, TVS_REF_FORCE_BUILT="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-batch", "1"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    rec = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][0])
+    assert rec["cpu_baseline"]["kind"] == "reference+shim", res.stderr[-1500:]

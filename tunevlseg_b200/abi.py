@@ -16,7 +16,7 @@ import torch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtvs_b200.so")
 
 ACT_NONE, ACT_QGELU, ACT_RELU, ACT_DQGELU, ACT_DRELU, ACT_RES_RELU = range(6)
-AB_BF16, AB_TF32, AB_F16, AB_BF16_F16, AB_F16_BF16 = range(5)
+AB_BF16, AB_TF32, AB_F16 = range(3)
 H16 = (torch.bfloat16, torch.float16)       # 16-bit activation formats of the kind::f16 MMA (per operand)
 BLEND_NONE, BLEND_RATIO, BLEND_ADD = range(3)
 
@@ -180,10 +180,9 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     ``conv_hw=(H, W)``: implicit-GEMM 3x3 convolution - A is the zero-bordered image [B*(H+2)*(W+2), C] from ``pad_nhwc``,
     W is [N, 9*C]; outputs / residual are unpadded [B*H*W, N]."""
     require_device()
-    ab = {(torch.bfloat16, torch.bfloat16): AB_BF16, (torch.float32, torch.float32): AB_TF32, (torch.float16, torch.float16): AB_F16,
-          (torch.bfloat16, torch.float16): AB_BF16_F16, (torch.float16, torch.bfloat16): AB_F16_BF16}.get((A.dtype, W.dtype))
-    if ab is None:
-        raise TvsError(f"gemm: A and W must both be f32 (tf32 MMA) or each bf16 / fp16 (kind::f16 MMA), got {A.dtype} / {W.dtype}")
+    ab = {(torch.bfloat16, torch.bfloat16): AB_BF16, (torch.float32, torch.float32): AB_TF32, (torch.float16, torch.float16): AB_F16}.get((A.dtype, W.dtype))
+    if ab is None:      # a mixed fp16 x bf16 kind::f16 MMA is an illegal instruction on sm_100 (measured)
+        raise TvsError(f"gemm: A and W must both be f32 (tf32 MMA), both bf16 or both fp16 (kind::f16 MMA), got {A.dtype} / {W.dtype}")
     _chk(A, A.dtype, "A", True); _chk(W, W.dtype, "W", True)
     _chk(bias, torch.float32, "bias"); _chk(residual, torch.float32, "residual", True)
     _chk(out_f32, torch.float32, "out_f32", True); _chk(out_bf16, H16, "out_bf16", True)

@@ -916,7 +916,8 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     TVS_REQUIRE(args != nullptr, "tvs_gemm_bf16: null args");
     const tvs_gemm_args& a = *args;
     TVS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "tvs_gemm_bf16: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
-    TVS_REQUIRE(a.ab_dtype >= TVS_AB_BF16 && a.ab_dtype <= TVS_AB_F16_BF16, "tvs_gemm_bf16: ab_dtype must be one of the TVS_AB_* values (got %d)", a.ab_dtype);
+    TVS_REQUIRE(a.ab_dtype == TVS_AB_BF16 || a.ab_dtype == TVS_AB_TF32 || a.ab_dtype == TVS_AB_F16,
+                "tvs_gemm_bf16: ab_dtype must be TVS_AB_BF16, TVS_AB_TF32 or TVS_AB_F16 (got %d; mixed fp16 x bf16 operands are illegal on sm_100)", a.ab_dtype);
     const int kal = a.ab_dtype == TVS_AB_TF32 ? 4 : 8;   // 16-byte rows for TMA
     TVS_REQUIRE(a.K % kal == 0 && a.lda % kal == 0 && a.ldw % kal == 0, "tvs_gemm_bf16: K, lda, ldw must be multiples of %d (K=%d lda=%lld ldw=%lld)",
                 kal, a.K, (long long)a.lda, (long long)a.ldw);
@@ -943,8 +944,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.act = a.act;
     ep.round_out = a.reserved & TVS_GEMM_ROUND_OUT_TF32;
     ep.out16_f16 = (a.reserved & TVS_GEMM_OUT16_F16) ? 1 : 0;
-    ep.fmt_a = (a.ab_dtype == TVS_AB_F16 || a.ab_dtype == TVS_AB_F16_BF16) ? 0 : 1;
-    ep.fmt_b = (a.ab_dtype == TVS_AB_F16 || a.ab_dtype == TVS_AB_BF16_F16) ? 0 : 1;
+    ep.fmt_a = ep.fmt_b = a.ab_dtype == TVS_AB_F16 ? 0 : 1;
     ep.conv_wp = ep.conv_hp = ep.conv_kpt = 0;
     ep.vec_ok = vec_ok ? 1 : 0;
     auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
