@@ -32,7 +32,8 @@ int64_t tvs_launch_count(void);
 /* 0 when the current device is sm_100 and the library can run on it */
 int tvs_device_check(void);
 /* template instance chosen by the calling thread's last tvs_gemm_bf16 launch:
- * (tile_n << 16) | (pipeline stages << 8) | (tf32 << 4) | cta_group (1 = independent CTAs, 2 = cta_group::2 pairs).
+ * (tile_n << 16) | (pipeline stages << 8) | (epilogue << 5) | (tf32 << 4) | cta_group (1 = independent CTAs, 2 = cta_group::2
+ * pairs); epilogue: 0 = generic (runtime flags), 1-4 = the straight-line epilogues of the hot tower shapes (gemm_sm100.cu).
  * Lets tests assert that the benched shapes really run the pair kernel. */
 int32_t tvs_gemm_last_variant(void);
 

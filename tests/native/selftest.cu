@@ -4,6 +4,7 @@
 //     tests/native/selftest [gemm|attn|ln|loss|all]
 // Exit code 0 = all selected cases pass.  A watchdog (alarm) aborts a hung kernel after 180 s.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <signal.h>
@@ -100,7 +101,7 @@ __global__ void ref_gemm_kernel(const __nv_bfloat16* A, const __nv_bfloat16* W, 
     out[(size_t)m * N + n] = acc;
 }
 
-static void gemm_case(int M, int N, int K, int act, bool use_bias, bool use_res, bool out32, bool out16, bool pre, int tile_n, bool timeit = false) {
+static void gemm_case(int M, int N, int K, int act, bool use_bias, bool use_res, bool out32, bool out16, bool pre, int tile_n, bool timeit = false, bool f16out = false) {
     std::vector<float> a((size_t)M * K), w((size_t)N * K), bias(N), res((size_t)M * N), aux((size_t)M * N);
     for (auto& x : a) x = frand();
     for (auto& x : w) x = frand(1.f / sqrtf((float)K));
@@ -127,6 +128,7 @@ static void gemm_case(int M, int N, int K, int act, bool use_bias, bool use_res,
     g.pre_bf16 = pre ? dPre : nullptr; g.ldpre = N;
     g.aux_bf16 = deriv ? dAux : nullptr; g.ldaux = N;
     g.act = act; g.tile_n = tile_n;
+    if (f16out) g.reserved |= TVS_GEMM_OUT16_F16;        // the 16-bit activation output as IEEE fp16 (fc1 of the vision tower)
     TV(tvs_gemm_bf16(&g, nullptr));
     CK(cudaDeviceSynchronize());
     dim3 grid((N + 127) / 128, M);
@@ -146,9 +148,10 @@ static void gemm_case(int M, int N, int K, int act, bool use_bias, bool use_res,
     if (out16) {
         auto o = host(dOut16, (size_t)M * N);
         double err = 0;
-        for (size_t i = 0; i < o.size(); ++i) err = std::max(err, (double)fabsf(bf(o[i]) - ref[i]));
-        snprintf(name, sizeof name, "gemm M=%d N=%d K=%d act=%d b=%d r=%d bn=%d bf16", M, N, K, act, use_bias, use_res, tile_n);
-        report(name, err / std::max(1.0, scale), 1e-2);
+        for (size_t i = 0; i < o.size(); ++i)
+            err = std::max(err, (double)fabsf((f16out ? __half2float(*reinterpret_cast<const __half*>(&o[i])) : bf(o[i])) - ref[i]));
+        snprintf(name, sizeof name, "gemm M=%d N=%d K=%d act=%d b=%d r=%d bn=%d %s", M, N, K, act, use_bias, use_res, tile_n, f16out ? "fp16" : "bf16");
+        report(name, err / std::max(1.0, scale), f16out ? 2e-3 : 1e-2);
     }
     if (pre) {
         auto o = host(dPre, (size_t)M * N);
@@ -209,6 +212,7 @@ static void test_gemm_step_shapes() {
     STEP_CASE(gemm_case(15648, 2304, 768, TVS_ACT_NONE, true, false, false, true, false, 0));
     STEP_CASE(gemm_case(15648, 768, 768, TVS_ACT_NONE, true, true, true, false, false, 0));
     STEP_CASE(gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, 0));
+    STEP_CASE(gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, 0, false, true));      // fp16 activation out (EPI_FC1)
     STEP_CASE(gemm_case(15648, 768, 3072, TVS_ACT_NONE, true, true, true, false, false, 0));
     STEP_CASE(gemm_case(15648, 3072, 768, TVS_ACT_DQGELU, false, false, false, true, false, 0));
     STEP_CASE(gemm_case(15648, 768, 3072, TVS_ACT_NONE, false, false, false, true, false, 0));
@@ -683,12 +687,18 @@ int main(int argc, char** argv) {
         gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, false, bn, true);
         printf("-- N=3072: gelu + pre (fc1 forward)\n");
         gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, bn, true);
+        printf("-- N=3072: gelu + pre, fp16 activation out (fc1 forward as the engine runs it)\n");
+        gemm_case(15648, 3072, 768, TVS_ACT_QGELU, true, false, false, true, true, bn, true, true);
         printf("-- N=3072: dgelu (aux read, one store)\n");
         gemm_case(15648, 3072, 768, TVS_ACT_DQGELU, false, false, false, true, false, bn, true);
         printf("-- N=768 K=768: residual f32 in/out\n");
         gemm_case(15648, 768, 768, TVS_ACT_NONE, true, true, true, false, false, 128, true);
         printf("-- N=768 K=768: bf16 out only\n");
         gemm_case(15648, 768, 768, TVS_ACT_NONE, true, false, false, true, false, 128, true);
+        printf("-- N=768 K=3072: residual f32 in/out (fc2 forward)\n");
+        gemm_case(15648, 768, 3072, TVS_ACT_NONE, true, true, true, false, false, 128, true);
+        printf("-- N=2304 K=768: bias, bf16 out (QKV)\n");
+        gemm_case(15648, 2304, 768, TVS_ACT_NONE, true, false, false, true, false, 128, true);
     }
     printf("launches: %lld\n", (long long)tvs_launch_count());
     printf(g_fail ? "SELFTEST FAILED (%d cases)\n" : "SELFTEST PASSED\n", g_fail);

@@ -65,7 +65,7 @@ def test_full_geometry_at_bench_batch(case, B, with_grads):
     M = B * (1 + (spec.image_size // spec.patch_size) ** 2 + st.num_context)
     pair = {v for v in used if v.startswith(f"{M}x") and v.endswith("cta_group::2")}
     print(f"GEMM variants at M={M}: {sorted(v for v in used if v.startswith(f'{M}x'))}")
-    assert any("|256x6 bf16 cta_group::2" in v for v in pair) and any("|128x8 bf16 cta_group::2" in v for v in pair), \
+    assert any("|256x6 bf16" in v for v in pair) and any("|128x8 bf16" in v for v in pair), \
         f"the benched pair-GEMM instances did not run: {sorted(used)}"
 
     ref_chunks, ref_loss = [], 0.0

@@ -222,7 +222,8 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
 def gemm_last_variant() -> str:
     """Template instance the calling thread's last ``gemm`` launched, e.g. ``"256x6 bf16 cta_group::2"``."""
     v = load().tvs_gemm_last_variant()
-    return f"{v >> 16}x{(v >> 8) & 0xFF} {'tf32' if (v >> 4) & 1 else 'bf16'} cta_group::{v & 0xF}"
+    epi = ("generic", "out_bf16", "res_f32", "fc1", "dqgelu")[(v >> 5) & 7]
+    return f"{v >> 16}x{(v >> 8) & 0xFF} {'tf32' if (v >> 4) & 1 else 'bf16'} epi:{epi} cta_group::{v & 0xF}"
 
 
 def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None, round_tf32=False):

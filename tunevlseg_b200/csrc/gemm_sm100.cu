@@ -363,6 +363,55 @@ __device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const ui
     }
 }
 
+// ---- specialised epilogues (template parameter EPI of the kernel) -------------------------------------------------------
+// The generic epilogue above decides everything from runtime flags; on a kernel of ~8 000 SASS instructions the compiler's
+// unswitching of those flags is fragile (measured in round 2: adding two cold-path branches re-rolled the dGELU path into
+// four branches PER ELEMENT, 93 -> 167 us, and cost the plain bf16 epilogue 8 %).  The shapes that carry the step get
+// straight-line epilogues with no flag tests at all; everything else (ragged N, convolutions, tf32, rare flag sets) keeps the
+// generic code.  All of them require: 32-byte aligned rows (vec256_ok), N % 32 == 0.
+enum { EPI_GENERIC = 0, EPI_OUT_BF16 = 1 /* (+bias) -> bf16 */, EPI_RES_F32 = 2 /* (+bias) + residual -> f32 */,
+       EPI_FC1 = 3 /* + bias -> bf16 pre-activation; QuickGELU -> fp16 */, EPI_DQGELU = 4 /* * QuickGELU'(aux bf16) -> bf16 */ };
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0, const uint32_t (&ext)[32]) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    if (EPI != EPI_DQGELU && ep.bias) {        // kernel-uniform
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t b[8];
+            ld256(ep.bias + col0 + 8 * q, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * q + i] += __uint_as_float(b[i]);
+        }
+    }
+    if (EPI == EPI_OUT_BF16) {
+        st_bf16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
+    } else if (EPI == EPI_RES_F32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(v[8 * q + i] + __uint_as_float(ext[8 * q + i]));
+            st256(ep.out_f32 + row * ep.ldo32 + col0 + 8 * q, o);
+        }
+    } else if (EPI == EPI_FC1) {
+        st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+        st_f16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
+    } else if (EPI == EPI_DQGELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float2 u = unpack_bf16x2(ext[i]);
+            v[2 * i] *= quick_gelu_grad(u.x);
+            v[2 * i + 1] *= quick_gelu_grad(u.y);
+        }
+        st_bf16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
+    }
+}
+
 // one 32x32 chunk: acc = this thread's row (lane) of the chunk; stage = this warp's private staging area
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&acc)[32], float* stage, long long row0, int col0,
                                                int M, int N, int lane) {
@@ -532,7 +581,7 @@ struct TileIter {
     }
 };
 
-template <int BN, int STAGES, bool TF32, int CL>
+template <int BN, int STAGES, bool TF32, int CL, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
                          int N, int K, GemmEpilogue ep, int* __restrict__ sched) {
@@ -736,6 +785,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const bool extras = direct && row_ok && (ep.residual != nullptr || is_dact(ep.act));
             // a group takes PAIRS of adjacent chunks (64 columns): for the bf16 arrays a thread then reads / writes whole
             // 128-byte lines within a few hundred cycles instead of a quarter of a line per visit
+            if (EPI != EPI_GENERIC) {
+                // straight-line epilogue of a hot shape (host guarantees vec256_ok, N % 32 == 0, no convolution)
+#pragma unroll 1
+                for (int cc = grp * 2; cc < BN / 32; cc += (cc & 1) ? 3 : 1) {
+                    const int col0 = n_blk * BN + cc * 32;
+                    if (row0 >= M || col0 >= N) break;
+                    uint32_t r[32], ext[32];
+                    tmem_ld_32x32(t_row + cc * 32, r);
+                    if (row_ok) {        // operands of this chunk in flight together with the TMEM load
+                        if (EPI == EPI_DQGELU) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t a8[8];
+                                ld256(ep.aux_bf16 + orow * ep.ldaux + col0 + 16 * h, a8);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) ext[8 * h + i] = a8[i];
+                            }
+                        } else if (EPI == EPI_RES_F32) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t r8[8];
+                                ld256(ep.residual + orow * ep.ldr + col0 + 8 * q, r8);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) ext[8 * q + i] = r8[i];
+                            }
+                        }
+                    }
+                    tmem_ld_wait();
+                    if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext);
+                }
+            } else {
 #pragma unroll 1
             for (int cc = grp * 2; cc < BN / 32; cc += (cc & 1) ? 3 : 1) {
                 const int c = cc;
@@ -768,6 +848,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
                 }
             }
+            }   // EPI_GENERIC
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -843,15 +924,14 @@ static int* sched_slot() {
 }
 
 static thread_local int g_last_variant = 0;
-
-template <int BN, int STAGES, bool TF32, int CL>
-static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
+template <int BN, int STAGES, bool TF32, int CL, int EPI>
+static int launch_gemm_inst(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
     using L = GemmSmem<BN, STAGES, CL>;
-    g_last_variant = (BN << 16) | (STAGES << 8) | ((TF32 ? 1 : 0) << 4) | CL;
+    g_last_variant = (BN << 16) | (STAGES << 8) | (EPI << 5) | ((TF32 ? 1 : 0) << 4) | CL;
     CUtensorMap ta, tw;
     if (int rc = make_tmap(&ta, a.A, a.M, a.conv_h ? a.K / 9 : a.K, a.lda, BM, TF32)) return rc;
     if (int rc = make_tmap(&tw, a.W, a.N, a.K, a.ldw, BN / CL, TF32)) return rc;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, TF32, CL>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, TF32, CL, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -873,6 +953,32 @@ static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaSt
     if (sched && mode == 'm') TVS_CUDA(cudaMemsetAsync(sched, 0, 2 * sizeof(int), stream));
     TVS_CUDA(launch_pdl(kern, dim3(launch_clusters * CL), dim3(GEMM_THREADS), L::TOTAL, stream, CL, ta, tw, a.M, a.N, a.K, ep, sched));
     return check_launch("gemm_bf16_tcgen05_kernel");
+}
+
+// Which straight-line epilogue (if any) covers this call.  TVS_GEMM_EPI=generic forces the runtime-flag epilogue (A/B switch).
+static int pick_epi(const tvs_gemm_args& a, const GemmEpilogue& ep, bool tf32) {
+    static const bool generic_only = [] { const char* e = getenv("TVS_GEMM_EPI"); return e && e[0] == 'g'; }();
+    if (generic_only || tf32 || a.conv_h || !ep.vec256_ok || ep.staged || a.N % 32 != 0 || ep.round_out) return EPI_GENERIC;
+    const bool o16 = ep.out_bf16 != nullptr, o32 = ep.out_f32 != nullptr, res = ep.residual != nullptr, pre = ep.pre_bf16 != nullptr;
+    if (ep.act == TVS_ACT_NONE && o16 && !ep.out16_f16 && !o32 && !res && !pre) return EPI_OUT_BF16;
+    if (ep.act == TVS_ACT_NONE && o32 && res && !o16 && !pre) return EPI_RES_F32;
+    if (ep.act == TVS_ACT_QGELU && o16 && ep.out16_f16 && pre && !o32 && !res) return EPI_FC1;
+    if (ep.act == TVS_ACT_DQGELU && o16 && !ep.out16_f16 && !o32 && !res && !pre && !ep.bias) return EPI_DQGELU;
+    return EPI_GENERIC;
+}
+
+template <int BN, int STAGES, bool TF32, int CL>
+static int launch_gemm_cl(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
+    if constexpr (!TF32 && BN >= 128) {       // the instances the vision tower runs at M = B * S: specialised epilogues
+        switch (pick_epi(a, ep, TF32)) {
+            case EPI_OUT_BF16: return launch_gemm_inst<BN, STAGES, TF32, CL, EPI_OUT_BF16>(a, ep, stream);
+            case EPI_RES_F32: return launch_gemm_inst<BN, STAGES, TF32, CL, EPI_RES_F32>(a, ep, stream);
+            case EPI_FC1: return launch_gemm_inst<BN, STAGES, TF32, CL, EPI_FC1>(a, ep, stream);
+            case EPI_DQGELU: return launch_gemm_inst<BN, STAGES, TF32, CL, EPI_DQGELU>(a, ep, stream);
+            default: break;
+        }
+    }
+    return launch_gemm_inst<BN, STAGES, TF32, CL, EPI_GENERIC>(a, ep, stream);
 }
 
 // CTA pairs pay off when the GEMM fills the machine; tiny problems keep independent CTAs
