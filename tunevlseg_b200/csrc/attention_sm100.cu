@@ -702,7 +702,8 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint64_t* s_full = bars + 9;        // [2]
     uint64_t* ew_done = bars + 11;      // [2]
     uint64_t* o_done = bars + 13;       // one phase per P V
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* acc_full = bars + 14;     // completes once, with the LAST P V
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int ot = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int E = H * AHD;
@@ -724,6 +725,7 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             mbar_init(&ew_done[s], 128);
         }
         mbar_init(o_done, 1);
+        mbar_init(acc_full, 1);
         fence_barrier_init();
     }
     if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -768,6 +770,7 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     umma_ts(tb + C_O, tb + 64 * bfj + 8 * k, bv + 128 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&in_empty[stg]);
                 umma_commit(o_done);
+                if (j == n_it - 1) umma_commit(acc_full);
             }
             __syncwarp();
         };
@@ -857,7 +860,12 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             tc_fence_before();
             mbar_arrive(&ew_done[bf]);
         }
-        mbar_wait(o_done, (n_it - 1) & 1);
+        // NOT o_done: a parity wait cannot tell phase n_it - 1 from phase n_it - 3.  When this warp leaves the loop only P V of
+        // step n_it - 3 is known to have completed (it precedes the last Q K^T in the MMA stream); if P V (n_it - 2) is still in
+        // flight, o_done's CURRENT parity differs from (n_it - 1) & 1 and the wait falls through - O was then read two
+        // accumulations early (round 2: non-reproducible CRIS decoder attention, S = 676, one run in ~5).  acc_full
+        // completes exactly once, with the last P V.
+        mbar_wait(acc_full, 0);
         tc_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld32(tl + C_O, o0);
