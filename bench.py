@@ -403,7 +403,7 @@ def summarise_kernels(recs):
     """recs: (name, key, e0, e1, flops, bytes) per op of ONE step (the events are re-stamped by every replay of an instrumented
     graph) -> {kernel: (total_ms, flops, bytes, launches)} of that step."""
     agg = {}
-    for name, key, a, b, fl, by in recs:
+    for name, key, a, b, fl, by, *_ in recs:
         k = f"{name}:{key}" if key else name
         t, f, y, c = agg.get(k, (0.0, 0.0, 0.0, 0))
         agg[k] = (t + a.elapsed_time(b), f + fl, y + by, c + 1)
@@ -443,9 +443,30 @@ def rooflines(agg_runs, timing):
                 e["traffic_source"] = tj[k].get("source")
         return e
 
-    t_k = next((kv for kv in top if kv[1][1] > 0), None)
+    # the dominant TENSOR kernel is a kernel INSTANCE (template instantiation): the GEMM launches of one instance are pooled
+    # over their shapes and epilogues - summed algorithmic FLOPs over summed duration
+    inst = {}
+    for k, (t, f, y, c) in mean.items():
+        if f <= 0:
+            continue
+        name, _, key = k.partition(":")
+        ik, label = k, key
+        if name == "gemm" and "|" in key:          # key = "<M>x<N>x<K>[_fmt]|<tile>x<stages> <kind> epi:<epilogue> cta_group::<n>"
+            shape, variant = key.split("|")
+            tile_kind, _, rest = variant.partition(" epi:")
+            epi, _, cta = rest.partition(" ")
+            ik, label = f"gemm_bf16_tcgen05_kernel<{tile_kind} {cta}>", f"{shape} {epi}"
+        tt, ff, yy, cc, shapes = inst.get(ik, (0.0, 0.0, 0.0, 0, []))
+        inst[ik] = (tt + t, ff + f, yy + y, cc + c, shapes + [(label, c, round(1e3 * t / c, 1), round(f / (t * 1e-3) / 1e12, 1))])
+    t_k = max(inst.items(), key=lambda kv: kv[1][0]) if inst else None
     h_k = next((kv for kv in top if kv[1][2] > 0 and kv[1][1] == 0), None)
-    out["tensor"] = entry(*t_k, True) if t_k else None
+    out["tensor"] = None
+    if t_k:
+        e = entry(t_k[0], t_k[1][:4], True)
+        e["family_share_of_kernel_time"] = round(sum(v[0] for kk, v in inst.items() if kk.split("<")[0] == t_k[0].split("<")[0]) / total, 3)
+        if t_k[0].startswith("gemm_bf16_tcgen05_kernel<"):
+            e["launches"] = [{"shape_epilogue": sh, "n": n, "avg_us": us, "tflops": tf} for sh, n, us, tf in sorted(t_k[1][4], key=lambda r: -r[1] * r[2])]
+        out["tensor"] = e
     out["hbm"] = entry(*h_k, False) if h_k else None
     return out
 
@@ -533,10 +554,25 @@ def run_train_workload(ctx: Ctx, name: str, steps: int, warmup: int, headline: b
         for _ in range(2):
             probe()
         torch.cuda.synchronize()
+        t_probe = []
         for _ in range(reps):
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
             probe()
+            p1.record()
             torch.cuda.synchronize()
+            t_probe.append(p0.elapsed_time(p1))
             runs.append(summarise_kernels(recs))
+        probe_ms = statistics.mean(t_probe)
+        timing += "; the instrumented replay takes %.3f ms against %.3f ms for the plain graph" % (probe_ms, ms_step)
+        if rank == 0 and headline and args.timeline:
+            base = min(recs, key=lambda r: recs[0][2].elapsed_time(r[2]))[2]
+            streams = {}
+            with open(args.timeline, "w") as fh:
+                fh.write("idx,stream,name,key,start_us,end_us\n")
+                for i, (nm, key, a, b, *_rest) in enumerate(recs):
+                    sid = streams.setdefault(_rest[2] if len(_rest) > 2 else 0, len(streams))
+                    fh.write(f"{i},{sid},{nm},{key},{1e3 * base.elapsed_time(a):.1f},{1e3 * base.elapsed_time(b):.1f}\n")
         probe.graph.reset()
         del probe
     except Exception as e:  # noqa: BLE001 - fall back to one eager pass behind a device-side spin
@@ -668,6 +704,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="measure only the headline workload")
     ap.add_argument("--profile-kernels", action="store_true", help="also print the per-kernel share table to stderr")
     ap.add_argument("--no-graph", action="store_true", help="drive every kernel launch from Python instead of one CUDA graph")
+    ap.add_argument("--timeline", default="", help="write the per-kernel timeline of one instrumented replay of the headline step (CSV: stream, start, end)")
     ap.add_argument("--workload", default="maple", choices=list(WORKLOADS),
                     help="headline workload: maple = BASELINE.json's metric (default); the others are also reported under `secondary`")
     args = ap.parse_args()

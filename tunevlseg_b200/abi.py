@@ -472,7 +472,8 @@ _prof: list | None = None
 
 
 def set_profiler(records: list | None) -> None:
-    """When ``records`` is a list every op below appends (name, key, start_event, end_event, algorithmic_flops)."""
+    """When ``records`` is a list every op below appends (name, key, start_event, end_event, algorithmic_flops,
+    algorithmic_bytes, stream handle)."""
     global _prof
     _prof = records
 
@@ -544,7 +545,7 @@ def _wrap(fn, name):
         key, fl = _flops(name, args, kwargs)
         if name == "gemm":
             key += f"|{gemm_last_variant()}"
-        _prof.append((name, key, e0, e1, fl, _bytes(name, args, kwargs)))
+        _prof.append((name, key, e0, e1, fl, _bytes(name, args, kwargs), torch.cuda.current_stream().cuda_stream))
         return out
 
     op.__name__, op.__doc__ = fn.__name__, fn.__doc__
