@@ -373,17 +373,16 @@ enum { EPI_GENERIC = 0, EPI_OUT_BF16 = 1 /* (+bias) -> bf16 */, EPI_RES_F32 = 2 
        EPI_FC1 = 3 /* + bias -> bf16 pre-activation; QuickGELU -> fp16 */, EPI_DQGELU = 4 /* * QuickGELU'(aux bf16) -> bf16 */ };
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0, const uint32_t (&ext)[32]) {
+__device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0, const uint32_t (&ext)[32],
+                                              const float* __restrict__ s_bias /* this chunk's 32 bias values in shared memory, or nullptr */) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-    if (EPI != EPI_DQGELU && ep.bias) {        // kernel-uniform
+    if (EPI != EPI_DQGELU && s_bias != nullptr) {        // kernel-uniform; 8 broadcast LDS.128
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t b[8];
-            ld256(ep.bias + col0 + 8 * q, b);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * q + i] += __uint_as_float(b[i]);
+        for (int q = 0; q < 8; ++q) {
+            const float4 b = reinterpret_cast<const float4*>(s_bias)[q];
+            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
         }
     }
     if (EPI == EPI_OUT_BF16) {
@@ -409,6 +408,28 @@ __device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint
             v[2 * i + 1] *= quick_gelu_grad(u.y);
         }
         st_bf16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
+    }
+}
+
+// the global operands of one chunk of a specialised epilogue (residual row segment / saved pre-activation), issued early
+template <int EPI>
+__device__ __forceinline__ void spec_load_ext(const GemmEpilogue& ep, long long row, int col0, uint32_t (&ext)[32]) {
+    if (EPI == EPI_DQGELU) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t a8[8];
+            ld256(ep.aux_bf16 + row * ep.ldaux + col0 + 16 * h, a8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ext[8 * h + i] = a8[i];
+        }
+    } else if (EPI == EPI_RES_F32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r8[8];
+            ld256(ep.residual + row * ep.ldr + col0 + 8 * q, r8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ext[8 * q + i] = r8[i];
+        }
     }
 }
 
@@ -764,6 +785,64 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int ew = (warp - 4) & 3;     // TMEM lane quarter = warp % 4
         const int grp = (warp - 4) >> 2;   // 0 / 1
         uint32_t acc = 0, acc_phase = 0;
+        if (EPI != EPI_GENERIC) {
+            // ---- straight-line epilogue of a hot shape (host guarantees vec256_ok, N % 32 == 0, no convolution) ----
+            // Everything the math needs besides the accumulator is requested BEFORE the wait it would otherwise follow:
+            //   * the bias slice of this warp's chunks goes global -> registers before the wait for the MMAs of the tile, then
+            //     into a private shared-memory strip (broadcast LDS in the math instead of four exposed 256-bit global loads per
+            //     chunk: the first version lost ~0.3 us per chunk there);
+            //   * the residual / saved pre-activation segment of chunk k + 1 is requested while chunk k's TMEM load is in flight
+            //     (double-buffered registers), the first chunk's before the wait for the tile.
+            constexpr int NCH = BN / 64;                 // chunks of 32 columns per group and tile (pairs {2g, 2g+1}, {2g+4, 2g+5})
+            float* s_bias = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 4) * (NCH * 32);     // the staged path's area is unused here
+            for (int tile = tiles.next(); tile >= 0; tile = tiles.next()) {
+                const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
+                const long long row0 = static_cast<long long>(m_blk) * BM + ew * 32;
+                const long long orow = row0 + lane;
+                const bool row_ok = orow < M;
+                const bool use_bias = EPI != EPI_DQGELU && ep.bias != nullptr;
+                float bias_r[NCH];
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int col = n_blk * BN + (grp * 2 + (k & 1) + (k >> 1) * 4) * 32 + lane;
+                    bias_r[k] = (use_bias && col < N) ? __ldg(ep.bias + col) : 0.f;
+                }
+                uint32_t ext[2][32];
+                if (row_ok && n_blk * BN + grp * 64 < N) spec_load_ext<EPI>(ep, orow, n_blk * BN + grp * 64, ext[0]);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                if (use_bias) {
+                    __syncwarp();                        // the previous tile's reads of the strip are done
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) s_bias[k * 32 + lane] = bias_r[k];
+                    __syncwarp();
+                }
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int cc = grp * 2 + (k & 1) + (k >> 1) * 4;
+                    const int col0 = n_blk * BN + cc * 32;
+                    if (row0 < M && col0 < N) {          // warp-uniform
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_row + cc * 32, r);
+                        if (k + 1 < NCH) {
+                            const int coln = n_blk * BN + (grp * 2 + ((k + 1) & 1) + ((k + 1) >> 1) * 4) * 32;
+                            if (row_ok && coln < N) spec_load_ext<EPI>(ep, orow, coln, ext[(k + 1) & 1]);
+                        }
+                        tmem_ld_wait();
+                        if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext[k & 1], use_bias ? s_bias + k * 32 : nullptr);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CL == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+                    else mbar_arrive(&tmem_empty[acc]);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        } else
         for (int tile = tiles.next(); tile >= 0; tile = tiles.next()) {
             const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -785,37 +864,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const bool extras = direct && row_ok && (ep.residual != nullptr || is_dact(ep.act));
             // a group takes PAIRS of adjacent chunks (64 columns): for the bf16 arrays a thread then reads / writes whole
             // 128-byte lines within a few hundred cycles instead of a quarter of a line per visit
-            if (EPI != EPI_GENERIC) {
-                // straight-line epilogue of a hot shape (host guarantees vec256_ok, N % 32 == 0, no convolution)
-#pragma unroll 1
-                for (int cc = grp * 2; cc < BN / 32; cc += (cc & 1) ? 3 : 1) {
-                    const int col0 = n_blk * BN + cc * 32;
-                    if (row0 >= M || col0 >= N) break;
-                    uint32_t r[32], ext[32];
-                    tmem_ld_32x32(t_row + cc * 32, r);
-                    if (row_ok) {        // operands of this chunk in flight together with the TMEM load
-                        if (EPI == EPI_DQGELU) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                uint32_t a8[8];
-                                ld256(ep.aux_bf16 + orow * ep.ldaux + col0 + 16 * h, a8);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) ext[8 * h + i] = a8[i];
-                            }
-                        } else if (EPI == EPI_RES_F32) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t r8[8];
-                                ld256(ep.residual + orow * ep.ldr + col0 + 8 * q, r8);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) ext[8 * q + i] = r8[i];
-                            }
-                        }
-                    }
-                    tmem_ld_wait();
-                    if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext);
-                }
-            } else {
 #pragma unroll 1
             for (int cc = grp * 2; cc < BN / 32; cc += (cc & 1) ? 3 : 1) {
                 const int c = cc;
@@ -848,7 +896,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     epilogue_chunk(ep, r, stage, row0, col0, M, N, lane);
                 }
             }
-            }   // EPI_GENERIC
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
