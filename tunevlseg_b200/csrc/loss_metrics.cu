@@ -18,18 +18,24 @@
 namespace tvs {
 
 constexpr int LOSS_THREADS = 256;
+constexpr int NSLOT = 9;          // per block: I, P, G, bce (double) + tp, n_ge, n_t, tp_gt, n_gt (int64), 9 x 8 bytes per slot
 
 static int loss_blocks_per_sample(int B, long long N) {
-    long long want = (16LL * sm_count() + B - 1) / B;     // ~8 resident blocks per SM: the kernels are latency bound on their two loads per pixel quad
-    long long cap = (N + 4 * LOSS_THREADS - 1) / (4 * LOSS_THREADS);
+    long long want = (8LL * sm_count() + B - 1) / B;      // ~8 blocks of 256 threads per SM
+    long long cap = (N + 8 * LOSS_THREADS - 1) / (8 * LOSS_THREADS);      // at least two quads per thread
     long long n = want < cap ? want : cap;
     return static_cast<int>(n < 1 ? 1 : n);
 }
 
+// Per-pixel work, kept off the integer pipe: the first version spent 58 % of the ALU pipe on 11 integer counters per pixel and
+// a 64-bit float->int conversion of the mask, and ran at 58 % of the HBM roofline (ncu, B = 256 @ 416^2).  The counters are
+// kept as FLOATS (0/1 increments, exact below 2^24 per thread and per block) on the FMA pipe, and only five are needed:
+//   tp = #(p >= thr, t), n_ge = #(p >= thr), n_t = #(t), tp_gt = #(p > thr, t), n_gt = #(p > thr)
+//   fp = n_ge - tp, fn = n_t - tp;  confusion matrix: c11 = tp_gt, c01 = n_gt - tp_gt, c10 = n_t - tp_gt, c00 = n - n_t - c01
+// t = mask.long() of a {0, 1} mask (image_text_mask_module.py:107): t = (y >= 1).
 struct PixelStats {
     float I, P, G, bce;
-    unsigned tp, fp, fn;          // p >= thr
-    unsigned c00, c01, c10, c11;  // [t][p > thr]
+    float tp, nge, nt, tpgt, ngt;
 };
 
 template <bool PROBS>
@@ -38,8 +44,8 @@ __device__ __forceinline__ void pixel(float x, float y, float thr, PixelStats& s
     if (PROBS) {
         p = x;   // the caller already holds probabilities (metric(preds, target) API): threshold them as they are
     } else {
-        // fast path: one MUFU.EX2, one MUFU.RCP, one MUFU.LG2 per pixel (an IEEE division plus log1pf had made this HBM-sized
-        // kernel instruction bound).  t = exp(-|x|) in (0, 1]; sigmoid(x) = 1 / (1 + t) for x >= 0, t / (1 + t) otherwise.
+        // fast path: one MUFU.EX2, one MUFU.RCP, one MUFU.LG2 per pixel.  t = exp(-|x|) in (0, 1];
+        // sigmoid(x) = 1 / (1 + t) for x >= 0, t / (1 + t) otherwise.
         const float t = __expf(-fabsf(x));
         const float r = __fdividef(1.0f, 1.0f + t);
         p = x >= 0.f ? r : t * r;
@@ -49,127 +55,132 @@ __device__ __forceinline__ void pixel(float x, float y, float thr, PixelStats& s
         }
         s.bce += fmaxf(x, 0.f) - x * y + __logf(1.0f + t);
     }
-    s.I += p * y;
+    s.I = fmaf(p, y, s.I);
     s.P += p;
     s.G += y;
-    const unsigned t = static_cast<unsigned>(static_cast<long long>(y)) & 1u;
-    const unsigned ge = p >= thr, gt = p > thr;
-    s.tp += ge & t;
-    s.fp += ge & (t ^ 1u);
-    s.fn += (ge ^ 1u) & t;
-    s.c00 += (t ^ 1u) & (gt ^ 1u);
-    s.c01 += (t ^ 1u) & gt;
-    s.c10 += t & (gt ^ 1u);
-    s.c11 += t & gt;
+    const float tf = y >= 1.0f ? 1.0f : 0.0f;
+    const float gef = p >= thr ? 1.0f : 0.0f, gtf = p > thr ? 1.0f : 0.0f;
+    s.tp = fmaf(gef, tf, s.tp);
+    s.nge += gef;
+    s.nt += tf;
+    s.tpgt = fmaf(gtf, tf, s.tpgt);
+    s.ngt += gtf;
 }
 
 template <bool PROBS>
 __global__ void __launch_bounds__(LOSS_THREADS)
-dicebce_partial_kernel(const float* __restrict__ logits, const float* __restrict__ mask, long long N, float thr, double* __restrict__ part_out,
-                       long long* __restrict__ cnt_out) {
+dicebce_partial_kernel(const float* __restrict__ logits, const float* __restrict__ mask, long long N, float thr, double* __restrict__ slot_out) {
     const int b = blockIdx.y, nblk = gridDim.x;
     const float* x = logits + static_cast<long long>(b) * N;
     const float* y = mask + static_cast<long long>(b) * N;
-    PixelStats s = {0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0, 0, 0, 0};
+    PixelStats s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
     if (vec) {
-        const long long n4 = N >> 2;
-        for (long long i = static_cast<long long>(blockIdx.x) * LOSS_THREADS + threadIdx.x; i < n4; i += static_cast<long long>(nblk) * LOSS_THREADS) {
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
-            const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + i);
-            pixel<PROBS>(xv.x, yv.x, thr, s);
-            pixel<PROBS>(xv.y, yv.y, thr, s);
-            pixel<PROBS>(xv.z, yv.z, thr, s);
-            pixel<PROBS>(xv.w, yv.w, thr, s);
+        const long long n4 = N >> 2, stride = static_cast<long long>(nblk) * LOSS_THREADS;
+        long long i = static_cast<long long>(blockIdx.x) * LOSS_THREADS + threadIdx.x;
+        // two quads per trip: four 128-bit loads in flight per thread before the first use
+        for (; i + stride < n4; i += 2 * stride) {
+            const float4 xa = __ldcs(reinterpret_cast<const float4*>(x) + i), ya = __ldcs(reinterpret_cast<const float4*>(y) + i);
+            const float4 xb = __ldcs(reinterpret_cast<const float4*>(x) + i + stride), yb = __ldcs(reinterpret_cast<const float4*>(y) + i + stride);
+            pixel<PROBS>(xa.x, ya.x, thr, s); pixel<PROBS>(xa.y, ya.y, thr, s); pixel<PROBS>(xa.z, ya.z, thr, s); pixel<PROBS>(xa.w, ya.w, thr, s);
+            pixel<PROBS>(xb.x, yb.x, thr, s); pixel<PROBS>(xb.y, yb.y, thr, s); pixel<PROBS>(xb.z, yb.z, thr, s); pixel<PROBS>(xb.w, yb.w, thr, s);
+        }
+        if (i < n4) {
+            const float4 xa = __ldcs(reinterpret_cast<const float4*>(x) + i), ya = __ldcs(reinterpret_cast<const float4*>(y) + i);
+            pixel<PROBS>(xa.x, ya.x, thr, s); pixel<PROBS>(xa.y, ya.y, thr, s); pixel<PROBS>(xa.z, ya.z, thr, s); pixel<PROBS>(xa.w, ya.w, thr, s);
         }
     } else {
         for (long long i = static_cast<long long>(blockIdx.x) * LOSS_THREADS + threadIdx.x; i < N; i += static_cast<long long>(nblk) * LOSS_THREADS)
             pixel<PROBS>(x[i], y[i], thr, s);
     }
-    // block reduction: floats in double, counters as 64-bit
-    __shared__ double sd[LOSS_THREADS / 32][4];
-    __shared__ unsigned long long sc[LOSS_THREADS / 32][7];
+    // block reduction.  Loss sums: float per thread, double across threads.  Counters: exact small integers in float, summed in
+    // float inside the warp (<= 32 * 2^24 / 32 ...: a warp never sees 2^24 pixels), in double across warps.
+    __shared__ double sd[LOSS_THREADS / 32][NSLOT];
     double d[4] = {s.I, s.P, s.G, s.bce};
-    unsigned long long c[7] = {s.tp, s.fp, s.fn, s.c00, s.c01, s.c10, s.c11};
+    float c[5] = {s.tp, s.nge, s.nt, s.tpgt, s.ngt};
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
 #pragma unroll
-        for (int k = 0; k < 7; ++k) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+        for (int k = 0; k < 5; ++k) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) sd[warp][k] = d[k];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) sc[warp][k] = c[k];
+        for (int k = 0; k < 5; ++k) sd[warp][4 + k] = static_cast<double>(c[k]);
     }
     __syncthreads();
-    if (threadIdx.x < 11) {
-        const long long slot = static_cast<long long>(b) * nblk + blockIdx.x;
-        if (threadIdx.x < 4) {
-            double t = 0;
-            for (int w = 0; w < LOSS_THREADS / 32; ++w) t += sd[w][threadIdx.x];
-            part_out[slot * 4 + threadIdx.x] = t;
-        } else {
-            unsigned long long t = 0;
-            for (int w = 0; w < LOSS_THREADS / 32; ++w) t += sc[w][threadIdx.x - 4];
-            cnt_out[slot * 7 + (threadIdx.x - 4)] = static_cast<long long>(t);
-        }
+    if (threadIdx.x < NSLOT) {
+        double t = 0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) t += sd[w][threadIdx.x];
+        slot_out[(static_cast<long long>(b) * nblk + blockIdx.x) * NSLOT + threadIdx.x] = t;      // counters: exact integers in double
     }
 }
 
-// one warp per sample: lanes stride over the blocks of that sample, then a fixed-order butterfly - deterministic, and the
-// nblk * 11 loads of a sample are in flight together (the first version walked them serially in one thread per sample: 33 us)
-__global__ void __launch_bounds__(256)
-dicebce_finalize_kernel(const double* __restrict__ part_in, const long long* __restrict__ cnt_in, int B, int nblk, long long N,
-                        float lambda_dice, float lambda_ce, double* __restrict__ parts, long long* __restrict__ counts,
-                        long long* __restrict__ confmat, float* __restrict__ loss) {
-    extern __shared__ double sh[];  // [B] dice term, [B] bce sum, then 4*B int64 conf
+// One block, one warp per sample at a time: lanes stride over the blocks of that sample (all loads of a sample in flight
+// together), fixed-order butterfly - deterministic.  Then warp 0 reduces over the samples, again in a fixed order.
+__global__ void __launch_bounds__(1024)
+dicebce_finalize_kernel(const double* __restrict__ slot_in, int B, int nblk, long long N, float lambda_dice, float lambda_ce,
+                        double* __restrict__ parts, long long* __restrict__ counts, long long* __restrict__ confmat, float* __restrict__ loss) {
+    extern __shared__ double sh[];  // [B] dice term, [B] bce sum, then 4*B conf counts (exact integers in double)
     double* s_dice = sh;
     double* s_bce = sh + B;
-    long long* s_conf = reinterpret_cast<long long*>(sh + 2 * B);
+    double* s_conf = sh + 2 * B;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     for (int b = warp; b < B; b += nwarp) {
-        double p[4] = {0, 0, 0, 0};
-        long long c[7] = {0, 0, 0, 0, 0, 0, 0};
+        double v[NSLOT];
+#pragma unroll
+        for (int j = 0; j < NSLOT; ++j) v[j] = 0;
         for (int k = lane; k < nblk; k += 32) {
-            const long long slot = static_cast<long long>(b) * nblk + k;
+            const double* sl = slot_in + (static_cast<long long>(b) * nblk + k) * NSLOT;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[j] += part_in[slot * 4 + j];
-#pragma unroll
-            for (int j = 0; j < 7; ++j) c[j] += cnt_in[slot * 7 + j];
+            for (int j = 0; j < NSLOT; ++j) v[j] += sl[j];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
-#pragma unroll
-            for (int j = 0; j < 7; ++j) c[j] += __shfl_xor_sync(0xffffffffu, c[j], o);
+            for (int j = 0; j < NSLOT; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
         }
         if (lane == 0) {
+            const double tp = v[4], nge = v[5], nt = v[6], tpgt = v[7], ngt = v[8];
             if (parts)
-                for (int j = 0; j < 4; ++j) parts[b * 4 + j] = p[j];
-            if (counts)
-                for (int j = 0; j < 3; ++j) counts[b * 3 + j] = c[j];
-            for (int j = 0; j < 4; ++j) s_conf[b * 4 + j] = c[3 + j];
-            s_dice[b] = 1.0 - (2.0 * p[0] + 1e-5) / (p[1] + p[2] + 1e-5);
-            s_bce[b] = p[3];
+                for (int j = 0; j < 4; ++j) parts[b * 4 + j] = v[j];
+            if (counts) {
+                counts[b * 3 + 0] = static_cast<long long>(tp);
+                counts[b * 3 + 1] = static_cast<long long>(nge - tp);
+                counts[b * 3 + 2] = static_cast<long long>(nt - tp);
+            }
+            const double c01 = ngt - tpgt;
+            s_conf[b * 4 + 0] = static_cast<double>(N) - nt - c01;     // tn
+            s_conf[b * 4 + 1] = c01;                                   // fp
+            s_conf[b * 4 + 2] = nt - tpgt;                             // fn
+            s_conf[b * 4 + 3] = tpgt;                                  // tp
+            s_dice[b] = 1.0 - (2.0 * v[0] + 1e-5) / (v[1] + v[2] + 1e-5);
+            s_bce[b] = v[3];
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double dice = 0, bce = 0;
-        long long cf[4] = {0, 0, 0, 0};
-        for (int b = 0; b < B; ++b) {
-            dice += s_dice[b];
-            bce += s_bce[b];
-            for (int j = 0; j < 4; ++j) cf[j] += s_conf[b * 4 + j];
+    if (warp == 0) {
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int b = lane; b < B; b += 32) {
+            acc[0] += s_dice[b];
+            acc[1] += s_bce[b];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[2 + j] += s_conf[b * 4 + j];
         }
-        if (loss) *loss = static_cast<float>(lambda_dice * dice / B + lambda_ce * bce / (static_cast<double>(B) * static_cast<double>(N)));
-        if (confmat)
-            for (int j = 0; j < 4; ++j) confmat[j] += cf[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        }
+        if (lane == 0) {
+            if (loss) *loss = static_cast<float>(lambda_dice * acc[0] / B + lambda_ce * acc[1] / (static_cast<double>(B) * static_cast<double>(N)));
+            if (confmat)
+                for (int j = 0; j < 4; ++j) confmat[j] += static_cast<long long>(acc[2 + j]);
+        }
     }
 }
 
@@ -226,7 +237,7 @@ static int finalize_smem_opt_in(size_t sh) {
 
 extern "C" __attribute__((visibility("default"))) int64_t tvs_dicebce_scratch_bytes(int32_t B, int64_t N) {
     const int nblk = tvs::loss_blocks_per_sample(B, N);
-    return static_cast<int64_t>(B) * nblk * (4 * sizeof(double) + 7 * sizeof(long long));
+    return static_cast<int64_t>(B) * nblk * tvs::NSLOT * sizeof(double);
 }
 
 extern "C" __attribute__((visibility("default"))) int tvs_dicebce_metrics_fwd(const float* logits, const float* mask, int32_t B, int64_t N, float threshold, float lambda_dice,
@@ -236,15 +247,14 @@ extern "C" __attribute__((visibility("default"))) int tvs_dicebce_metrics_fwd(co
     TVS_REQUIRE(logits && mask && scratch, "tvs_dicebce_metrics_fwd: null pointer");
     TVS_REQUIRE(B > 0 && B <= 4096 && N > 0, "tvs_dicebce_metrics_fwd: bad shape B=%d N=%lld", B, (long long)N);
     const int nblk = loss_blocks_per_sample(B, N);
-    double* part = static_cast<double*>(scratch);
-    long long* cnt = reinterpret_cast<long long*>(part + static_cast<long long>(B) * nblk * 4);
+    double* slots = static_cast<double*>(scratch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dicebce_partial_kernel<false><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(logits, mask, N, threshold, part, cnt);
+    dicebce_partial_kernel<false><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(logits, mask, N, threshold, slots);
     if (int rc = check_launch("dicebce_partial_kernel")) return rc;
-    const size_t sh = static_cast<size_t>(B) * (2 * sizeof(double) + 4 * sizeof(long long));
+    const size_t sh = static_cast<size_t>(B) * 6 * sizeof(double);
     if (int rc = finalize_smem_opt_in(sh)) return rc;
-    dicebce_finalize_kernel<<<1, 256, sh, st>>>(part, cnt, B, nblk, N, lambda_dice, lambda_ce, parts, reinterpret_cast<long long*>(counts),
-                                                reinterpret_cast<long long*>(confmat), loss);
+    dicebce_finalize_kernel<<<1, 1024, sh, st>>>(slots, B, nblk, N, lambda_dice, lambda_ce, parts, reinterpret_cast<long long*>(counts),
+                                                 reinterpret_cast<long long*>(confmat), loss);
     return check_launch("dicebce_finalize_kernel");
 }
 
@@ -266,14 +276,13 @@ extern "C" __attribute__((visibility("default"))) int tvs_metrics_from_probs(con
     TVS_REQUIRE(preds && mask && scratch, "tvs_metrics_from_probs: null pointer");
     TVS_REQUIRE(B > 0 && B <= 4096 && N > 0, "tvs_metrics_from_probs: bad shape B=%d N=%lld", B, (long long)N);
     const int nblk = loss_blocks_per_sample(B, N);
-    double* part = static_cast<double*>(scratch);
-    long long* cnt = reinterpret_cast<long long*>(part + static_cast<long long>(B) * nblk * 4);
+    double* slots = static_cast<double*>(scratch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dicebce_partial_kernel<true><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(preds, mask, N, threshold, part, cnt);
+    dicebce_partial_kernel<true><<<dim3(nblk, B), LOSS_THREADS, 0, st>>>(preds, mask, N, threshold, slots);
     if (int rc = check_launch("dicebce_partial_kernel")) return rc;
-    const size_t sh = static_cast<size_t>(B) * (2 * sizeof(double) + 4 * sizeof(long long));
+    const size_t sh = static_cast<size_t>(B) * 6 * sizeof(double);
     if (int rc = finalize_smem_opt_in(sh)) return rc;
-    dicebce_finalize_kernel<<<1, 256, sh, st>>>(part, cnt, B, nblk, N, 0.f, 0.f, nullptr, reinterpret_cast<long long*>(counts),
-                                                reinterpret_cast<long long*>(confmat), nullptr);
+    dicebce_finalize_kernel<<<1, 1024, sh, st>>>(slots, B, nblk, N, 0.f, 0.f, nullptr, reinterpret_cast<long long*>(counts),
+                                                 reinterpret_cast<long long*>(confmat), nullptr);
     return check_launch("dicebce_finalize_kernel");
 }
