@@ -89,6 +89,14 @@ typedef struct tvs_gemm_args {
                                               (ky, kx, c).  Outputs / residual / aux are UNPADDED [B*H*W, N] matrices: the
                                               epilogue maps rows and skips the border.  No im2col matrix ever exists: each k-block
                                               is a TMA load of the A rows shifted by its tap's offset. */
+    /* Deep-prompt overwrite fused into the residual epilogue (base_multimodal_clipseg.py:394-398, base_visual_learner.py:18-23:
+     * the prompt rows of the block output are REPLACED by the next depth's context).  When ovr_ctx != NULL the output rows whose
+     * position inside their sample (row % ovr_S) lies in [ovr_row0, ovr_row0 + ovr_n) receive
+     * ovr_ctx[(row / ovr_S) * ovr_batch_stride + (row % ovr_S - ovr_row0) * N + col] instead of the GEMM result
+     * (ovr_batch_stride = 0: one shared context; n * N: per-sample contexts, CoCoOp).  Implemented for the 16-bit
+     * bias + f32-residual -> f32 GEMM (fc2 of a vision block); other configurations are rejected - use tvs_prompt_overwrite. */
+    const float* ovr_ctx; int64_t ovr_batch_stride;
+    int32_t ovr_S, ovr_row0, ovr_n, ovr_reserved;
 } tvs_gemm_args;
 
 int tvs_gemm_bf16(const tvs_gemm_args* args, void* stream);

@@ -38,7 +38,8 @@ def round_tf32(x, y):
     y.copy_(_tf32_rn(x))
 
 
-def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False, conv_hw=None):
+def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False, conv_hw=None,
+         overwrite=None):
     H16 = (BF16, torch.float16)          # kind::f16 takes two bf16 or two fp16 operands (mixing is illegal on sm_100); kind::tf32 two fp32
     assert A.dtype == W.dtype and A.dtype in (BF16, torch.float16, F32), (A.dtype, W.dtype)
     assert A.dim() == 2 and W.dim() == 2, (A.shape, W.shape)
@@ -74,6 +75,13 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
         v = v + residual
     if act == abi.ACT_RES_RELU:
         v = torch.relu(v)
+    if overwrite is not None:        # fused deep-prompt overwrite: only the 16-bit bias + f32-residual -> f32 GEMM implements it
+        ctx, S_, row0, n_ = overwrite
+        assert A.dtype in H16 and residual is not None and out_f32 is not None and out_bf16 is None and pre_bf16 is None and act == abi.ACT_NONE
+        assert v.shape[0] % S_ == 0 and ctx.shape[-2:] == (n_, v.shape[1]) and v.shape[1] % 32 == 0
+        v = v.clone().view(-1, S_, v.shape[1])
+        v[:, row0:row0 + n_] = ctx
+        v = v.view(-1, v.shape[-1])
     for o in (out_f32, out_bf16):
         if o is not None:
             assert o.shape == v.shape and o.stride(1) == 1
@@ -328,7 +336,8 @@ def head_bwd(dlogits, tconv, add_out, bias_t, ratio, blend, B, G, P, ksize, dtco
             lg = (1 - rr) * (_untile(tc, B, img, img, P) + bias_t) + rr * (add - add.detach() + add_out)
     outs = torch.autograd.grad(lg, [tc, am, ba] + ([rr] if rr is not None else []), g)
     dtconv_bf16.copy_(outs[0])
-    daddmap.copy_(outs[1])
+    if daddmap is not None:          # None: the caller computes the tap-map gradient itself (two GEMMs, engine.DecoderFn.backward)
+        daddmap.copy_(outs[1])
     dbias_a += outs[2]
     if rr is not None and dratio is not None:
         dratio += outs[3]

@@ -290,3 +290,28 @@ def test_attention_forward_is_reproducible_run_to_run(B, S, H):
     ref = (torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh).transpose(1, 2).reshape(B * S, D)
     err = (outs[0][0].float() - ref).abs().max().item()
     assert err <= 2 ** -6 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("M_S,per_sample", [((32 * 489, 489), False), ((6 * 21, 21), True), ((32 * 489, 489), True)])
+def test_gemm_fused_prompt_overwrite(M_S, per_sample):
+    """Deep prompts are replaced IN the fc2 epilogue (north_star; base_multimodal_clipseg.py:394-398): rows S-n .. S-1 of every
+    sample of the output equal the context, every other row the plain bias + residual GEMM, bit for bit."""
+    from tunevlseg_b200 import abi
+
+    (M, S), n, N, K = M_S, 4, 768, 1024
+    B = M // S
+    g = torch.Generator(device="cuda").manual_seed(M + per_sample)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).half()
+    bias, res = torch.randn(N, device="cuda", generator=g), torch.randn(M, N, device="cuda", generator=g)
+    ctx = torch.randn((B, n, N) if per_sample else (n, N), device="cuda", generator=g)
+    plain, fused = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    abi.gemm(A, W, bias=bias, residual=res, out_f32=plain, tile_n=128)
+    abi.gemm(A, W, bias=bias, residual=res, out_f32=fused, overwrite=(ctx, S, S - n, n))
+    assert "epi:res_f32" in abi.gemm_last_variant()
+    torch.cuda.synchronize()
+    want = plain.view(B, S, N).clone()
+    want[:, S - n:] = ctx
+    assert torch.equal(fused.view(B, S, N), want)
+    with pytest.raises(abi.TvsError):        # a configuration without the fused path must say so, not ignore the request
+        abi.gemm(A.float(), W.float(), bias=bias, residual=res, out_f32=fused, overwrite=(ctx, S, S - n, n))

@@ -38,6 +38,8 @@ class GemmArgs(Structure):
         ("aux_bf16", c_void_p), ("ldaux", c_int64),
         ("act", c_int32), ("tile_n", c_int32), ("ab_dtype", c_int32), ("reserved", c_int32),
         ("conv_h", c_int32), ("conv_w", c_int32),
+        ("ovr_ctx", c_void_p), ("ovr_batch_stride", c_int64),
+        ("ovr_S", c_int32), ("ovr_row0", c_int32), ("ovr_n", c_int32), ("ovr_reserved", c_int32),
     ]
 
 
@@ -174,11 +176,13 @@ def _chk(t: torch.Tensor | None, dtype, name: str, dim2: bool = False) -> None:
 
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=ACT_NONE,
-         tile_n=0, round_out=False, conv_hw=None):
+         tile_n=0, round_out=False, conv_hw=None, overwrite=None):
     """C[M,N] = epilogue(A[M,K] @ W[N,K]^T); see tvs_gemm_bf16 in include/tvs_b200.h.  2-D views with a row stride
     are accepted (ld = stride(0)).  ``round_out``: out_f32 is rounded to nearest tf32 (it only feeds further tf32 GEMMs).
     ``conv_hw=(H, W)``: implicit-GEMM 3x3 convolution - A is the zero-bordered image [B*(H+2)*(W+2), C] from ``pad_nhwc``,
-    W is [N, 9*C]; outputs / residual are unpadded [B*H*W, N]."""
+    W is [N, 9*C]; outputs / residual are unpadded [B*H*W, N].
+    ``overwrite=(ctx, S, row0, n)``: deep-prompt overwrite fused into the epilogue - output rows at positions row0 .. row0+n-1 of
+    every S-row sample receive ctx ((n, N) shared or (B, n, N) per sample, f32) instead of the result (fc2 of a vision block)."""
     require_device()
     ab = {(torch.bfloat16, torch.bfloat16): AB_BF16, (torch.float32, torch.float32): AB_TF32, (torch.float16, torch.float16): AB_F16}.get((A.dtype, W.dtype))
     if ab is None:      # a mixed fp16 x bf16 kind::f16 MMA is an illegal instruction on sm_100 (measured)
@@ -216,6 +220,13 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.ab_dtype = ab
     g.reserved = (1 if round_out else 0) | (2 if (out_bf16 is not None and out_bf16.dtype == torch.float16) else 0)
     g.conv_h, g.conv_w = conv_hw if conv_hw is not None else (0, 0)
+    if overwrite is not None:
+        ctx, S_, row0, n_ = overwrite
+        _chk(ctx, torch.float32, "overwrite ctx")
+        if ctx.shape[-1] != N or ctx.shape[-2] != n_:
+            raise TvsError(f"gemm: overwrite ctx must be (..., {n_}, {N}), got {tuple(ctx.shape)}")
+        g.ovr_ctx, g.ovr_batch_stride = ctx.data_ptr(), (0 if ctx.dim() == 2 else n_ * N)
+        g.ovr_S, g.ovr_row0, g.ovr_n = S_, row0, n_
     _ck(load().tvs_gemm_bf16(byref(g), _stream()), "tvs_gemm_bf16")
 
 

@@ -44,6 +44,12 @@ struct GemmEpilogue {
     int round_out;   // out_f32 is rounded to nearest tf32 (cvt.rna): it only feeds further kind::tf32 MMAs, which truncate
     int fmt_a, fmt_b;   // kind::f16 operand formats of A and W in the instruction descriptor: 0 = IEEE fp16, 1 = bf16 (ignored by kind::tf32)
     int out16_f16;      // the 16-bit activation output (out_bf16) is written as IEEE fp16 (11-bit significand) instead of bf16
+    // deep-prompt overwrite fused into the residual epilogue (EPI_RES_F32): output rows whose position inside their sample,
+    // row % ovr_S, lies in [ovr_row0, ovr_row0 + ovr_n) receive ovr_ctx[(row / ovr_S) * ovr_bs + (row % ovr_S - ovr_row0) * N + col]
+    // instead of the GEMM result (base_multimodal_clipseg.py:394-398: the prompt rows are re-written after every block < depth)
+    const float* ovr_ctx;
+    long long ovr_bs;
+    int ovr_S, ovr_row0, ovr_n;
     // implicit-GEMM 3x3 convolution (conv_wp != 0): A is a zero-bordered channels-last image [B, conv_hp, conv_wp, C] seen as
     // a [B*hp*wp, C] matrix; k-block kb belongs to tap kb / conv_kpt and loads the A rows SHIFTED by that tap's offset
     // in the flattened image (the physical zero border makes every interior pixel's 9 taps correct); the epilogue maps
@@ -374,7 +380,8 @@ enum { EPI_GENERIC = 0, EPI_OUT_BF16 = 1 /* (+bias) -> bf16 */, EPI_RES_F32 = 2 
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0, const uint32_t (&ext)[32],
-                                              const float* __restrict__ s_bias /* this chunk's 32 bias values in shared memory, or nullptr */) {
+                                              const float* __restrict__ s_bias /* this chunk's 32 bias values in shared memory, or nullptr */,
+                                              bool ovr = false /* EPI_RES_F32: ext holds the prompt row that replaces the result */) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
@@ -392,7 +399,7 @@ __device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint
         for (int q = 0; q < 4; ++q) {
             uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(v[8 * q + i] + __uint_as_float(ext[8 * q + i]));
+            for (int i = 0; i < 8; ++i) o[i] = ovr ? ext[8 * q + i] : __float_as_uint(v[8 * q + i] + __uint_as_float(ext[8 * q + i]));
             st256(ep.out_f32 + row * ep.ldo32 + col0 + 8 * q, o);
         }
     } else if (EPI == EPI_FC1) {
@@ -413,7 +420,7 @@ __device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint
 
 // the global operands of one chunk of a specialised epilogue (residual row segment / saved pre-activation), issued early
 template <int EPI>
-__device__ __forceinline__ void spec_load_ext(const GemmEpilogue& ep, long long row, int col0, uint32_t (&ext)[32]) {
+__device__ __forceinline__ void spec_load_ext(const GemmEpilogue& ep, long long row, int col0, uint32_t (&ext)[32], const float* ovr_row = nullptr) {
     if (EPI == EPI_DQGELU) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -426,7 +433,7 @@ __device__ __forceinline__ void spec_load_ext(const GemmEpilogue& ep, long long 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t r8[8];
-            ld256(ep.residual + row * ep.ldr + col0 + 8 * q, r8);
+            ld256(ovr_row ? ovr_row + col0 + 8 * q : ep.residual + row * ep.ldr + col0 + 8 * q, r8);
 #pragma unroll
             for (int i = 0; i < 8; ++i) ext[8 * q + i] = r8[i];
         }
@@ -807,8 +814,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const int col = n_blk * BN + (grp * 2 + (k & 1) + (k >> 1) * 4) * 32 + lane;
                     bias_r[k] = (use_bias && col < N) ? __ldg(ep.bias + col) : 0.f;
                 }
+                const float* ovr_row = nullptr;       // this thread's output row is a prompt row: its replacement values
+                if (EPI == EPI_RES_F32 && ep.ovr_ctx != nullptr && row_ok) {
+                    const long long smp = orow / ep.ovr_S;
+                    const int pr = static_cast<int>(orow - smp * ep.ovr_S) - ep.ovr_row0;
+                    if (pr >= 0 && pr < ep.ovr_n) ovr_row = ep.ovr_ctx + smp * ep.ovr_bs + static_cast<long long>(pr) * N;
+                }
                 uint32_t ext[2][32];
-                if (row_ok && n_blk * BN + grp * 64 < N) spec_load_ext<EPI>(ep, orow, n_blk * BN + grp * 64, ext[0]);
+                if (row_ok && n_blk * BN + grp * 64 < N) spec_load_ext<EPI>(ep, orow, n_blk * BN + grp * 64, ext[0], ovr_row);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 if (use_bias) {
@@ -827,10 +840,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         tmem_ld_32x32(t_row + cc * 32, r);
                         if (k + 1 < NCH) {
                             const int coln = n_blk * BN + (grp * 2 + ((k + 1) & 1) + ((k + 1) >> 1) * 4) * 32;
-                            if (row_ok && coln < N) spec_load_ext<EPI>(ep, orow, coln, ext[(k + 1) & 1]);
+                            if (row_ok && coln < N) spec_load_ext<EPI>(ep, orow, coln, ext[(k + 1) & 1], ovr_row);
                         }
                         tmem_ld_wait();
-                        if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext[k & 1], use_bias ? s_bias + k * 32 : nullptr);
+                        if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext[k & 1], use_bias ? s_bias + k * 32 : nullptr, ovr_row != nullptr);
                     }
                 }
                 tc_fence_before();
@@ -1098,6 +1111,17 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.round_out = a.reserved & TVS_GEMM_ROUND_OUT_TF32;
     ep.out16_f16 = (a.reserved & TVS_GEMM_OUT16_F16) ? 1 : 0;
     ep.fmt_a = ep.fmt_b = a.ab_dtype == TVS_AB_F16 ? 0 : 1;
+    ep.ovr_ctx = a.ovr_ctx;
+    ep.ovr_bs = a.ovr_batch_stride;
+    ep.ovr_S = a.ovr_S;
+    ep.ovr_row0 = a.ovr_row0;
+    ep.ovr_n = a.ovr_n;
+    if (a.ovr_ctx) {
+        TVS_REQUIRE(a.ovr_S > 0 && a.ovr_row0 >= 0 && a.ovr_n > 0 && a.ovr_row0 + a.ovr_n <= a.ovr_S && a.M % a.ovr_S == 0,
+                    "tvs_gemm_bf16: prompt overwrite needs M = B * S and 0 <= row0, row0 + n <= S (M=%d S=%d row0=%d n=%d)", a.M, a.ovr_S, a.ovr_row0, a.ovr_n);
+        TVS_REQUIRE((reinterpret_cast<uintptr_t>(a.ovr_ctx) & 31) == 0 && a.N % 8 == 0 && a.ovr_batch_stride % 8 == 0,
+                    "tvs_gemm_bf16: prompt overwrite needs 32-byte aligned context rows");
+    }
     ep.conv_wp = ep.conv_hp = ep.conv_kpt = 0;
     ep.vec_ok = vec_ok ? 1 : 0;
     auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
@@ -1120,6 +1144,12 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N);
+    if (a.ovr_ctx) {        // only the straight-line residual epilogue implements the fused overwrite
+        if (!a.tile_n && bn < 128) bn = 128;
+        TVS_REQUIRE(a.ab_dtype != TVS_AB_TF32 && bn >= 128 && pick_epi(a, ep, false) == EPI_RES_F32,
+                    "tvs_gemm_bf16: the fused prompt overwrite is implemented for the 16-bit residual GEMM (bias + f32 residual -> f32, "
+                    "N %% 32 == 0, aligned rows, tile_n >= 128); use tvs_prompt_overwrite otherwise");
+    }
     const bool tf32 = a.ab_dtype == TVS_AB_TF32;
     switch (bn) {
         case 64: return tf32 ? launch_gemm<64, 8, true>(a, ep, s) : launch_gemm<64, 8, false>(a, ep, s);

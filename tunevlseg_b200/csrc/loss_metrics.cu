@@ -12,6 +12,8 @@
 // Two kernels: (1) grid (nblk, B) - every block reduces a slice of one sample to 4 doubles + 7 counters in
 // `scratch`; (2) one block - fixed-order reduction over blocks and samples (deterministic), writes
 // parts / counts / loss and accumulates the confusion matrix.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tvs_b200.h"
 
@@ -20,8 +22,10 @@ namespace tvs {
 constexpr int LOSS_THREADS = 256;
 constexpr int NSLOT = 9;          // per block: I, P, G, bce (double) + tp, n_ge, n_t, tp_gt, n_gt (int64), 9 x 8 bytes per slot
 
-static int loss_blocks_per_sample(int B, long long N) {
-    long long want = (8LL * sm_count() + B - 1) / B;      // ~8 blocks of 256 threads per SM
+static int loss_blocks_per_sample(int B, long long N, int per_sm = 8) {
+    static const int env = [] { const char* e = getenv("TVS_LOSS_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();     // tuning switch
+    if (env > 0) per_sm = env;
+    long long want = (static_cast<long long>(per_sm) * sm_count() + B - 1) / B;      // blocks of 256 threads per SM, over all samples
     long long cap = (N + 8 * LOSS_THREADS - 1) / (8 * LOSS_THREADS);      // at least two quads per thread
     long long n = want < cap ? want : cap;
     return static_cast<int>(n < 1 ? 1 : n);
@@ -263,7 +267,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_dicebce_bwd(const floa
     using namespace tvs;
     TVS_REQUIRE(logits && mask && parts && dlogits, "tvs_dicebce_bwd: null pointer");
     TVS_REQUIRE(B > 0 && N > 0, "tvs_dicebce_bwd: bad shape");
-    const int nblk = loss_blocks_per_sample(B, N);
+    const int nblk = loss_blocks_per_sample(B, N, 16);
     dicebce_bwd_kernel<<<dim3(nblk, B), LOSS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, mask, parts, gscale, B, N, lambda_dice,
                                                                                               lambda_ce, dlogits);
     return check_launch("dicebce_bwd_kernel");

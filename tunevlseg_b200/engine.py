@@ -69,6 +69,15 @@ def tf32_rn(w: torch.Tensor) -> torch.Tensor:
 FFN_MODE = os.environ.get("TVS_FFN", "split")
 
 
+# TVS_HEAD_BWD=kernel: the additive branch's gradient w.r.t. the low-resolution tap map by the stencil kernel
+# (head_bwd_addmap_kernel, 128 us: barrier-bound); default: two tf32 GEMMs against the separable tap matrix (~30 us)
+HEAD_BWD_GEMM = os.environ.get("TVS_HEAD_BWD", "gemm") != "kernel"
+
+
+# TVS_FUSE_OVERWRITE=0: deep-prompt overwrite as a separate kernel after every block (A/B switch); default: in the fc2 epilogue
+FUSE_OVERWRITE = os.environ.get("TVS_FUSE_OVERWRITE", "1") != "0"
+
+
 # TVS_TAIL=0: run the bottom block's backward on every row (A/B measurements); default: prompt rows only
 TAIL_PRUNE = os.environ.get("TVS_TAIL", "1") != "0"
 
@@ -183,6 +192,36 @@ class PackedClipSeg:
         self.w_tconv = tf32_rn(tw.reshape(self.Dr, -1).t())                          # [P*P, Dr] f32 (tf32 MMA)
         self.w_tconv_t = _bf(tw.reshape(self.Dr, -1))                                # [Dr, P*P]
         self.b_tconv = _f(dec.transposed_convolution.bias)
+        self._tap_mats: dict = {}
+
+    def tap_matrix(self, ks: int) -> torch.Tensor:
+        if ks not in self._tap_mats:
+            self._tap_mats[ks] = head_tap_matrix(self.grid, self.patch, ks, self.cls.device)
+        return self._tap_mats[ks]
+
+
+def head_tap_matrix(G: int, P: int, ks: int, device) -> torch.Tensor:
+    """Wm[(t, k), c] = weight with which pixel coordinate c, shifted by tap k and clamped (replicate padding), reads the low-res
+    index t through ``Upsample(scale_factor=P, bilinear, align_corners=False)`` (base_clipseg.py:57-71).  The additive branch is
+    separable in these weights, logits_add[Y, X] = sum wy(Y; ky, yi) wx(X; kx, xi) addmap[yi, xi, ky, kx], so its backward is two
+    small GEMMs with this matrix (DecoderFn.backward).  fp32 arithmetic as in csrc/elementwise.cu ``bilin``; rows padded to a
+    multiple of 8.  The weights are multiples of 1 / (2P): exact in tf32."""
+    import numpy as np
+
+    f = np.float32
+    W, half = G * P, (ks - 1) // 2
+    rows = (G * ks + 7) // 8 * 8
+    m = np.zeros((rows, W), np.float32)
+    for c in range(W):
+        for k in range(ks):
+            cc = min(max(c + k - half, 0), W - 1)
+            src = max(f((f(cc) + f(0.5)) / f(P)) - f(0.5), f(0))
+            i0 = min(int(src), G - 1)
+            i1 = min(i0 + 1, G - 1)
+            w1 = f(src - f(i0))
+            m[i0 * ks + k, c] += f(1) - w1
+            m[i1 * ks + k, c] += w1
+    return torch.from_numpy(m).to(device)
 
 
 def packed_for(model) -> PackedClipSeg:
@@ -220,8 +259,10 @@ class Saved:
     u: torch.Tensor
 
 
-def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: bool):
-    """Pre-LN block (modeling_clipseg.py:357-387).  x: f32 [B*S, D] -> f32 [B*S, D]."""
+def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: bool, overwrite=None):
+    """Pre-LN block (modeling_clipseg.py:357-387).  x: f32 [B*S, D] -> f32 [B*S, D].
+    ``overwrite=(ctx, row0, n)``: the deep-prompt re-write of the block output (rows row0 .. row0+n-1 of every sample become
+    ``ctx``, base_multimodal_clipseg.py:394-398) - fused into the fc2 epilogue on the 16-bit path, a separate kernel otherwise."""
     M, D, F = B * S, pk.D, pk.F
     hi = pk.tf32                       # fp32 activations + kind::tf32 MMAs for the small, precision-critical towers
     adt = F32 if hi else pk.act16      # 16-bit forward operands: fp16 in the vision tower (FWD16), q / k / v stay bf16
@@ -251,7 +292,11 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     abi.gemm(ln, pk.w1_32 if hi else pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_f32=a if hi else None,
              out_bf16=None if hi else a, act=abi.ACT_QGELU, round_out=hi)
     x2 = _e((M, D), F32, x)
-    abi.gemm(a, pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2)
+    fuse = overwrite is not None and not hi and D % 32 == 0 and FUSE_OVERWRITE
+    abi.gemm(a, pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2,
+             overwrite=(overwrite[0], S, overwrite[1], overwrite[2]) if fuse else None)
+    if overwrite is not None and not fuse:
+        abi.prompt_overwrite(x2.view(B, S, D), overwrite[1], overwrite[2], overwrite[0])
     sv = Saved(x, mean1, rstd1, qkv, att, lse, x1, mean2, rstd2, u) if save else None
     return x2, sv
 
@@ -425,9 +470,8 @@ class VisionTowerFn(torch.autograd.Function):
         n_run = max(pk.extract_layers) + 1
         saved, taps = [], {}
         for idx in range(1, n_run + 1):
-            x, sv = encoder_layer_fwd(pk.v_layers[idx - 1], x, B, S, False, None, pk.eps, need_grad)
-            if idx < prompt_depth:
-                abi.prompt_overwrite(x.view(B, S, -1), S - n, n, cv[idx])
+            x, sv = encoder_layer_fwd(pk.v_layers[idx - 1], x, B, S, False, None, pk.eps, need_grad,
+                                      overwrite=(cv[idx], S - n, n) if idx < prompt_depth else None)
             saved.append(sv)
             if (idx - 1) in pk.extract_layers:
                 taps[idx - 1] = x
@@ -521,9 +565,8 @@ class TextTowerFn(torch.autograd.Function):
         km = None if key_mask is None else key_mask.to(torch.uint8).contiguous()
         saved = []
         for idx in range(1, len(pk.t_layers) + 1):
-            x, sv = encoder_layer_fwd(pk.t_layers[idx - 1], x, B, S, True, km, pk.eps, need_grad)
-            if idx < depth:
-                abi.prompt_overwrite(x.view(B, S, D), 1, n_ctx, cd[idx - 1])
+            x, sv = encoder_layer_fwd(pk.t_layers[idx - 1], x, B, S, True, km, pk.eps, need_grad,
+                                      overwrite=(cd[idx - 1], 1, n_ctx) if idx < depth else None)
             saved.append(sv)
         xf = _e((B * S, D), F32, x)
         mean_f, rstd_f = _e((B * S,), F32, x), _e((B * S,), F32, x)
@@ -649,7 +692,22 @@ class DecoderFn(torch.autograd.Function):
             daddmap = torch.zeros((B * G2, wa16.shape[0]), dtype=F32, device=dev)
             dba = torch.zeros(1, dtype=F32, device=dev)
             dr_ = torch.zeros(1, dtype=F32, device=dev)
-            abi.head_bwd(dl, tconv, add_out, pk.b_tconv, ratio_d, blend, B, G, P, ks, dtconv16, daddmap[:, :KK], dba, dr_)
+            Wimg = G * P
+            if HEAD_BWD_GEMM and Wimg % 4 == 0:
+                # daddmap[b, yi, xi, ky, kx] = wb * sum_{Y, X} dl[b, Y, X] wy(Y; ky, yi) wx(X; kx, xi): contract X, then Y, on the
+                # tensor cores (kind::tf32; the operands are gradients: the MMA's truncation is far inside their tolerance)
+                abi.head_bwd(dl, tconv, add_out, pk.b_tconv, ratio_d, blend, B, G, P, ks, dtconv16, None, dba, dr_)
+                wm = pk.tap_matrix(ks)                                   # [R, W], R = G * ks padded to 8
+                R = wm.shape[0]
+                t1 = _e((R, B * Wimg), F32, dl)
+                abi.gemm(wm, dl.view(B * Wimg, Wimg), out_f32=t1)        # t1[(xi, kx), (b, Y)] = sum_X wx dl
+                t1p = t1.view(R, B, Wimg).permute(1, 0, 2).contiguous()  # [(b, xi, kx), Y]
+                c2 = _e((B * R, R), F32, dl)
+                abi.gemm(t1p.view(B * R, Wimg), wm, out_f32=c2)          # c2[(b, xi, kx), (yi, ky)] = sum_Y wy t1
+                dam = c2.view(B, R, R)[:, :G * ks, :G * ks].reshape(B, G, ks, G, ks).permute(0, 3, 1, 4, 2).reshape(B * G2, KK)
+                daddmap[:, :KK] = dam * ratio_d if blend == abi.BLEND_RATIO else dam
+            else:
+                abi.head_bwd(dl, tconv, add_out, pk.b_tconv, ratio_d, blend, B, G, P, ks, dtconv16, daddmap[:, :KK], dba, dr_)
             abi.gemm(dtconv16, pk.w_tconv_t, out_f32=dfeat)
             da16 = _e(tuple(daddmap.shape), BF16, dl)
             abi.cast_bf16(daddmap, da16)
