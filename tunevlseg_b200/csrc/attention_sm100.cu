@@ -464,6 +464,277 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward, second version: 32-row inner tiles with TWO score buffers in TMEM and a software-pipelined MMA stream.
+// In attn_tc_kernel<DQ|DKV> a CTA alternates MMA (S, dP) -> element-wise -> MMA (accumulate) on ONE 64-column score buffer;
+// ncu (round 2): tensor pipe 23-25 %, warps stalled on TMEM loads, each kernel at ~55 % of its TMEM read-out floor
+// (64 B/clk/SM), because the element-wise stage of a CTA idles while its own score MMAs run and the co-resident CTA only
+// partly fills the hole.  Here S / dP of step it + 1 are queued before the accumulate MMAs of step it, so the tensor core
+// works on the next score tile while the exponentials of the current one run; same 256 TMEM columns (two buffers of
+// 32 + 32 columns, accumulators at 128 / 192), two CTAs per SM, 4-stage inner ring of 4 KB tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int BT = 32;                          // inner rows per step
+constexpr int BITILE = BT * AHD * 2;            // 4 KB
+constexpr int BST = 4;                          // inner stages
+struct Bwd2Smem {
+    static constexpr int OUTER = 0;
+    static constexpr int INNER = 2 * ATILE;
+    static constexpr int VEC = INNER + BST * 2 * BITILE;            // DKV: [BST][2][BT] floats (lse, delta); DQ: [2][128] floats (delta halves)
+    static constexpr int BAR = VEC + 2 * AT * 4;
+    static constexpr int TOTAL = BAR + 16 * 8 + 1024;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(ATC_THREADS_BWD, 2)
+attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                    const __grid_constant__ CUtensorMap map_qkv_in, const __grid_constant__ CUtensorMap map_do_in, int S, int H,
+                    const __nv_bfloat16* __restrict__ out, float* __restrict__ delta_out, const float* __restrict__ lse_in,
+                    const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv, int ot0, int o_f16) {
+    using L = Bwd2Smem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* s_outer0 = smem + L::OUTER;
+    uint8_t* s_outer1 = s_outer0 + ATILE;
+    uint8_t* s_inner = smem + L::INNER;                         // stage s: tile0 at s * 2 * BITILE, tile1 at + BITILE
+    float* s_vec = reinterpret_cast<float*>(smem + L::VEC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+    uint64_t* outer_full = bars;
+    uint64_t* in_full = bars + 1;      // [BST]
+    uint64_t* in_empty = bars + 5;     // [BST]
+    uint64_t* s_full = bars + 9;       // [2]
+    uint64_t* ew_done = bars + 11;     // [2]
+    uint64_t* acc_full = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int ot = blockIdx.x + ot0, h = blockIdx.y, b = blockIdx.z;
+    const int E = H * AHD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_TMA = 8, W_MMA = 9;
+    const int n_it = (S + BT - 1) / BT;
+    constexpr uint32_t TMEM_COLS = 256, C_ACC0 = 128, C_ACC1 = 192;
+    auto CS = [](int bf) -> uint32_t { return 64u * bf; };
+    auto CDP = [](int bf) -> uint32_t { return 64u * bf + 32u; };
+    const long long bh = static_cast<long long>(b) * H + h;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_qkv);
+        tma_prefetch_desc(&map_do);
+        mbar_init(outer_full, 1);
+        for (int s = 0; s < BST; ++s) {
+            mbar_init(&in_full[s], MODE == MODE_DKV ? 2 : 1);
+            mbar_init(&in_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&ew_done[s], 256);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == W_TMA) {
+        const int cq = h * AHD, ck = E + h * AHD, cv = 2 * E + h * AHD;
+        if (elect_one()) {
+            mbar_expect_tx(outer_full, 2 * ATILE);
+            if (MODE == MODE_DQ) {
+                tma_load_3d(s_outer0, &map_qkv, cq, ot * AT, b, outer_full);
+                tma_load_3d(s_outer1, &map_do, h * AHD, ot * AT, b, outer_full);
+            } else {
+                tma_load_3d(s_outer0, &map_qkv, ck, ot * AT, b, outer_full);
+                tma_load_3d(s_outer1, &map_qkv, cv, ot * AT, b, outer_full);
+            }
+        }
+        for (int it = 0; it < n_it; ++it) {
+            const int stage = it % BST, par = (it / BST) & 1;
+            uint8_t* t0 = s_inner + stage * 2 * BITILE;
+            uint8_t* t1 = t0 + BITILE;
+            mbar_wait(&in_empty[stage], par ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&in_full[stage], 2 * BITILE);
+                if (MODE == MODE_DQ) {
+                    tma_load_3d(t0, &map_qkv_in, ck, it * BT, b, &in_full[stage]);
+                    tma_load_3d(t1, &map_qkv_in, cv, it * BT, b, &in_full[stage]);
+                } else {
+                    tma_load_3d(t0, &map_qkv_in, cq, it * BT, b, &in_full[stage]);
+                    tma_load_3d(t1, &map_do_in, h * AHD, it * BT, b, &in_full[stage]);
+                }
+            }
+            if (MODE == MODE_DKV) {
+                __syncwarp();
+                float* v_lse = s_vec + stage * 2 * BT;
+                const int q = it * BT + lane;
+                v_lse[lane] = q < S ? lse_in[bh * S + q] * L2E : INFINITY;
+                v_lse[BT + lane] = q < S ? delta_in[bh * S + q] : 0.f;
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&in_full[stage]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == W_MMA) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(AT, BT, 0, 0);
+        constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
+        mbar_wait(outer_full, 0);
+        tc_fence_after();
+        const uint64_t a0 = umma_desc_sw128(smem_u32(s_outer0));
+        const uint64_t a1 = umma_desc_sw128(smem_u32(s_outer1));
+        // accumulate MMAs of step j: the packed A operand of K-step k (16 inner rows = 8 columns) sits at the start of the 16
+        // columns the element-wise warps of half k read themselves
+        auto issue_acc = [&](int j) {
+            const int bfj = j & 1, stg = j % BST;
+            mbar_wait(&ew_done[bfj], (j >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stg * 2 * BITILE));
+                const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stg * 2 * BITILE + BITILE));
+                if (MODE == MODE_DQ) {
+#pragma unroll
+                    for (int k = 0; k < BT / 16; ++k)   // dQ += dS K_j
+                        umma_ts(tb + C_ACC0, tb + 64 * bfj + 16 * k, b0 + 128 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < BT / 16; ++k)   // dV += P^T dO_i
+                        umma_ts(tb + C_ACC0, tb + 64 * bfj + 16 * k, b1 + 128 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < BT / 16; ++k)   // dK += dS^T Q_i
+                        umma_ts(tb + C_ACC1, tb + 64 * bfj + 32 + 16 * k, b0 + 128 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&in_empty[stg]);
+                if (j == n_it - 1) umma_commit(acc_full);
+            }
+            __syncwarp();
+        };
+        for (int it = 0; it < n_it; ++it) {
+            const int stage = it % BST, par = (it / BST) & 1, bf = it & 1;
+            mbar_wait(&in_full[stage], par);
+            tc_fence_after();
+            // score buffer bf was last read (as packed P / dS) by the accumulate MMAs of step it - 2: issued earlier in program order
+            if (elect_one()) {
+                const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * BITILE));
+                const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * BITILE + BITILE));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb + 64 * bf, a0 + 2 * k, b0 + 2 * k, idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tb + 64 * bf + 32, a1 + 2 * k, b1 + 2 * k, idesc_s, k > 0);
+                umma_commit(&s_full[bf]);
+            }
+            __syncwarp();
+            if (it >= 1) issue_acc(it - 1);
+        }
+        issue_acc(n_it - 1);
+    } else {
+        // element-wise warps: thread = TMEM lane = row (query for DQ, key for DKV); `half` = which 16 of the 32 score columns
+        const int quarter = warp & 3, half = warp >> 2;
+        const int tid = quarter * 32 + lane;
+        const uint32_t tl = tb + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int row = ot * AT + tid;
+        const bool row_ok = row < S;
+        const float my_lse = (MODE == MODE_DQ && row_ok) ? lse_in[bh * S + row] * L2E : INFINITY;
+        float my_del = 0.f;
+        if (MODE == MODE_DQ) {
+            if (out != nullptr) {
+                // delta = rowsum(dO o O): this thread's half of the dO row from the swizzled outer tile, its half of the O row from
+                // global memory; the halves meet through shared memory
+                mbar_wait(outer_full, 0);
+                float part = 0.f;
+                const long long tok = static_cast<long long>(b) * S + (row_ok ? row : 0);
+                const uint4* orow = reinterpret_cast<const uint4*>(out + tok * E + h * AHD + 32 * half);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int chunk = 4 * half + c;
+                    const uint4 g = *reinterpret_cast<const uint4*>(s_outer1 + tid * 128 + ((chunk ^ (tid & 7)) << 4));
+                    const uint4 o = row_ok ? orow[c] : make_uint4(0u, 0u, 0u, 0u);
+                    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a = unpack_bf16x2(gw[i]), bb = o_f16 ? unpack_f16x2(ow[i]) : unpack_bf16x2(ow[i]);
+                        part = fmaf(a.x, bb.x, part);
+                        part = fmaf(a.y, bb.y, part);
+                    }
+                }
+                s_vec[half * AT + tid] = part;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                my_del = s_vec[tid] + s_vec[AT + tid];
+                if (half == 0 && row_ok) delta_out[bh * S + row] = my_del;
+            } else if (row_ok) {
+                my_del = delta_in[bh * S + row];
+            }
+        }
+        for (int it = 0; it < n_it; ++it) {
+            const int bf = it & 1, stage = it % BST;
+            mbar_wait(&s_full[bf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tS = tl + 64 * bf + 16 * half, tD = tS + 32;
+            const int c0 = it * BT + 16 * half;
+            const float* v_lse = s_vec + stage * 2 * BT + 16 * half;
+            const float* v_del = v_lse + BT;
+            uint32_t sA[16], dA[16];
+            tmem_ld16(tS, sA);
+            tmem_ld16(tD, dA);
+            tmem_ld_wait();
+            uint32_t pkp[8], pks[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const float s0 = __uint_as_float(sA[i]), s1 = __uint_as_float(sA[i + 1]);
+                const float g0 = __uint_as_float(dA[i]), g1 = __uint_as_float(dA[i + 1]);
+                float p0, p1, d0, d1;
+                if (MODE == MODE_DQ) {
+                    p0 = (c0 + i < S) ? fast_exp2(fmaf(s0, L2E, -my_lse)) : 0.f;
+                    p1 = (c0 + i + 1 < S) ? fast_exp2(fmaf(s1, L2E, -my_lse)) : 0.f;
+                    d0 = p0 * (g0 - my_del);
+                    d1 = p1 * (g1 - my_del);
+                } else {
+                    const float2 l2 = *reinterpret_cast<const float2*>(v_lse + i);
+                    const float2 e2 = *reinterpret_cast<const float2*>(v_del + i);
+                    p0 = row_ok ? fast_exp2(fmaf(s0, L2E, -l2.x)) : 0.f;
+                    p1 = row_ok ? fast_exp2(fmaf(s1, L2E, -l2.y)) : 0.f;
+                    d0 = p0 * (g0 - e2.x);
+                    d1 = p1 * (g1 - e2.y);
+                }
+                pks[i / 2] = pack_bf16x2(d0, d1);
+                if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
+            }
+            if (MODE == MODE_DQ) {
+                tmem_st8(tS, pks);           // dS
+            } else {
+                tmem_st8(tS, pkp);           // P^T
+                tmem_st8(tD, pks);           // dS^T
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&ew_done[bf]);
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        uint32_t a0r[32];
+        tmem_ld32(tl + C_ACC0 + 32 * half, a0r);
+        tmem_ld_wait();
+        const long long tok = static_cast<long long>(b) * S + row;
+        __nv_bfloat16* drow = dqkv + tok * 3 * E + h * AHD + 32 * half;
+        if (MODE == MODE_DQ) {
+            if (row_ok) store_row_bf16_32(drow, a0r);
+        } else {
+            if (row_ok) store_row_bf16_32(drow + 2 * E, a0r);     // dV
+            tmem_ld32(tl + C_ACC1 + 32 * half, a0r);
+            tmem_ld_wait();
+            if (row_ok) store_row_bf16_32(drow + E, a0r);         // dK
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tb, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // dedicated forward kernel: as MODE_FWD above (two passes over the keys, P kept in TMEM) but with TWO score buffers in
 // TMEM and a software-pipelined MMA stream - Q K_{it+1}^T is queued before P_{it} V_{it}, so the tensor core works on
 // the next score tile while the exp stage of the current one runs; the per-iteration critical path is the exp stage
@@ -974,12 +1245,45 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
     return check_launch("attn_tc_fwd_kernel");
 }
 
+template <int MODE>
+static int launch_bwd2(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mqi, const CUtensorMap& mdi, int B, int S, int H,
+                       const __nv_bfloat16* out, float* delta_out, const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st,
+                       int ot0, int o_f16) {
+    auto kern = attn_tc_bwd2_kernel<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Bwd2Smem::TOTAL));
+        attr_set = true;
+    }
+    dim3 grid((S + AT - 1) / AT - ot0, H, B);
+    TVS_CUDA(launch_pdl(kern, grid, dim3(ATC_THREADS_BWD), Bwd2Smem::TOTAL, st, 1, mq, md, mqi, mdi, S, H, out, delta_out, lse_in, delta_in, dqkv, ot0, o_f16));
+    return check_launch(MODE == MODE_DQ ? "attn_tc_bwd2_kernel<dq>" : "attn_tc_bwd2_kernel<dkv>");
+}
+
 // delta must already hold rowsum(dO o O)
 // row_begin > 0: dqkv is produced only for the 128-row tiles that contain rows >= row_begin (queries for dQ, keys for dK / dV)
 // out_o != nullptr (whole-sequence backward only): delta is computed by the dQ kernel from O and dO and written for the dK / dV kernel
 int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const float* lse, float* delta, int B, int S, int H, void* dqkv, cudaStream_t st,
                 int row_begin, int o_f16) {
     const int ot0 = row_begin / AT;
+    // TVS_ATTN_BWD=2: the double-buffered 32-row kernels (attn_tc_bwd2_kernel).  Measured equal to the single-buffer kernels
+    // (170.1 vs 170.0 us per layer, B = 32, S = 489): removing the MMA -> element-wise -> MMA serialisation did not move the
+    // time, so that chain is not what bounds the backward; the default stays the round-1 pair.
+    static const bool v2 = [] { const char* e = getenv("TVS_ATTN_BWD"); return e && e[0] == '2'; }();
+    if (v2) {
+        CUtensorMap mq, md, mqi, mdi;      // 128-row boxes for the outer tiles, 32-row boxes for the inner ones
+        if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
+        if (int rc = make_tmap3(&md, dout, H * AHD, S, B)) return rc;
+        if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, BT)) return rc;
+        if (int rc = make_tmap3(&mdi, dout, H * AHD, S, B, BT)) return rc;
+        __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
+        if (out_o != nullptr && ot0 == 0) {      // dQ first: it produces delta on the way
+            if (int rc = launch_bwd2<MODE_DQ>(mq, md, mqi, mdi, B, S, H, static_cast<const __nv_bfloat16*>(out_o), delta, lse, delta, dq, st, 0, o_f16)) return rc;
+            return launch_bwd2<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, lse, delta, dq, st, 0, 0);
+        }
+        if (int rc = launch_bwd2<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, lse, delta, dq, st, ot0, 0)) return rc;
+        return launch_bwd2<MODE_DQ>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, lse, delta, dq, st, ot0, 0);
+    }
     CUtensorMap mq, md, mqi, mdi;      // 128-row boxes for the outer tiles, 64-row boxes for the inner ones
     if (int rc = make_tmap3(&mq, qkv, 3 * H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&md, dout, H * AHD, S, B)) return rc;
