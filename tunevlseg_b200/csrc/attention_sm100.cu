@@ -410,16 +410,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                     const float s0 = __uint_as_float(sA[i]), s1 = __uint_as_float(sA[i + 1]);
                     const float g0 = __uint_as_float(dA[i]), g1 = __uint_as_float(dA[i + 1]);
                     float p0, p1, d0, d1;
+                    // No per-element masks: a key past the sequence end has an all-zero K / V row (TMA zero fill), so its finite
+                    // p and dS multiply zeros in dQ += dS K; a key ROW past the end (DKV) only feeds dK / dV rows that are never
+                    // stored; a query past the end has lse = +inf, hence p = dS = 0.  (The masks cost ~3 of ~9 issue slots per
+                    // score, and the element-wise warps are issue-bound: ncu round 2.)
                     if (MODE == MODE_DQ) {
-                        p0 = (c0 + i < S) ? fast_exp2(fmaf(s0, L2E, -my_lse)) : 0.f;
-                        p1 = (c0 + i + 1 < S) ? fast_exp2(fmaf(s1, L2E, -my_lse)) : 0.f;
+                        p0 = fast_exp2(fmaf(s0, L2E, -my_lse));
+                        p1 = fast_exp2(fmaf(s1, L2E, -my_lse));
                         d0 = p0 * (g0 - my_del);
                         d1 = p1 * (g1 - my_del);
                     } else {
                         const float2 l2 = *reinterpret_cast<const float2*>(v_lse + i);      // lse = +inf for queries past the end -> p = 0
                         const float2 e2 = *reinterpret_cast<const float2*>(v_del + i);
-                        p0 = row_ok ? fast_exp2(fmaf(s0, L2E, -l2.x)) : 0.f;
-                        p1 = row_ok ? fast_exp2(fmaf(s1, L2E, -l2.y)) : 0.f;
+                        p0 = fast_exp2(fmaf(s0, L2E, -l2.x));
+                        p1 = fast_exp2(fmaf(s1, L2E, -l2.y));
                         d0 = p0 * (g0 - e2.x);
                         d1 = p1 * (g1 - e2.y);
                     }
@@ -684,15 +688,15 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                 const float g0 = __uint_as_float(dA[i]), g1 = __uint_as_float(dA[i + 1]);
                 float p0, p1, d0, d1;
                 if (MODE == MODE_DQ) {
-                    p0 = (c0 + i < S) ? fast_exp2(fmaf(s0, L2E, -my_lse)) : 0.f;
-                    p1 = (c0 + i + 1 < S) ? fast_exp2(fmaf(s1, L2E, -my_lse)) : 0.f;
+                    p0 = fast_exp2(fmaf(s0, L2E, -my_lse));
+                    p1 = fast_exp2(fmaf(s1, L2E, -my_lse));
                     d0 = p0 * (g0 - my_del);
                     d1 = p1 * (g1 - my_del);
                 } else {
                     const float2 l2 = *reinterpret_cast<const float2*>(v_lse + i);
                     const float2 e2 = *reinterpret_cast<const float2*>(v_del + i);
-                    p0 = row_ok ? fast_exp2(fmaf(s0, L2E, -l2.x)) : 0.f;
-                    p1 = row_ok ? fast_exp2(fmaf(s1, L2E, -l2.y)) : 0.f;
+                    p0 = fast_exp2(fmaf(s0, L2E, -l2.x));
+                    p1 = fast_exp2(fmaf(s1, L2E, -l2.y));
                     d0 = p0 * (g0 - e2.x);
                     d1 = p1 * (g1 - e2.y);
                 }
