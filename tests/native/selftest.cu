@@ -575,6 +575,8 @@ static void test_ln() {
     ln_case(5, 512);
     ln_case(1003, 64);
     ln_case(9, 1024);
+    ln_case(2051, 768);       // two rows per warp (M >= 2048), odd row count
+    ln_case(15648, 64);       // half-warp-per-row kernels at the decoder shape
 }
 
 // ------------------------------------------------------------------------------------------------
