@@ -701,6 +701,14 @@ int main(int argc, char** argv) {
         gemm_case(15648, 768, 3072, TVS_ACT_NONE, true, true, true, false, false, 128, true);
         printf("-- N=2304 K=768: bias, bf16 out (QKV)\n");
         gemm_case(15648, 2304, 768, TVS_ACT_NONE, true, false, false, true, false, 128, true);
+        printf("-- tile width 256 on the N = 768 / 2304 shapes (pairs: 256 x 256 tiles)\n");
+        gemm_case(15648, 768, 3072, TVS_ACT_NONE, true, true, true, false, false, 256, true);
+        gemm_case(15648, 768, 3072, TVS_ACT_NONE, false, false, false, true, false, 256, true);
+        gemm_case(15648, 768, 3072, TVS_ACT_NONE, false, false, false, true, false, 128, true);
+        gemm_case(15648, 2304, 768, TVS_ACT_NONE, true, false, false, true, false, 256, true);
+        gemm_case(15648, 768, 2304, TVS_ACT_NONE, false, false, false, true, false, 256, true);
+        gemm_case(15648, 768, 2304, TVS_ACT_NONE, false, false, false, true, false, 128, true);
+        gemm_case(15648, 768, 768, TVS_ACT_NONE, true, true, true, false, false, 256, true);
     }
     printf("launches: %lld\n", (long long)tvs_launch_count());
     printf(g_fail ? "SELFTEST FAILED (%d cases)\n" : "SELFTEST PASSED\n", g_fail);

@@ -1054,7 +1054,7 @@ static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStrea
     return launch_gemm_cl<BN, STAGES, TF32, 1>(a, ep, stream);
 }
 
-static int pick_tile_n(int M, int N) {
+static int pick_tile_n(int M, int N, int K) {
     if (N <= 64) return 64;
     const int sms = sm_count();
     const int num_m = (M + BM - 1) / BM;
@@ -1062,6 +1062,12 @@ static int pick_tile_n(int M, int N) {
     // narrowest tile - twice the CTAs and half the MMA time per k-block
     if (static_cast<long long>(num_m) * ((N + 127) / 128) < sms) return 64;
     if (N <= 128) return 128;
+    // Compute-heavy shapes that will run as CTA pairs (launch_gemm): 256-wide tiles.  The pair kernels are bound by L2 -> SM
+    // ingress (~64 B/clk/SM, ncu round 2); a 256 x 256 pair tile needs 64 B/clk per SM, a 256 x 128 one 96 B/clk, which
+    // outweighs the wave quantisation the estimate below optimises (measured at M = 15 648: N = 768, K = 3072 70.7 -> 66.6 us
+    // with the fp32 residual epilogue, 61.7 -> 57.7 plain; N = 2304, K = 768 47.7 -> 44.5; N = 768, K = 2304 47.6 -> 44.7;
+    // the memory-bound N = K = 768 stays on single-CTA 128-wide tiles: 38.0 vs 43.1).
+    if (N % 256 == 0 && static_cast<long long>(N) * K >= 768LL * 1024 && static_cast<long long>(num_m) * (N / 256) >= 2LL * sms) return 256;
     auto eff = [&](int bn) {
         long long tiles = static_cast<long long>(num_m) * ((N + bn - 1) / bn);
         long long waves = (tiles + sms - 1) / sms;
@@ -1143,7 +1149,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
         ep.conv_kpt = (a.K / 9) / bk;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N);
+    int bn = a.tile_n ? a.tile_n : pick_tile_n(a.M, a.N, a.K);
     if (a.ovr_ctx) {        // only the straight-line residual epilogue implements the fused overwrite
         if (!a.tile_n && bn < 128) bn = 128;
         TVS_REQUIRE(a.ab_dtype != TVS_AB_TF32 && bn >= 128 && pick_epi(a, ep, false) == EPI_RES_F32,
