@@ -510,6 +510,8 @@ def _flops(name, args, kwargs) -> tuple[str, float]:
         i = 4 if name == "cross_attn_fwd" else 7
         B, Sq, Sk, H = args[i:i + 4]
         return f"B{B}Sq{Sq}Sk{Sk}H{H}", 0.0
+    if name in ("layernorm_fwd", "layernorm_bwd"):          # per-shape rows: the [B*S, 768] tower launches are not pooled with the
+        return "x".join(str(d) for d in args[0].shape), 0.0     # launch-bound [B*L, 512] text-tower ones in the roofline table
     if name in ("im2col_nhwc", "col2im_nhwc", "round_tf32", "relu_mask"):
         t = args[-1] if name == "im2col_nhwc" else args[0]
         return "x".join(str(d) for d in t.shape), 0.0
@@ -542,8 +544,44 @@ def _bytes(name, args, kwargs) -> float:
     return 0.0
 
 
+# NVTX ranges (tracing): TVS_NVTX=1 brackets every library call ("tvs.<op> <shape>") and the phases the
+# engines mark with ``nvtx_range`` (towers, decoder, loss, optimizer), so a timeline tool shows the step's structure.  Off by
+# default: the ranges are host-side markers and cost a few hundred nanoseconds per call outside graph replay.
+NVTX = os.environ.get("TVS_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    """``with abi.nvtx_range("vision_tower.fwd"):`` - a no-op unless TVS_NVTX=1."""
+
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _wrap(fn, name):
     def op(*args, **kwargs):
+        if _prof is None and not NVTX:
+            return fn(*args, **kwargs)
+        if NVTX:
+            torch.cuda.nvtx.range_push(f"tvs.{name} {_flops(name, args, kwargs)[0]}".rstrip())
+            try:
+                return op_inner(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return op_inner(*args, **kwargs)
+
+    def op_inner(*args, **kwargs):
         if _prof is None:
             return fn(*args, **kwargs)
         # inside a stream capture the events become EVENT-RECORD NODES of the graph (cudaEventRecordExternal): every replay

@@ -40,6 +40,21 @@ F32 = torch.float32
 FWD16 = F16 if os.environ.get("TVS_F16", "1") != "0" else BF16
 
 
+def _phase(name: str):
+    """NVTX range around one phase of the step (TVS_NVTX=1; a no-op otherwise)."""
+    def deco(fn):
+        if not abi.NVTX:
+            return fn
+
+        def wrapped(*a, **k):
+            with abi.nvtx_range(name):
+                return fn(*a, **k)
+
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
 def _e(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
@@ -461,6 +476,7 @@ class VisionTowerFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_phase("vision_tower.fwd")
     def forward(ctx, ctx_vis, image, pk: PackedClipSeg, prompt_depth: int):
         B = image.shape[0]
         n = ctx_vis.shape[1]
@@ -482,6 +498,7 @@ class VisionTowerFn(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @_phase("vision_tower.bwd")
     def backward(ctx, *dtaps):
         pk = ctx.pk
         B, S, n, depth, n_run, depth_alloc = ctx.dims
@@ -556,6 +573,7 @@ class TextTowerFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_phase("text_tower.fwd")
     def forward(ctx, emb, ctx_deep, key_mask, pool_pos, pk: PackedClipSeg, n_ctx: int):
         B, S, D = emb.shape
         need_grad = emb.requires_grad or (ctx_deep is not None and ctx_deep.requires_grad)
@@ -581,6 +599,7 @@ class TextTowerFn(torch.autograd.Function):
         return cond
 
     @staticmethod
+    @_phase("text_tower.bwd")
     def backward(ctx, dcond):
         pk = ctx.pk
         B, S, D, depth, n, cd_shape = ctx.dims
@@ -618,6 +637,7 @@ class DecoderFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_phase("decoder.fwd")
     def forward(ctx, tap0, tap1, tap2, cond, add_w, add_b, ratio, pk: PackedClipSeg, blend: int, n_strip: int):
         taps = (tap0, tap1, tap2)
         B, S, Dv = tap0.shape
@@ -676,6 +696,7 @@ class DecoderFn(torch.autograd.Function):
         return logits
 
     @staticmethod
+    @_phase("decoder.bwd")
     def backward(ctx, dlogits):
         pk = ctx.pk
         B, S, Dv, blend, n_strip = ctx.dims
@@ -759,6 +780,7 @@ class DiceBceFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_phase("dicebce.fwd")
     def forward(ctx, logits, mask, threshold, lambda_dice, lambda_ce, confmat):
         B = logits.shape[0]
         lg = logits.detach().to(F32).contiguous()
@@ -778,6 +800,7 @@ class DiceBceFn(torch.autograd.Function):
         return loss.reshape(()), counts
 
     @staticmethod
+    @_phase("dicebce.bwd")
     def backward(ctx, dloss, _dcounts):
         lg, mk, parts = ctx.saved_tensors
         dl = torch.empty_like(lg)

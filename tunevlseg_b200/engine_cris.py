@@ -20,7 +20,7 @@ from types import SimpleNamespace
 import torch
 
 from . import abi
-from .engine import BF16, F32, PackedLayer, _e, encoder_layer_bwd, encoder_layer_fwd, rn_act, tf32_rn
+from .engine import BF16, F32, PackedLayer, _e, _phase, encoder_layer_bwd, encoder_layer_fwd, rn_act, tf32_rn
 
 BN_EPS = 1e-5
 LN_EPS = 1e-5
@@ -366,6 +366,7 @@ def _conv_nograd(op: ConvOp, x, B, H, W, *, residual=None, act=None, x_rounded=F
 
 
 @torch.no_grad()
+@_phase("cris.encode_image")
 def encode_image(pk: PackedCris, image):
     """image (B,3,H,W) f32 -> (v3, v4, v5) as f32 [B*h*w, C] matrices with their (h, w).
 
@@ -662,6 +663,7 @@ class TailFn(torch.autograd.Function):
     (1, mid, k, k) are trainable, so their (tiny) weight gradients are produced here."""
 
     @staticmethod
+    @_phase("cris.tail.fwd")
     def forward(ctx, pred, fq, w0, w2, b2, ratio, pk: PackedCris, B, h, w, G):
         img = pk.image_size
         P = img // G
@@ -699,6 +701,7 @@ class TailFn(torch.autograd.Function):
         return logits
 
     @staticmethod
+    @_phase("cris.tail.bwd")
     def backward(ctx, dlogits):
         pk = ctx.pk
         B, h, w, G, P, ks, mid = ctx.geom
@@ -741,6 +744,7 @@ class CrisTextFn(torch.autograd.Function):
     Returns (ln_final(x) (B,S,D), text_projection(pooled) (B,E))."""
 
     @staticmethod
+    @_phase("cris.text_encoder.fwd")
     def forward(ctx, emb, ctx_over, key_mask, pool_pos, pk: PackedCris, n_ctx: int):
         B, S, D = emb.shape
         x = emb.detach().to(F32).contiguous().view(B * S, D).clone()
@@ -765,6 +769,7 @@ class CrisTextFn(torch.autograd.Function):
         return words.view(B, S, D), state
 
     @staticmethod
+    @_phase("cris.text_encoder.bwd")
     def backward(ctx, dwords, dstate):
         pk = ctx.pk
         B, S, D, depth, n, co_shape = ctx.dims
@@ -789,6 +794,7 @@ class CrisTextFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------------------
 # neck / decoder / projector composition (torch autograd over the primitives above)
 # ------------------------------------------------------------------------------------------------------------------
+@_phase("cris.fpn")
 def fpn(pk: PackedCris, vis, state, B):
     (v3, H3, W3), (v4, H4, W4), (v5, H5, W5) = vis
     s = linear(state, pk.txt_proj, relu=True)                                         # (B, C5)
@@ -809,6 +815,7 @@ def fpn(pk: PackedCris, vis, state, B):
     return conv(fq, pk.coord1, B, H4, W4), H4, W4
 
 
+@_phase("cris.transformer_decoder")
 def transformer_decoder(pk: PackedCris, fq, words, key_mask, B, H, W):
     S, C = H * W, fq.shape[1]
     L = words.shape[1]
@@ -828,6 +835,7 @@ def transformer_decoder(pk: PackedCris, fq, words, key_mask, B, H, W):
     return layer_norm(vis, pk.dec_norm).reshape(B * S, C)
 
 
+@_phase("cris.projector")
 def projector(pk: PackedCris, fq, state, B, H, W):
     x = conv(upsample2x(fq, B, H, W), pk.pv1, B, 2 * H, 2 * W)
     x = conv(upsample2x(x, B, 2 * H, 2 * W), pk.pv3, B, 4 * H, 4 * W)

@@ -168,7 +168,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             self._check_aliasing(f)
             if world > 1:
-                dist.all_reduce(f["grad"], op=dist.ReduceOp.SUM, group=self.process_group)
+                with abi.nvtx_range("ddp.all_reduce_flat_grad"):
+                    dist.all_reduce(f["grad"], op=dist.ReduceOp.SUM, group=self.process_group)
             abi.counter_inc(f["step_dev"])
             b1, b2 = group["betas"]
             abi.adamw_flat(f["param"], f["grad"], f["m"], f["v"], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
