@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TVS_ABI_VERSION 2
+#define TVS_ABI_VERSION 3
 
 int tvs_version(void);
 const char* tvs_last_error(void);
@@ -351,6 +351,28 @@ int tvs_preproc_image_u8(const uint8_t* img, int32_t Hi, int32_t Wi, int64_t ld_
                          void* stream);
 int tvs_resize_nearest_f32(const float* in, int32_t Hi, int32_t Wi, int64_t ld, const int32_t* xofs,
                            const int32_t* yofs, int32_t Ho, int32_t Wo, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Train-time augmentations on the device (configs/experiment/coop/clipseg.yaml:84-103 `train_transforms`):
+ * albumentations.Affine(interpolation=INTER_CUBIC, mode=BORDER_REPLICATE) = cv2.warpAffine on the resized uint8 image
+ * (masks: INTER_NEAREST), RandomBrightnessContrast = a 256-entry uint8 look-up table, then Normalize + ToTensorV2.
+ * warpAffine is OpenCV's fixed-point walk (imgproc/src/imgwarp.cpp): adelta / bdelta int32 [Wo] and x0 / y0 int32 [Ho]
+ * are the tables cv::warpAffine builds from the inverted matrix (1/1024 pixel; x0 / y0 include the rounding term: 16 for
+ * INTER_CUBIC, 512 for INTER_NEAREST); tab = int16 [32][32][4][4], cv::initInterTab2D(INTER_CUBIC, fixed point, 2^15),
+ * device memory, 16-byte aligned.  lut: device uint8 [256] applied to the warped bytes, or NULL.  Outputs as in
+ * tvs_preproc_image_u8 (mean255 / inv_std255: HOST pointers to 3 floats).  All device arithmetic is integer: the uint8
+ * result equals cv2's bit for bit (oracle/augment.py, pinned to cv2).
+ * tvs_lut_normalize_u8: img uint8 [H, W, 3] -> lut (or NULL) -> (x - mean255) * inv_std255 -> f32 [3, H, W].
+ * ------------------------------------------------------------------------------------------------ */
+int tvs_warp_affine_u8(const uint8_t* img, int32_t Hi, int32_t Wi, int64_t ld_bytes, const int32_t* adelta,
+                       const int32_t* bdelta, const int32_t* x0, const int32_t* y0, const int16_t* tab,
+                       const uint8_t* lut, const float* mean255, const float* inv_std255, int32_t Ho, int32_t Wo,
+                       float* out_chw, uint8_t* out_u8_hwc, void* stream);
+int tvs_warp_affine_nearest_f32(const float* in, int32_t Hi, int32_t Wi, int64_t ld, const int32_t* adelta,
+                                const int32_t* bdelta, const int32_t* x0, const int32_t* y0, int32_t Ho, int32_t Wo,
+                                float* out, void* stream);
+int tvs_lut_normalize_u8(const uint8_t* img, int32_t H, int32_t W, int64_t ld_bytes, const uint8_t* lut,
+                         const float* mean255, const float* inv_std255, float* out_chw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     lib.tvs_version.restype = ctypes.c_int
-    assert lib.tvs_version() == 2          # TVS_ABI_VERSION (round 2: operand-format flags on attention / im2col)
+    assert lib.tvs_version() == 3          # TVS_ABI_VERSION (3: train-time augmentation entries)
     abi.load()      # argtypes for every entry resolve
 
 

@@ -62,3 +62,74 @@ def test_eval_transforms_reject_bad_inputs():
         t.image(np.zeros((8, 8, 3), dtype=np.float32))
     with pytest.raises(ValueError):
         t.mask(np.zeros((8, 8, 2), dtype=np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# train-time augmentations (clipseg.yaml:80-111): cv2.warpAffine / LUT on the device, bit-exact against the cv2-pinned oracle
+# ---------------------------------------------------------------------------------------------------------------------
+AUG_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augment_cv2.npz")
+
+
+@pytest.mark.parametrize("hi,wi,size,wide", [(480, 640, 352, False), (352, 352, 352, False), (333, 517, 416, False), (97, 131, 64, True),
+                                             (37, 53, 48, True), (5, 3, 16, True)])
+def test_train_transforms_match_oracle_bit_exact(hi, wi, size, wide):
+    from oracle import augment as OA
+    from tunevlseg_b200.data import GpuTrainTransforms
+
+    rng = np.random.default_rng(hi * 31 + wi)
+    img = rng.integers(0, 256, (hi, wi, 3), dtype=np.uint8)
+    mask = (rng.random((hi, wi)) < 0.3).astype(np.float32)
+    t = GpuTrainTransforms(size, MEAN, STD, seed=1)
+    resized, rmask = OP.resize_cubic_u8(img, size, size), OP.resize_nearest(mask, size, size)
+    for trial in range(3):
+        if wide:
+            M = OA.affine_matrix(size, size, rng.uniform(0.6, 1.5), rng.uniform(0.6, 1.5), rng.uniform(-0.2, 0.2) * size, rng.uniform(-0.2, 0.2) * size,
+                                 rng.uniform(-180, 180))
+        else:
+            M = OA.affine_matrix(size, size, rng.uniform(0.98, 1.02), rng.uniform(0.98, 1.02), rng.uniform(-0.02, 0.02) * size,
+                                 rng.uniform(-0.02, 0.02) * size, rng.uniform(-5, 5))
+        lut = OA.brightness_contrast_lut(1.0 + rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1))
+        for use_m, use_l in ((True, True), (True, False), (False, True), (False, False)):
+            out = t.apply(img, mask, M if use_m else None, lut if use_l else None)
+            u8 = OA.warp_affine_cubic_u8(resized, M[:2], (size, size)) if use_m else resized
+            u8 = OA.apply_lut(u8, lut) if use_l else u8
+            ref_mask = OA.warp_affine_nearest(rmask, M[:2], (size, size)) if use_m else rmask
+            assert np.array_equal(out["image"].cpu().numpy(), OP.normalize_chw(u8, MEAN, STD)), (trial, use_m, use_l)
+            assert np.array_equal(out["mask"].cpu().numpy()[0], ref_mask), (trial, use_m, use_l)
+
+
+def test_warp_affine_against_committed_cv2_vectors_and_u8_output():
+    from tunevlseg_b200 import abi
+    from tunevlseg_b200.data import affine_walk_tables, warp_cubic_table
+
+    g = np.load(AUG_GOLDEN)
+    tab = torch.from_numpy(warp_cubic_table()).cuda()
+    for i in range(int(g["n"])):
+        img, mask, M, lut = g[f"{i}/image"], g[f"{i}/mask"], g[f"{i}/matrix"], g[f"{i}/lut"]
+        h, w = img.shape[:2]
+        walk = tuple(torch.from_numpy(a).cuda() for a in affine_walk_tables(M, (w, h), False))
+        u8 = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+        abi.warp_affine_u8(torch.from_numpy(img).cuda(), walk, tab, out_u8=u8)
+        assert np.array_equal(u8.cpu().numpy(), g[f"{i}/cubic"]), i                     # cv2.warpAffine's own bytes
+        abi.warp_affine_u8(torch.from_numpy(img).cuda(), walk, tab, lut=torch.from_numpy(lut).cuda(), out_u8=u8)
+        assert np.array_equal(u8.cpu().numpy(), g[f"{i}/lut"][g[f"{i}/cubic"]]), i
+        walk_n = tuple(torch.from_numpy(a).cuda() for a in affine_walk_tables(M, (w, h), True))
+        out = torch.empty((h, w), dtype=torch.float32, device="cuda")
+        abi.warp_affine_nearest_f32(torch.from_numpy(mask).cuda(), walk_n, out)
+        assert np.array_equal(out.cpu().numpy(), g[f"{i}/nearest"]), i
+
+
+def test_train_transforms_draw_ranges_and_call_signature():
+    from tunevlseg_b200.data import GpuTrainTransforms
+
+    t = GpuTrainTransforms(64, MEAN, STD, seed=3, affine_p=1.0, brightness_contrast_p=1.0)
+    p = t.draw()
+    assert p["matrix"].shape == (3, 3) and p["lut"].shape == (256,) and p["lut"].dtype == np.uint8
+    s = np.linalg.svd(p["matrix"][:2, :2], compute_uv=False)
+    assert 0.979 <= s.min() and s.max() <= 1.021 and abs(p["matrix"][0, 2]) < 64 * 0.2
+    rng = np.random.default_rng(0)
+    out = t(image=rng.integers(0, 256, (80, 90, 3), dtype=np.uint8), mask=(rng.random((80, 90, 1)) < 0.5).astype(np.float32))
+    assert out["image"].shape == (3, 64, 64) and out["mask"].shape == (1, 64, 64) and out["image"].is_cuda
+    assert set(np.unique(out["mask"].cpu().numpy())) <= {0.0, 1.0}
+    never = GpuTrainTransforms(64, MEAN, STD, seed=3, affine_p=0.0, brightness_contrast_p=0.0).draw()
+    assert never["matrix"] is None and never["lut"] is None

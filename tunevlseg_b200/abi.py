@@ -109,6 +109,9 @@ def load():
         "tvs_ffn64_bwd": [P, P, P, P, P, P, P, I64, I32, I32, P, P],
         "tvs_preproc_image_u8": [P, I32, I32, I64, P, P, P, P, P, P, I32, I32, P, P, P],
         "tvs_resize_nearest_f32": [P, I32, I32, I64, P, P, I32, I32, P, P],
+        "tvs_warp_affine_u8": [P, I32, I32, I64, P, P, P, P, P, P, P, P, I32, I32, P, P, P],
+        "tvs_warp_affine_nearest_f32": [P, I32, I32, I64, P, P, P, P, I32, I32, P, P],
+        "tvs_lut_normalize_u8": [P, I32, I32, I64, P, P, P, P, P],
         "tvs_resample2d_fwd": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, I32, P, P],
         "tvs_resample2d_u8": [P, I32, I32, I32, I32, I32, P, P, P, P, I32, P, P],
         "tvs_resample2d_bwd": [P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, I32, I32, P, P],
@@ -800,3 +803,77 @@ def resize_nearest_f32(x, xofs, yofs, out):
         raise TvsError(f"resize_nearest_f32: out must be {(Ho, Wo)}")
     _ck(load().tvs_resize_nearest_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), xofs.data_ptr(), yofs.data_ptr(), Ho, Wo,
                                       out.data_ptr(), _stream()), "tvs_resize_nearest_f32")
+
+
+# ---- train-time augmentations (preprocess.cu) --------------------------------------------------------------------------------
+def _chk_hwc_u8(img_u8, what):
+    if not (img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.shape[2] == 3 and img_u8.stride(2) == 1
+            and img_u8.stride(1) == 3):
+        raise TvsError(f"{what}: image must be a CUDA uint8 HWC tensor with packed pixels, got {tuple(img_u8.shape)} {img_u8.dtype}")
+
+
+def _chk_walk(walk, what):
+    adelta, bdelta, x0, y0 = walk
+    for t in walk:
+        _chk(t, torch.int32, "walk table")
+    if adelta.numel() != bdelta.numel() or x0.numel() != y0.numel():
+        raise TvsError(f"{what}: walk tables must be (adelta [Wo], bdelta [Wo], x0 [Ho], y0 [Ho])")
+    return y0.numel(), adelta.numel()
+
+
+def warp_affine_u8(img_u8, walk, tab, mean255=None, inv_std255=None, lut=None, out_chw=None, out_u8=None):
+    """cv2.warpAffine(INTER_CUBIC, BORDER_REPLICATE) of a CUDA uint8 [Hi, Wi, 3] image.  walk = (adelta, bdelta, x0, y0) CUDA int32
+    tables of cv::warpAffine's fixed-point walk (rounding term 16 included); tab: CUDA int16 [32, 32, 4, 4] weight table;
+    lut: optional CUDA uint8 [256] applied to the warped bytes; out_chw f32 [3, Ho, Wo] (normalised) and / or out_u8 [Ho, Wo, 3]."""
+    require_device()
+    _chk_hwc_u8(img_u8, "warp_affine_u8")
+    Ho, Wo = _chk_walk(walk, "warp_affine_u8")
+    if not (tab.is_cuda and tab.dtype == torch.int16 and tab.numel() == 32 * 32 * 16 and tab.is_contiguous()):
+        raise TvsError("warp_affine_u8: tab must be a contiguous CUDA int16 [32, 32, 4, 4] tensor")
+    if lut is not None and not (lut.is_cuda and lut.dtype == torch.uint8 and lut.numel() == 256 and lut.is_contiguous()):
+        raise TvsError("warp_affine_u8: lut must be a contiguous CUDA uint8 [256] tensor")
+    if out_chw is None and out_u8 is None:
+        raise TvsError("warp_affine_u8: no output")
+    if out_chw is not None:
+        _chk(out_chw, torch.float32, "out_chw")
+        if tuple(out_chw.shape) != (3, Ho, Wo) or mean255 is None or inv_std255 is None:
+            raise TvsError(f"warp_affine_u8: out_chw must be {(3, Ho, Wo)} and needs mean255 / inv_std255")
+    if out_u8 is not None:
+        _chk(out_u8, torch.uint8, "out_u8")
+        if tuple(out_u8.shape) != (Ho, Wo, 3):
+            raise TvsError(f"warp_affine_u8: out_u8 must be {(Ho, Wo, 3)}, got {tuple(out_u8.shape)}")
+    m = (c_float * 3)(*[float(v) for v in (mean255 if mean255 is not None else (0, 0, 0))])
+    d = (c_float * 3)(*[float(v) for v in (inv_std255 if inv_std255 is not None else (1, 1, 1))])
+    Hi, Wi, _ = img_u8.shape
+    _ck(load().tvs_warp_affine_u8(img_u8.data_ptr(), Hi, Wi, img_u8.stride(0), walk[0].data_ptr(), walk[1].data_ptr(), walk[2].data_ptr(),
+                                  walk[3].data_ptr(), tab.data_ptr(), _p(lut), ctypes.cast(m, c_void_p), ctypes.cast(d, c_void_p), Ho, Wo,
+                                  _p(out_chw), _p(out_u8), _stream()), "tvs_warp_affine_u8")
+
+
+def warp_affine_nearest_f32(x, walk, out):
+    """cv2.warpAffine(INTER_NEAREST, BORDER_REPLICATE) of a CUDA f32 [Hi, Wi] mask; walk tables with the rounding term 512."""
+    require_device()
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1):
+        raise TvsError("warp_affine_nearest_f32: x must be a CUDA f32 [H, W] tensor with unit inner stride")
+    Ho, Wo = _chk_walk(walk, "warp_affine_nearest_f32")
+    _chk(out, torch.float32, "out")
+    if tuple(out.shape) != (Ho, Wo):
+        raise TvsError(f"warp_affine_nearest_f32: out must be {(Ho, Wo)}")
+    _ck(load().tvs_warp_affine_nearest_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), walk[0].data_ptr(), walk[1].data_ptr(),
+                                           walk[2].data_ptr(), walk[3].data_ptr(), Ho, Wo, out.data_ptr(), _stream()), "tvs_warp_affine_nearest_f32")
+
+
+def lut_normalize_u8(img_u8, lut, mean255, inv_std255, out_chw):
+    """(lut[img] - mean255) * inv_std255 -> f32 [3, H, W]; img CUDA uint8 [H, W, 3], lut CUDA uint8 [256] or None."""
+    require_device()
+    _chk_hwc_u8(img_u8, "lut_normalize_u8")
+    if lut is not None and not (lut.is_cuda and lut.dtype == torch.uint8 and lut.numel() == 256 and lut.is_contiguous()):
+        raise TvsError("lut_normalize_u8: lut must be a contiguous CUDA uint8 [256] tensor")
+    H, W, _ = img_u8.shape
+    _chk(out_chw, torch.float32, "out_chw")
+    if tuple(out_chw.shape) != (3, H, W):
+        raise TvsError(f"lut_normalize_u8: out_chw must be {(3, H, W)}")
+    m = (c_float * 3)(*[float(v) for v in mean255])
+    d = (c_float * 3)(*[float(v) for v in inv_std255])
+    _ck(load().tvs_lut_normalize_u8(img_u8.data_ptr(), H, W, img_u8.stride(0), _p(lut), ctypes.cast(m, c_void_p), ctypes.cast(d, c_void_p),
+                                    out_chw.data_ptr(), _stream()), "tvs_lut_normalize_u8")

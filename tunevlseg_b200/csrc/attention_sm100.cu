@@ -55,15 +55,21 @@ __device__ __forceinline__ void store_row_bf16_32(__nv_bfloat16* dst, const uint
     }
 }
 
+#ifndef ATC_BWD_STAGES
+#define ATC_BWD_STAGES 4
+#endif
 template <int MODE>
 struct AtcSmem {
     static constexpr int TI = 64;
     static constexpr int ITILE = TI * AHD * 2;
     static constexpr int N_OUTER = MODE == MODE_FWD ? 1 : 2;
+    // inner-tile ring.  Backward: FOUR stages - with two, the load of step it + 2 is only issued when step it retires and a
+    // step (~0.7 us of MMA + exponentials) is shorter than a TMA round trip under load, so every step waited for its tile
+    static constexpr int NST = MODE == MODE_FWD ? 2 : ATC_BWD_STAGES;
     static constexpr int OUTER = 0;
-    static constexpr int INNER = N_OUTER * ATILE;                 // 2 stages x 2 tiles
-    static constexpr int VEC = INNER + 4 * ITILE;                 // [2 stages][2][TI] floats (DKV: lse, delta)
-    static constexpr int BAR = VEC + 2 * 2 * TI * 4;
+    static constexpr int INNER = N_OUTER * ATILE;                 // NST stages x 2 tiles
+    static constexpr int VEC = INNER + NST * 2 * ITILE;           // [NST][2][TI] floats (DKV: lse, delta; DQ: 2 x 128 delta halves)
+    static constexpr int BAR = VEC + NST * 2 * TI * 4;
     static constexpr int TOTAL = BAR + 16 * 8 + 1024;             // barriers + tmem slot + alignment slack
 };
 
@@ -104,12 +110,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     float* s_vec = reinterpret_cast<float*>(smem + L::VEC);     // [stage][which][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
     uint64_t* outer_full = bars;
-    uint64_t* in_full = bars + 1;      // [2]
-    uint64_t* in_empty = bars + 3;     // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* ew_done = bars + 6;
-    uint64_t* acc_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    constexpr int NST = L::NST;
+    uint64_t* in_full = bars + 1;               // [NST]
+    uint64_t* in_empty = bars + 1 + NST;        // [NST]
+    uint64_t* s_full = bars + 1 + 2 * NST;
+    uint64_t* ew_done = s_full + 1;
+    uint64_t* acc_full = s_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+    static_assert((1 + 2 * NST + 4) * 8 <= 16 * 8, "barrier block too small");
 
     const int ot = blockIdx.x + ot0, h = blockIdx.y, b = blockIdx.z;     // ot0 > 0: only the outer tiles from ot0 on (tvs_attn_bwd_tail)
     const int E = H * AHD;
@@ -129,7 +137,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         tma_prefetch_desc(&map_qkv);
         if (MODE != MODE_FWD) tma_prefetch_desc(&map_do);
         mbar_init(outer_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&in_full[s], MODE == MODE_DKV ? 2 : 1);
             mbar_init(&in_empty[s], 1);
         }
@@ -162,7 +170,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             }
         }
         for (int it = 0; it < n_it; ++it) {
-            const int stage = it & 1, par = (it >> 1) & 1;
+            const int stage = it % NST, par = (it / NST) & 1;
             const int j = MODE == MODE_FWD ? it % n_in : it;
             uint8_t* t0 = s_inner + stage * 2 * ITILE;
             uint8_t* t1 = t0 + ITILE;
@@ -211,7 +219,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             const uint64_t a0 = umma_desc_sw128(smem_u32(s_outer0));
             const uint64_t a1 = umma_desc_sw128(smem_u32(s_outer1));
             for (int it = 0; it < n_it; ++it) {
-                const int stage = it & 1, par = (it >> 1) & 1;
+                const int stage = it % NST, par = (it / NST) & 1;
                 mbar_wait(&in_full[stage], par);
                 tc_fence_after();
                 const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE));
@@ -398,7 +406,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
                 const int c0 = it * TI + 32 * half;          // first inner row of this half (key for DQ, query for DKV)
-                const float* v_lse = s_vec + (it & 1) * 2 * TI + 32 * half;
+                const float* v_lse = s_vec + (it % NST) * 2 * TI + 32 * half;
                 const float* v_del = v_lse + TI;
                 uint32_t sA[32], dA[32];
                 tmem_ld32(tS, sA);
