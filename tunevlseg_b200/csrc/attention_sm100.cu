@@ -35,6 +35,28 @@ constexpr int ATC_THREADS = 192;
 constexpr float L2E = 1.4426950408889634f;
 enum { MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2 };
 
+// ATC_EXPERIMENT == 8: per-CTA timeline of the backward kernels (tools/microbench/attn_timeline.cu reads it back): the CTAs
+// (ot, h, b) = (0..1, 0, 0) log (clock64, event, warp, iteration) at every hand-off.  Not compiled into the product.
+#ifndef ATC_EXPERIMENT
+#define ATC_EXPERIMENT 0
+#endif
+#if ATC_EXPERIMENT == 8
+// [mode 0..2][cta 0..1][warp 0..9][128 events][2]: every warp owns its slots (no atomics: a returning atomic would stall the warp
+// for an L2 round trip at every event); stores are fire-and-forget
+__device__ unsigned long long g_tl[3 * 2 * 10 * 128 * 2];
+#define TL(ev, it)                                                                                                          \
+    do {                                                                                                                    \
+        if (blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 2 && (threadIdx.x & 31) == 0 && tl_n < 128) {                \
+            unsigned long long* p_ = g_tl + ((((MODE * 2 + blockIdx.x) * 10 + (threadIdx.x >> 5)) * 128 + tl_n) << 1);      \
+            p_[0] = clock64();                                                                                              \
+            p_[1] = ((unsigned long long)(ev) << 16) | ((it) & 255) | (1ull << 40);                                         \
+            ++tl_n;                                                                                                         \
+        }                                                                                                                   \
+    } while (0)
+#else
+#define TL(ev, it) do { } while (0)
+#endif
+
 __device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2, flushes denormals; exp2(-inf) = 0
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -56,15 +78,15 @@ __device__ __forceinline__ void store_row_bf16_32(__nv_bfloat16* dst, const uint
 }
 
 #ifndef ATC_BWD_STAGES
-#define ATC_BWD_STAGES 4
+#define ATC_BWD_STAGES 2
 #endif
 template <int MODE>
 struct AtcSmem {
     static constexpr int TI = 64;
     static constexpr int ITILE = TI * AHD * 2;
     static constexpr int N_OUTER = MODE == MODE_FWD ? 1 : 2;
-    // inner-tile ring.  Backward: FOUR stages - with two, the load of step it + 2 is only issued when step it retires and a
-    // step (~0.7 us of MMA + exponentials) is shorter than a TMA round trip under load, so every step waited for its tile
+    // inner-tile ring depth.  Measured (round 2, B = 32, S = 489): 2 / 3 / 4 stages = 171.5 / 175.0 / 173.0 us for the backward
+    // pair - the kernels do not wait for their tiles, so the default stays at two stages (ATC_BWD_STAGES to A/B)
     static constexpr int NST = MODE == MODE_FWD ? 2 : ATC_BWD_STAGES;
     static constexpr int OUTER = 0;
     static constexpr int INNER = N_OUTER * ATILE;                 // NST stages x 2 tiles
@@ -102,6 +124,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out,
                const float* __restrict__ lse_in, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv, int ot0, int o_f16) {
     using L = AtcSmem<MODE>;
+#if ATC_EXPERIMENT == 8
+    unsigned tl_n = 0;
+#endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* s_outer0 = smem + L::OUTER;
@@ -142,7 +167,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             mbar_init(&in_empty[s], 1);
         }
         mbar_init(s_full, 1);
+#if ATC_EXPERIMENT == 1 || ATC_EXPERIMENT == 4
+        mbar_init(ew_done, MODE == MODE_FWD ? EW_WARPS * 32 : EW_WARPS);
+#else
         mbar_init(ew_done, EW_WARPS * 32);
+#endif
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -153,6 +182,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     const uint32_t tb = *tmem_slot;
     pdl_wait();        // set-up above is private; q / k / v (and dO, lse, delta) come from the preceding kernels
     pdl_trigger();
+    TL(30, 0);
 
     if (warp == W_TMA) {
         // ------------------------------------------------------------------ TMA producer
@@ -175,6 +205,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             uint8_t* t0 = s_inner + stage * 2 * ITILE;
             uint8_t* t1 = t0 + ITILE;
             mbar_wait(&in_empty[stage], par ^ 1);       // whole warp, converged: uniform loop state
+            TL(20, it);
             if (elect_one()) {
                 if (MODE == MODE_FWD) {
                     const bool second = it >= n_in;
@@ -216,12 +247,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
             auto PK = [](int k) -> uint32_t { return k < 2 ? 8u * k : 32u + 8u * (k - 2); };
             mbar_wait(outer_full, 0);
             tc_fence_after();
+            TL(31, 0);
             const uint64_t a0 = umma_desc_sw128(smem_u32(s_outer0));
             const uint64_t a1 = umma_desc_sw128(smem_u32(s_outer1));
             for (int it = 0; it < n_it; ++it) {
                 const int stage = it % NST, par = (it / NST) & 1;
                 mbar_wait(&in_full[stage], par);
                 tc_fence_after();
+                TL(1, it);
                 const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE));
                 const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE + ITILE));
                 const bool last = it == n_it - 1;
@@ -258,8 +291,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                         umma_commit(s_full);
                     }
                     __syncwarp();
+                    TL(2, it);
+#if ATC_EXPERIMENT != 7
                     mbar_wait(ew_done, it & 1);
+#endif
                     tc_fence_after();
+                    TL(3, it);
                     if (elect_one()) {
                         if (MODE == MODE_DQ) {
 #pragma unroll
@@ -277,6 +314,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                         if (last) umma_commit(acc_full);
                     }
                     __syncwarp();
+                    TL(4, it);
                 }
             }
         }
@@ -402,16 +440,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 }
             }
             const uint32_t tS = tl + C_S + 32 * half, tD = tl + C_DP + 32 * half;
+            TL(9, 0);
             for (int it = 0; it < n_it; ++it) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
+                TL(10, it);
                 const int c0 = it * TI + 32 * half;          // first inner row of this half (key for DQ, query for DKV)
                 const float* v_lse = s_vec + (it % NST) * 2 * TI + 32 * half;
                 const float* v_del = v_lse + TI;
                 uint32_t sA[32], dA[32];
+#if ATC_EXPERIMENT == 6
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { sA[i] = it + i; dA[i] = it - i; }
+#else
                 tmem_ld32(tS, sA);
                 tmem_ld32(tD, dA);
                 tmem_ld_wait();
+#endif
+                TL(11, it);
                 uint32_t pkp[16], pks[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -422,7 +468,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                     // p and dS multiply zeros in dQ += dS K; a key ROW past the end (DKV) only feeds dK / dV rows that are never
                     // stored; a query past the end has lse = +inf, hence p = dS = 0.  (The masks cost ~3 of ~9 issue slots per
                     // score, and the element-wise warps are issue-bound: ncu round 2.)
+#if ATC_EXPERIMENT >= 2      // timing experiments only (results are wrong)
+                    p0 = fmaf(s0, L2E, -my_lse); p1 = fmaf(s1, L2E, -my_lse); d0 = p0 * (g0 - my_del); d1 = p1 * (g1 - my_del);
+                    if (false) {
+#else
                     if (MODE == MODE_DQ) {
+#endif
                         p0 = fast_exp2(fmaf(s0, L2E, -my_lse));
                         p1 = fast_exp2(fmaf(s1, L2E, -my_lse));
                         d0 = p0 * (g0 - my_del);
@@ -435,10 +486,356 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                         d0 = p0 * (g0 - e2.x);
                         d1 = p1 * (g1 - e2.y);
                     }
+#if ATC_EXPERIMENT >= 3
+                    pks[i / 2] = sA[i] ^ dA[i + 1]; pkp[i / 2] = sA[i + 1] ^ dA[i];
+                    if (false)
+#endif
+                    {
+                        pks[i / 2] = pack_bf16x2(d0, d1);
+                        if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
+                    }
+                }
+                // the packed values overwrite the first 16 of the 32 columns this thread has just read (both loads completed)
+#if ATC_EXPERIMENT == 5 || ATC_EXPERIMENT == 6
+                if (pks[3] == 0x12345678u && pkp[5] == 0x9abcdef0u) tmem_st16(tS, pks);
+                else if (false)
+#endif
+                if (MODE == MODE_DQ) {
+                    tmem_st16(tS, pks);          // dS
+                } else {
+                    tmem_st16(tS, pkp);          // P^T
+                    tmem_st16(tD, pks);          // dS^T
+                }
+                TL(12, it);
+                tmem_st_wait();
+                tc_fence_before();
+                TL(13, it);
+#if ATC_EXPERIMENT == 1 || ATC_EXPERIMENT == 4
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ew_done);
+#else
+                mbar_arrive(ew_done);
+#endif
+            }
+            TL(14, n_it);
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            TL(32, 0);
+            uint32_t a0[32];
+            tmem_ld32(tl + C_ACC0 + 32 * half, a0);
+            tmem_ld_wait();
+            const long long tok = static_cast<long long>(b) * S + row;
+            __nv_bfloat16* drow = dqkv + tok * 3 * E + h * AHD + 32 * half;
+            if (MODE == MODE_DQ) {
+                if (row_ok) store_row_bf16_32(drow, a0);
+            } else {
+                if (row_ok) store_row_bf16_32(drow + 2 * E, a0);     // dV
+                tmem_ld32(tl + C_ACC1 + 32 * half, a0);
+                tmem_ld_wait();
+                if (row_ok) store_row_bf16_32(drow + E, a0);         // dK
+            }
+        }
+    }
+
+    TL(33, 0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tb, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, PERSISTENT version (round 2, the default).  A per-CTA timeline of attn_tc_kernel<DQ|DKV> (clock64 stamps at every
+// hand-off, tools/microbench/attn_timeline.cu) showed where its 172 us per layer go: a CTA lives ~23.7 k clk, of which ~5 k
+// pass before its first MMA (tensor-map fetch + the TMA round trip of the outer tiles, with all 296 resident CTAs asking at
+// once) and ~1 k in the epilogue - a quarter of every CTA's life with the tensor pipe and the exponential units idle, six
+// rounds of CTAs per SM.  (Also measured there: a tcgen05.mma 128 x 64 x 16 with both operands in shared memory takes 48 clk,
+// not 32 - 6 KB of operand reads per instruction against 128 B/clk - so S / dP cost 384 clk per step and the pair of kernels
+// cannot go below ~50 us per layer; the TMEM read-out (515-740 B/clk/SM measured) and the MUFU (16 / clk) are not the bound.)
+// Here 2 x #SM CTAs stay resident and walk the (outer tile, head, sample) items round-robin: barriers, TMEM and tensor maps are
+// set up once, the outer tiles are double-buffered and those of item k + 1 are requested while item k computes, the inner ring
+// never drains between items, and the accumulator read-out of item k overlaps the first S / dP MMAs of item k + 1.
+// Same arithmetic, same operand layouts and the same per-item instruction order as attn_tc_kernel, so results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+#ifndef ATC_BWDP_STAGES
+#define ATC_BWDP_STAGES 2
+#endif
+struct BwdPSmem {
+    static constexpr int TI = 64;
+    static constexpr int ITILE = TI * AHD * 2;                    // 8 KB
+    static constexpr int NST = ATC_BWDP_STAGES;
+    static constexpr int OUTER = 0;                               // [2 buffers][2 tiles] of ATILE
+    static constexpr int INNER = 4 * ATILE;                       // [NST][2 tiles] of ITILE
+    static constexpr int VEC = INNER + NST * 2 * ITILE;           // DKV: [NST][2][TI] floats (lse, delta); DQ: [2][128] delta halves
+    static constexpr int VEC_BYTES = (NST * 2 * TI > 2 * AT ? NST * 2 * TI : 2 * AT) * 4;
+    static constexpr int BAR = VEC + VEC_BYTES;
+    static constexpr int NBAR = 4 + 2 * NST + 3;                  // outer_full[2], outer_empty[2], in_full / in_empty[NST], s_full, ew_done, acc_full
+    static constexpr int TOTAL = BAR + (NBAR + 1) * 8 + 1024;     // barriers + tmem slot + alignment slack
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(ATC_THREADS_BWD, 2)
+attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                    const __grid_constant__ CUtensorMap map_qkv_in, const __grid_constant__ CUtensorMap map_do_in, int S, int H, int n_ot,
+                    int n_items, const __nv_bfloat16* __restrict__ out, float* __restrict__ delta_out, const float* __restrict__ lse_in,
+                    const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv, int ot0, int o_f16) {
+    static_assert(MODE == MODE_DQ || MODE == MODE_DKV, "backward modes only");
+    using L = BwdPSmem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* s_outer = smem + L::OUTER;                         // buffer u: tile0 at u*2*ATILE, tile1 at +ATILE
+    uint8_t* s_inner = smem + L::INNER;                         // stage s: tile0 at s*2*ITILE, tile1 at +ITILE
+    float* s_vec = reinterpret_cast<float*>(smem + L::VEC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+    constexpr int NST = L::NST, TI = L::TI, ITILE = L::ITILE;
+    uint64_t* outer_full = bars;                // [2]
+    uint64_t* outer_empty = bars + 2;           // [2]
+    uint64_t* in_full = bars + 4;               // [NST]
+    uint64_t* in_empty = bars + 4 + NST;        // [NST]
+    uint64_t* s_full = bars + 4 + 2 * NST;
+    uint64_t* ew_done = s_full + 1;
+    uint64_t* acc_full = s_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+
+    const int E = H * AHD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int EW_WARPS = 8, W_TMA = EW_WARPS, W_MMA = EW_WARPS + 1;
+    const int n_in = (S + TI - 1) / TI;
+    constexpr uint32_t TMEM_COLS = 256;
+    constexpr uint32_t C_S = 0, C_DP = TI, C_ACC0 = 128, C_ACC1 = 192;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_qkv);
+        tma_prefetch_desc(&map_do);
+        tma_prefetch_desc(&map_qkv_in);
+        tma_prefetch_desc(&map_do_in);
+        for (int u = 0; u < 2; ++u) {
+            mbar_init(&outer_full[u], 1);
+            mbar_init(&outer_empty[u], 1);
+        }
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&in_full[s], MODE == MODE_DKV ? 2 : 1);
+            mbar_init(&in_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(ew_done, EW_WARPS * 32);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tmem_slot;
+    pdl_wait();        // set-up above is private; q / k / v, dO, lse (and delta) come from the preceding kernels
+    pdl_trigger();
+
+    // item w -> (outer tile, head, sample); the outer tile runs fastest so that neighbouring CTAs share K / V (or Q / dO) in L2
+    auto item = [&](int w, int& ot, int& h, int& b) {
+        ot = ot0 + w % n_ot;
+        const int hb = w / n_ot;
+        h = hb % H;
+        b = hb / H;
+    };
+
+    if (warp == W_TMA) {
+        // ------------------------------------------------------------------ TMA producer
+        auto load_outer = [&](int k, int w) {          // outer tiles of the k-th item of this CTA into buffer k & 1
+            int ot, h, b;
+            item(w, ot, h, b);
+            const int u = k & 1;
+            mbar_wait(&outer_empty[u], ((k >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                uint8_t* o0 = s_outer + u * 2 * ATILE;
+                mbar_expect_tx(&outer_full[u], 2 * ATILE);
+                if (MODE == MODE_DQ) {
+                    tma_load_3d(o0, &map_qkv, h * AHD, ot * AT, b, &outer_full[u]);
+                    tma_load_3d(o0 + ATILE, &map_do, h * AHD, ot * AT, b, &outer_full[u]);
+                } else {
+                    tma_load_3d(o0, &map_qkv, E + h * AHD, ot * AT, b, &outer_full[u]);
+                    tma_load_3d(o0 + ATILE, &map_qkv, 2 * E + h * AHD, ot * AT, b, &outer_full[u]);
+                }
+            }
+            __syncwarp();
+        };
+        int g = 0, k = 0;
+        if (static_cast<int>(blockIdx.x) < n_items) load_outer(0, blockIdx.x);
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++k) {
+            int ot, h, b;
+            item(w, ot, h, b);
+            const long long bh = static_cast<long long>(b) * H + h;
+            const int cq = h * AHD, ck = E + h * AHD, cv = 2 * E + h * AHD;
+            const int w_next = w + gridDim.x;
+            bool prefetched = w_next >= n_items;
+            for (int it = 0; it < n_in; ++it, ++g) {
+                const int stage = g % NST, par = (g / NST) & 1;
+                uint8_t* t0 = s_inner + stage * 2 * ITILE;
+                uint8_t* t1 = t0 + ITILE;
+                mbar_wait(&in_empty[stage], par ^ 1);       // whole warp, converged: uniform loop state
+                if (elect_one()) {
+                    mbar_expect_tx(&in_full[stage], 2 * ITILE);
+                    if (MODE == MODE_DQ) {
+                        tma_load_3d(t0, &map_qkv_in, ck, it * TI, b, &in_full[stage]);
+                        tma_load_3d(t1, &map_qkv_in, cv, it * TI, b, &in_full[stage]);
+                    } else {
+                        tma_load_3d(t0, &map_qkv_in, cq, it * TI, b, &in_full[stage]);
+                        tma_load_3d(t1, &map_do_in, h * AHD, it * TI, b, &in_full[stage]);
+                    }
+                }
+                if (MODE == MODE_DKV) {
+                    __syncwarp();
+                    float* v_lse = s_vec + stage * 2 * TI;
+                    float* v_del = v_lse + TI;
+#pragma unroll
+                    for (int c = 0; c < TI / 32; ++c) {
+                        const int qi = lane + 32 * c, q = it * TI + qi;
+                        v_lse[qi] = q < S ? lse_in[bh * S + q] * L2E : INFINITY;
+                        v_del[qi] = q < S ? delta_in[bh * S + q] : 0.f;
+                    }
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(&in_full[stage]);
+                }
+                __syncwarp();
+                // once the ring has wrapped inside this item the previous item has retired (its last MMAs released the stage we
+                // have just been given), so its outer buffer is free: ask for the next item's outer tiles now, a whole item ahead
+                if (!prefetched && it == NST) {
+                    load_outer(k + 1, w_next);
+                    prefetched = true;
+                }
+            }
+            if (!prefetched) load_outer(k + 1, w_next);      // short sequences: may wait for this item's MMAs
+        }
+    } else if (warp == W_MMA) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_s = umma_idesc_bf16(AT, TI, 0, 0);
+        constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
+        auto PK = [](int kk) -> uint32_t { return kk < 2 ? 8u * kk : 32u + 8u * (kk - 2); };
+        int g = 0, k = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++k) {
+            const int u = k & 1;
+            mbar_wait(&outer_full[u], (k >> 1) & 1);
+            tc_fence_after();
+            const uint64_t a0 = umma_desc_sw128(smem_u32(s_outer + u * 2 * ATILE));
+            const uint64_t a1 = umma_desc_sw128(smem_u32(s_outer + u * 2 * ATILE + ATILE));
+            for (int it = 0; it < n_in; ++it, ++g) {
+                const int stage = g % NST, par = (g / NST) & 1;
+                mbar_wait(&in_full[stage], par);
+                tc_fence_after();
+                const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE));
+                const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE + ITILE));
+                const bool last = it == n_in - 1;
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_ss(tb + C_S, a0 + 2 * kk, b0 + 2 * kk, idesc_s, kk > 0);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_ss(tb + C_DP, a1 + 2 * kk, b1 + 2 * kk, idesc_s, kk > 0);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+                // ew_done of step (k, 0) also tells that the element-wise warps have read the accumulators of item k - 1 out of
+                // TMEM (their epilogue precedes this step in program order), so the first accumulate MMA may overwrite them
+                mbar_wait(ew_done, g & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    if (MODE == MODE_DQ) {
+#pragma unroll
+                        for (int kk = 0; kk < TI / 16; ++kk)   // dQ += dS K_j
+                            umma_ts(tb + C_ACC0, tb + C_S + PK(kk), b0 + 128 * kk, idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < TI / 16; ++kk)   // dV += P^T dO_i
+                            umma_ts(tb + C_ACC0, tb + C_S + PK(kk), b1 + 128 * kk, idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int kk = 0; kk < TI / 16; ++kk)   // dK += dS^T Q_i
+                            umma_ts(tb + C_ACC1, tb + C_DP + PK(kk), b0 + 128 * kk, idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&in_empty[stage]);
+                    if (last) {
+                        umma_commit(acc_full);
+                        umma_commit(&outer_empty[u]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ element-wise stage (see attn_tc_kernel)
+        const int quarter = warp & 3, half = warp >> 2;
+        const int tid = quarter * 32 + lane;
+        const uint32_t tl = tb + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t tS = tl + C_S + 32 * half, tD = tl + C_DP + 32 * half;
+        int g = 0, k = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++k) {
+            int ot, h, b;
+            item(w, ot, h, b);
+            const long long bh = static_cast<long long>(b) * H + h;
+            const int row = ot * AT + tid;
+            const bool row_ok = row < S;
+            const int u = k & 1;
+            const float my_lse = (MODE == MODE_DQ && row_ok) ? lse_in[bh * S + row] * L2E : INFINITY;
+            float my_del = 0.f;
+            if (MODE == MODE_DQ) {
+                if (out != nullptr) {
+                    // delta = rowsum(dO o O) from the swizzled dO tile of this item and the O row in global memory (attn_tc_kernel)
+                    mbar_wait(&outer_full[u], (k >> 1) & 1);
+                    const uint8_t* s_do = s_outer + u * 2 * ATILE + ATILE;
+                    float part = 0.f;
+                    const long long tok = static_cast<long long>(b) * S + (row_ok ? row : 0);
+                    const uint4* orow = reinterpret_cast<const uint4*>(out + tok * E + h * AHD + 32 * half);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int chunk = 4 * half + c;
+                        const uint4 gq = *reinterpret_cast<const uint4*>(s_do + tid * 128 + ((chunk ^ (tid & 7)) << 4));
+                        const uint4 o = row_ok ? orow[c] : make_uint4(0u, 0u, 0u, 0u);
+                        const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 a = unpack_bf16x2(gw[i]), bb = o_f16 ? unpack_f16x2(ow[i]) : unpack_bf16x2(ow[i]);
+                            part = fmaf(a.x, bb.x, part);
+                            part = fmaf(a.y, bb.y, part);
+                        }
+                    }
+                    s_vec[half * AT + tid] = part;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    my_del = s_vec[tid] + s_vec[AT + tid];
+                    if (half == 0 && row_ok) delta_out[bh * S + row] = my_del;      // the dK / dV kernel that follows reads it
+                } else if (row_ok) {
+                    my_del = delta_in[bh * S + row];
+                }
+            }
+            for (int it = 0; it < n_in; ++it, ++g) {
+                mbar_wait(s_full, g & 1);
+                tc_fence_after();
+                const float* v_lse = s_vec + (g % NST) * 2 * TI + 32 * half;
+                const float* v_del = v_lse + TI;
+                uint32_t sA[32], dA[32];
+                tmem_ld32(tS, sA);
+                tmem_ld32(tD, dA);
+                tmem_ld_wait();
+                uint32_t pkp[16], pks[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float s0 = __uint_as_float(sA[i]), s1 = __uint_as_float(sA[i + 1]);
+                    const float g0 = __uint_as_float(dA[i]), g1 = __uint_as_float(dA[i + 1]);
+                    float p0, p1, d0, d1;
+                    if (MODE == MODE_DQ) {
+                        p0 = fast_exp2(fmaf(s0, L2E, -my_lse));
+                        p1 = fast_exp2(fmaf(s1, L2E, -my_lse));
+                        d0 = p0 * (g0 - my_del);
+                        d1 = p1 * (g1 - my_del);
+                    } else {
+                        const float2 l2 = *reinterpret_cast<const float2*>(v_lse + i);
+                        const float2 e2 = *reinterpret_cast<const float2*>(v_del + i);
+                        p0 = fast_exp2(fmaf(s0, L2E, -l2.x));
+                        p1 = fast_exp2(fmaf(s1, L2E, -l2.y));
+                        d0 = p0 * (g0 - e2.x);
+                        d1 = p1 * (g1 - e2.y);
+                    }
                     pks[i / 2] = pack_bf16x2(d0, d1);
                     if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
                 }
-                // the packed values overwrite the first 16 of the 32 columns this thread has just read (both loads completed)
                 if (MODE == MODE_DQ) {
                     tmem_st16(tS, pks);          // dS
                 } else {
@@ -449,7 +846,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 tc_fence_before();
                 mbar_arrive(ew_done);
             }
-            mbar_wait(acc_full, 0);
+            mbar_wait(acc_full, k & 1);
             tc_fence_after();
             uint32_t a0[32];
             tmem_ld32(tl + C_ACC0 + 32 * half, a0);
@@ -464,6 +861,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
                 tmem_ld_wait();
                 if (row_ok) store_row_bf16_32(drow + E, a0);         // dK
             }
+            tc_fence_before();      // orders these TMEM reads before the ew_done arrive of the next item's first step
         }
     }
 
@@ -1272,6 +1670,26 @@ static int launch_bwd2(const CUtensorMap& mq, const CUtensorMap& md, const CUten
     return check_launch(MODE == MODE_DQ ? "attn_tc_bwd2_kernel<dq>" : "attn_tc_bwd2_kernel<dkv>");
 }
 
+template <int MODE>
+static int launch_bwdp(const CUtensorMap& mq, const CUtensorMap& md, const CUtensorMap& mqi, const CUtensorMap& mdi, int B, int S, int H,
+                       const __nv_bfloat16* out, float* delta_out, const float* lse_in, const float* delta_in, __nv_bfloat16* dqkv, cudaStream_t st,
+                       int ot0, int o_f16) {
+    auto kern = attn_tc_bwdp_kernel<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdPSmem::TOTAL));
+        attr_set = true;
+    }
+    const int n_ot = (S + AT - 1) / AT - ot0;
+    const long long n_items = static_cast<long long>(n_ot) * H * B;
+    TVS_REQUIRE(n_items < (1LL << 31), "attention backward: too many (tile, head, sample) items");
+    const int resident = 2 * sm_count();          // two CTAs per SM (TMEM: 2 x 256 columns; shared memory: 2 x ~99 KB)
+    dim3 grid(static_cast<unsigned>(n_items < resident ? n_items : resident));
+    TVS_CUDA(launch_pdl(kern, grid, dim3(ATC_THREADS_BWD), BwdPSmem::TOTAL, st, 1, mq, md, mqi, mdi, S, H, n_ot, static_cast<int>(n_items), out, delta_out,
+                        lse_in, delta_in, dqkv, ot0, o_f16));
+    return check_launch(MODE == MODE_DQ ? "attn_tc_bwdp_kernel<dq>" : "attn_tc_bwdp_kernel<dkv>");
+}
+
 // delta must already hold rowsum(dO o O)
 // row_begin > 0: dqkv is produced only for the 128-row tiles that contain rows >= row_begin (queries for dQ, keys for dK / dV)
 // out_o != nullptr (whole-sequence backward only): delta is computed by the dQ kernel from O and dO and written for the dK / dV kernel
@@ -1301,6 +1719,17 @@ int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const floa
     if (int rc = make_tmap3(&md, dout, H * AHD, S, B)) return rc;
     if (int rc = make_tmap3(&mqi, qkv, 3 * H * AHD, S, B, 64)) return rc;
     if (int rc = make_tmap3(&mdi, dout, H * AHD, S, B, 64)) return rc;
+    // default: the persistent kernels (attn_tc_bwdp_kernel); TVS_ATTN_BWD=1: one CTA per (tile, head, sample) as in round 1
+    static const bool v1 = [] { const char* e = getenv("TVS_ATTN_BWD"); return e && e[0] == '1'; }();
+    if (!v1) {
+        __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
+        if (out_o != nullptr && ot0 == 0) {      // dQ first: it produces delta on the way
+            if (int rc = launch_bwdp<MODE_DQ>(mq, md, mqi, mdi, B, S, H, static_cast<const __nv_bfloat16*>(out_o), delta, lse, delta, dq, st, 0, o_f16)) return rc;
+            return launch_bwdp<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, lse, delta, dq, st, 0, 0);
+        }
+        if (int rc = launch_bwdp<MODE_DKV>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, lse, delta, dq, st, ot0, 0)) return rc;
+        return launch_bwdp<MODE_DQ>(mq, md, mqi, mdi, B, S, H, nullptr, nullptr, lse, delta, dq, st, ot0, 0);
+    }
     if (out_o != nullptr && ot0 == 0) {
         // dQ first: it produces delta on the way; dK / dV (disjoint columns of dqkv) follow in the stream
         if (int rc = launch_atc<MODE_DQ>(mq, md, mqi, mdi, B, S, H, static_cast<__nv_bfloat16*>(const_cast<void*>(out_o)), delta, nullptr, lse, delta,
@@ -1313,3 +1742,17 @@ int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const floa
 }
 
 }  // namespace tvs
+
+#if ATC_EXPERIMENT == 8
+extern "C" __attribute__((visibility("default"))) int tvs_debug_timeline(unsigned long long* host, int max_words, int reset) {
+    const int words = 3 * 2 * 10 * 128 * 2;
+    cudaDeviceSynchronize();
+    if (host && max_words >= words) cudaMemcpyFromSymbol(host, tvs::g_tl, sizeof(unsigned long long) * words);
+    if (reset) {
+        void* p = nullptr;
+        cudaGetSymbolAddress(&p, tvs::g_tl);
+        cudaMemset(p, 0, sizeof(unsigned long long) * words);
+    }
+    return words;
+}
+#endif
