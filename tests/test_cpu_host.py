@@ -178,7 +178,8 @@ def test_install_as_src_resolves_reference_targets():
                    "src.models.core_models.coop.context_learner.MapleContextLearner",
                    "src.models.core_models.coop.context_learner.CoCoOpContextLearner",
                    "src.models.core_models.coop.context_learner.SharedSeparateLearner",
-                   "src.models.components.hf_clipseg_wrapper.HFCLIPSegWrapper"):
+                   "src.models.components.hf_clipseg_wrapper.HFCLIPSegWrapper",
+                   "src.data.components.data_collator.CustomDataCollatorWithPadding"):
         mod, _, attr = target.rpartition(".")
         assert hasattr(importlib.import_module(mod), attr), target
 

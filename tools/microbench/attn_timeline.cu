@@ -37,7 +37,7 @@ int main() {
         if (tvs_attn_bwd(qkv, out, dout, lse, B, S, H, hd, 0, nullptr, delta, dqkv, 0, nullptr)) { printf("bwd: %s\n", tvs_last_error()); return 1; }
     tvs_debug_timeline(nullptr, 0, 1);
     tvs_attn_bwd(qkv, out, dout, lse, B, S, H, hd, 0, nullptr, delta, dqkv, 0, nullptr);
-    const int words = 3 * 2 * 10 * 128 * 2;
+    const int words = 3 * 2 * 10 * 512 * 2;
     std::vector<unsigned long long> ev(words);
     tvs_debug_timeline(ev.data(), words, 1);
     struct E_ { unsigned long long t; int evt, warp, it; };
@@ -45,8 +45,8 @@ int main() {
         for (int cta = 0; cta < 2; ++cta) {
             std::vector<E_> c;
             for (int w = 0; w < 10; ++w)
-                for (int i = 0; i < 128; ++i) {
-                    const unsigned long long* p = &ev[size_t((((mode * 2 + cta) * 10 + w) * 128 + i)) * 2];
+                for (int i = 0; i < 512; ++i) {
+                    const unsigned long long* p = &ev[size_t((((mode * 2 + cta) * 10 + w) * 512 + i)) * 2];
                     if (!(p[1] >> 40)) break;
                     c.push_back({p[0], int((p[1] >> 16) & 0xffff), w, int(p[1] & 255)});
                 }

@@ -35,6 +35,14 @@ def install_as_src() -> None:
         mod = importlib.import_module(f"{__name__}.{n}")
         sys.modules[f"src.{n}"] = mod
     setattr(sys.modules["src"], "models", sys.modules["src.models"])
+    # collate_fn: _target_: src.data.components.data_collator.CustomDataCollatorWithPadding (configs/experiment/coop/clipseg.yaml:133-143)
+    import types
+    for n in ("data", "data.components"):
+        sys.modules.setdefault(f"src.{n}", types.ModuleType(f"src.{n}"))
+    sys.modules["src.data.components.data_collator"] = importlib.import_module(f"{__name__}.data.data_collator")
+    setattr(sys.modules["src"], "data", sys.modules["src.data"])
+    setattr(sys.modules["src.data"], "components", sys.modules["src.data.components"])
+    setattr(sys.modules["src.data.components"], "data_collator", sys.modules["src.data.components.data_collator"])
     _alias_monai_loss()
 
 

@@ -43,11 +43,11 @@ enum { MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2 };
 #if ATC_EXPERIMENT == 8
 // [mode 0..2][cta 0..1][warp 0..9][128 events][2]: every warp owns its slots (no atomics: a returning atomic would stall the warp
 // for an L2 round trip at every event); stores are fire-and-forget
-__device__ unsigned long long g_tl[3 * 2 * 10 * 128 * 2];
+__device__ unsigned long long g_tl[3 * 2 * 10 * 512 * 2];
 #define TL(ev, it)                                                                                                          \
     do {                                                                                                                    \
-        if (blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 2 && (threadIdx.x & 31) == 0 && tl_n < 128) {                \
-            unsigned long long* p_ = g_tl + ((((MODE * 2 + blockIdx.x) * 10 + (threadIdx.x >> 5)) * 128 + tl_n) << 1);      \
+        if (blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 2 && (threadIdx.x & 31) == 0 && tl_n < 512) {                \
+            unsigned long long* p_ = g_tl + ((((MODE * 2 + blockIdx.x) * 10 + (threadIdx.x >> 5)) * 512 + tl_n) << 1);      \
             p_[0] = clock64();                                                                                              \
             p_[1] = ((unsigned long long)(ev) << 16) | ((it) & 255) | (1ull << 40);                                         \
             ++tl_n;                                                                                                         \
@@ -57,6 +57,13 @@ __device__ unsigned long long g_tl[3 * 2 * 10 * 128 * 2];
 #define TL(ev, it) do { } while (0)
 #endif
 
+// explicit shared-window load: the dynamic shared-memory base is re-aligned through integer arithmetic, after which the compiler
+// only knows a GENERIC pointer and emits LD.E (address-space check per access) instead of LDS
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2, flushes denormals; exp2(-inf) = 0
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -583,6 +590,9 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv, int ot0, int o_f16) {
     static_assert(MODE == MODE_DQ || MODE == MODE_DKV, "backward modes only");
     using L = BwdPSmem;
+#if ATC_EXPERIMENT == 8
+    unsigned tl_n = 0;
+#endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* s_outer = smem + L::OUTER;                         // buffer u: tile0 at u*2*ATILE, tile1 at +ATILE
@@ -631,6 +641,7 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     const uint32_t tb = *tmem_slot;
     pdl_wait();        // set-up above is private; q / k / v, dO, lse (and delta) come from the preceding kernels
     pdl_trigger();
+    TL(30, 0);
 
     // item w -> (outer tile, head, sample); the outer tile runs fastest so that neighbouring CTAs share K / V (or Q / dO) in L2
     auto item = [&](int w, int& ot, int& h, int& b) {
@@ -674,6 +685,7 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                 uint8_t* t0 = s_inner + stage * 2 * ITILE;
                 uint8_t* t1 = t0 + ITILE;
                 mbar_wait(&in_empty[stage], par ^ 1);       // whole warp, converged: uniform loop state
+                TL(20, it);
                 if (elect_one()) {
                     mbar_expect_tx(&in_full[stage], 2 * ITILE);
                     if (MODE == MODE_DQ) {
@@ -717,12 +729,14 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             const int u = k & 1;
             mbar_wait(&outer_full[u], (k >> 1) & 1);
             tc_fence_after();
+            TL(31, k);
             const uint64_t a0 = umma_desc_sw128(smem_u32(s_outer + u * 2 * ATILE));
             const uint64_t a1 = umma_desc_sw128(smem_u32(s_outer + u * 2 * ATILE + ATILE));
             for (int it = 0; it < n_in; ++it, ++g) {
                 const int stage = g % NST, par = (g / NST) & 1;
                 mbar_wait(&in_full[stage], par);
                 tc_fence_after();
+                TL(1, it);
                 const uint64_t b0 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE));
                 const uint64_t b1 = umma_desc_sw128(smem_u32(s_inner + stage * 2 * ITILE + ITILE));
                 const bool last = it == n_in - 1;
@@ -734,10 +748,12 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     umma_commit(s_full);
                 }
                 __syncwarp();
+                TL(2, it);
                 // ew_done of step (k, 0) also tells that the element-wise warps have read the accumulators of item k - 1 out of
                 // TMEM (their epilogue precedes this step in program order), so the first accumulate MMA may overwrite them
                 mbar_wait(ew_done, g & 1);
                 tc_fence_after();
+                TL(3, it);
                 if (elect_one()) {
                     if (MODE == MODE_DQ) {
 #pragma unroll
@@ -758,6 +774,7 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     }
                 }
                 __syncwarp();
+                TL(4, it);
             }
         }
     } else {
@@ -805,15 +822,18 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     my_del = delta_in[bh * S + row];
                 }
             }
+            TL(9, k);
             for (int it = 0; it < n_in; ++it, ++g) {
                 mbar_wait(s_full, g & 1);
                 tc_fence_after();
-                const float* v_lse = s_vec + (g % NST) * 2 * TI + 32 * half;
-                const float* v_del = v_lse + TI;
+                TL(10, it);
+                const uint32_t v_lse = smem_u32(s_vec) + static_cast<uint32_t>(((g % NST) * 2 * TI + 32 * half) * 4);
+                const uint32_t v_del = v_lse + TI * 4;
                 uint32_t sA[32], dA[32];
                 tmem_ld32(tS, sA);
                 tmem_ld32(tD, dA);
                 tmem_ld_wait();
+                TL(11, it);
                 uint32_t pkp[16], pks[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -826,12 +846,19 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                         d0 = p0 * (g0 - my_del);
                         d1 = p1 * (g1 - my_del);
                     } else {
-                        const float2 l2 = *reinterpret_cast<const float2*>(v_lse + i);
-                        const float2 e2 = *reinterpret_cast<const float2*>(v_del + i);
-                        p0 = fast_exp2(fmaf(s0, L2E, -l2.x));
-                        p1 = fast_exp2(fmaf(s1, L2E, -l2.y));
-                        d0 = p0 * (g0 - e2.x);
-                        d1 = p1 * (g1 - e2.y);
+                        // per-query lse / delta: the same address in every lane (broadcast).  128-bit loads, four queries each:
+                        // with 64-bit loads the 32 LDS per thread and step were what the dK / dV element-wise stage waited for
+#if ATC_EXPERIMENT == 9      // timing experiment: no shared-memory loads at all
+                        const float4 l4 = make_float4(my_lse, my_lse, my_lse, my_lse), e4 = make_float4(my_del, my_del, my_del, my_del);
+#else
+                        const float4 l4 = lds128(v_lse + (i & ~3) * 4);
+                        const float4 e4 = lds128(v_del + (i & ~3) * 4);
+#endif
+                        const bool hi = (i & 2) != 0;
+                        p0 = fast_exp2(fmaf(s0, L2E, -(hi ? l4.z : l4.x)));
+                        p1 = fast_exp2(fmaf(s1, L2E, -(hi ? l4.w : l4.y)));
+                        d0 = p0 * (g0 - (hi ? e4.z : e4.x));
+                        d1 = p1 * (g1 - (hi ? e4.w : e4.y));
                     }
                     pks[i / 2] = pack_bf16x2(d0, d1);
                     if (MODE == MODE_DKV) pkp[i / 2] = pack_bf16x2(p0, p1);
@@ -842,12 +869,16 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                     tmem_st16(tS, pkp);          // P^T
                     tmem_st16(tD, pks);          // dS^T
                 }
+                TL(12, it);
                 tmem_st_wait();
                 tc_fence_before();
+                TL(13, it);
                 mbar_arrive(ew_done);
             }
+            TL(14, k);
             mbar_wait(acc_full, k & 1);
             tc_fence_after();
+            TL(32, k);
             uint32_t a0[32];
             tmem_ld32(tl + C_ACC0 + 32 * half, a0);
             tmem_ld_wait();
@@ -862,6 +893,7 @@ attn_tc_bwdp_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                 if (row_ok) store_row_bf16_32(drow + E, a0);         // dK
             }
             tc_fence_before();      // orders these TMEM reads before the ew_done arrive of the next item's first step
+            TL(33, k);
         }
     }
 
@@ -1745,7 +1777,7 @@ int attn_tc_bwd(const void* qkv, const void* out_o, const void* dout, const floa
 
 #if ATC_EXPERIMENT == 8
 extern "C" __attribute__((visibility("default"))) int tvs_debug_timeline(unsigned long long* host, int max_words, int reset) {
-    const int words = 3 * 2 * 10 * 128 * 2;
+    const int words = 3 * 2 * 10 * 512 * 2;
     cudaDeviceSynchronize();
     if (host && max_words >= words) cudaMemcpyFromSymbol(host, tvs::g_tl, sizeof(unsigned long long) * words);
     if (reset) {

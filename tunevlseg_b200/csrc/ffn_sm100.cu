@@ -234,7 +234,14 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap map_w1_hi, const __grid_consta
         bar_sync_ew();                  // s_b1 complete
         for (int it = 0; it < n_it; ++it) {
             const int bf = it & 1;
-            const float* bj = s_b1 + it * FC + 32 * half;
+            // this step's 32 fc1 biases: explicit ld.shared (through the re-aligned generic base the compiler emitted LD.E)
+            float bj[32];
+            {
+                const uint32_t ba = smem_u32(s_b1 + it * FC + 32 * half);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bj[4 * q]), "=f"(bj[4 * q + 1]), "=f"(bj[4 * q + 2]), "=f"(bj[4 * q + 3]) : "r"(ba + 16 * q));
+            }
             mbar_wait(&s_full[bf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t tS = tl + 128 * bf + 32 * half;

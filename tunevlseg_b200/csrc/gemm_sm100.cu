@@ -380,15 +380,16 @@ enum { EPI_GENERIC = 0, EPI_OUT_BF16 = 1 /* (+bias) -> bf16 */, EPI_RES_F32 = 2 
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint32_t (&acc)[32], long long row, int col0, const uint32_t (&ext)[32],
-                                              const float* __restrict__ s_bias /* this chunk's 32 bias values in shared memory, or nullptr */,
+                                              uint32_t s_bias /* shared-window address of this chunk's 32 bias values, or 0 */,
                                               bool ovr = false /* EPI_RES_F32: ext holds the prompt row that replaces the result */) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-    if (EPI != EPI_DQGELU && s_bias != nullptr) {        // kernel-uniform; 8 broadcast LDS.128
-#pragma unroll
+    if (EPI != EPI_DQGELU && s_bias != 0) {              // kernel-uniform; 8 broadcast LDS.128 (explicit ld.shared: through the
+#pragma unroll                                           // re-aligned generic base the compiler emitted LD.E, round 2)
         for (int q = 0; q < 8; ++q) {
-            const float4 b = reinterpret_cast<const float4*>(s_bias)[q];
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(s_bias + 16 * q));
             v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
         }
     }
@@ -843,7 +844,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             if (row_ok && coln < N) spec_load_ext<EPI>(ep, orow, coln, ext[(k + 1) & 1], ovr_row);
                         }
                         tmem_ld_wait();
-                        if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext[k & 1], use_bias ? s_bias + k * 32 : nullptr, ovr_row != nullptr);
+                        if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext[k & 1], use_bias ? smem_u32(s_bias + k * 32) : 0u, ovr_row != nullptr);
                     }
                 }
                 tc_fence_before();
