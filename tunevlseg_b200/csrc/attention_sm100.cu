@@ -1613,6 +1613,275 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// one-pass forward, PERSISTENT (round 2, the default): attn_tc_fwd1_kernel's arithmetic and pipeline with 2 x #SM resident CTAs
+// walking the (query tile, head, sample) items - see attn_tc_bwdp_kernel for what a per-CTA timeline showed (a quarter of a
+// one-item CTA's life is set-up and the first TMA round trip).  Q is double-buffered and requested one item ahead, the K / V
+// ring and the two score buffers never drain between items, and the O read-out of item k overlaps Q K^T of item k + 1.
+// ------------------------------------------------------------------------------------------------
+struct FwdPSmem {
+    static constexpr int Q = 0;                                   // [2] x ATILE
+    static constexpr int INNER = 2 * ATILE;                       // [FST][2] x FITILE
+    static constexpr int BAR = INNER + FST * 2 * FITILE;
+    static constexpr int NBAR = 4 + 2 * FST + 6;                  // q_full[2], q_empty[2], in_full / in_empty[FST], s_full[2], ew_done[2], o_done, acc_full
+    static constexpr int TOTAL = BAR + (NBAR + 1) * 8 + 1024;
+};
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attn_tc_fwd1p_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_in, int S, int H, int n_ot, int n_items,
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ out32, float* __restrict__ lse_out, int o_f16) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* s_q = smem + FwdPSmem::Q;
+    uint8_t* s_inner = smem + FwdPSmem::INNER;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdPSmem::BAR);
+    uint64_t* q_full = bars;                    // [2]
+    uint64_t* q_empty = bars + 2;               // [2]
+    uint64_t* in_full = bars + 4;               // [FST]
+    uint64_t* in_empty = bars + 4 + FST;        // [FST]
+    uint64_t* s_full = bars + 4 + 2 * FST;      // [2]
+    uint64_t* ew_done = s_full + 2;             // [2]
+    uint64_t* o_done = s_full + 4;              // one phase per P V
+    uint64_t* acc_full = s_full + 5;            // one phase per item, with its LAST P V
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+
+    const int E = H * AHD;
+    const int warp = threadIdx.x >> 5;
+    const int n_it = (S + FTI - 1) / FTI;
+    constexpr uint32_t TMEM_COLS = 256, C_O = 128;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_in);
+        for (int u = 0; u < 2; ++u) {
+            mbar_init(&q_full[u], 1);
+            mbar_init(&q_empty[u], 1);
+            mbar_init(&s_full[u], 1);
+            mbar_init(&ew_done[u], 128);
+        }
+        for (int s = 0; s < FST; ++s) {
+            mbar_init(&in_full[s], 1);
+            mbar_init(&in_empty[s], 1);
+        }
+        mbar_init(o_done, 1);
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    auto item = [&](int w, int& ot, int& h, int& b) {
+        ot = w % n_ot;
+        const int hb = w / n_ot;
+        h = hb % H;
+        b = hb / H;
+    };
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ TMA producer
+        auto load_q = [&](int k, int w) {
+            int ot, h, b;
+            item(w, ot, h, b);
+            const int u = k & 1;
+            mbar_wait(&q_empty[u], ((k >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&q_full[u], ATILE);
+                tma_load_3d(s_q + u * ATILE, &map_q, h * AHD, ot * AT, b, &q_full[u]);
+            }
+            __syncwarp();
+        };
+        int g = 0, k = 0;
+        if (static_cast<int>(blockIdx.x) < n_items) load_q(0, blockIdx.x);
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++k) {
+            int ot, h, b;
+            item(w, ot, h, b);
+            const int ck = E + h * AHD, cv = 2 * E + h * AHD;
+            const int w_next = w + gridDim.x;
+            bool prefetched = w_next >= n_items;
+            for (int it = 0; it < n_it; ++it, ++g) {
+                const int stage = g % FST, par = (g / FST) & 1;
+                mbar_wait(&in_empty[stage], par ^ 1);
+                if (elect_one()) {
+                    uint8_t* t0 = s_inner + stage * 2 * FITILE;
+                    mbar_expect_tx(&in_full[stage], 2 * FITILE);
+                    tma_load_3d(t0, &map_in, ck, it * FTI, b, &in_full[stage]);
+                    tma_load_3d(t0 + FITILE, &map_in, cv, it * FTI, b, &in_full[stage]);
+                }
+                __syncwarp();
+                // the ring has wrapped inside this item: its step 0 has retired, hence the whole previous item - the Q buffer of
+                // item k + 1 (last used by item k - 1) is free
+                if (!prefetched && it == FST) {
+                    load_q(k + 1, w_next);
+                    prefetched = true;
+                }
+            }
+            if (!prefetched) load_q(k + 1, w_next);
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc_s = umma_idesc_bf16(AT, FTI, 0, 0);
+        constexpr uint32_t idesc_acc = umma_idesc_bf16(AT, AHD, 0, 1);
+        int g = 0, k = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++k) {
+            const int u = k & 1;
+            mbar_wait(&q_full[u], (k >> 1) & 1);
+            tc_fence_after();
+            const uint64_t a0 = umma_desc_sw128(smem_u32(s_q + u * ATILE));
+            // O += P_j V_j for step j of this item (global step gj); releases its K / V stage, completes one phase of o_done.
+            // ew_done of the item's step 0 also tells that the element-wise warps have read O of the previous item out of TMEM
+            auto issue_pv = [&](int j, int gj) {
+                const int bfj = gj & 1, stg = gj % FST;
+                mbar_wait(&ew_done[bfj], (gj >> 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t bv = umma_desc_sw128(smem_u32(s_inner + stg * 2 * FITILE + FITILE));
+#pragma unroll
+                    for (int kk = 0; kk < FTI / 16; ++kk)
+                        umma_ts(tb + C_O, tb + 64 * bfj + 8 * kk, bv + 128 * kk, idesc_acc, (j > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&in_empty[stg]);
+                    umma_commit(o_done);
+                    if (j == n_it - 1) {
+                        umma_commit(acc_full);
+                        umma_commit(&q_empty[u]);
+                    }
+                }
+                __syncwarp();
+            };
+            for (int it = 0; it < n_it; ++it, ++g) {
+                const int stage = g % FST, par = (g / FST) & 1, bf = g & 1;
+                mbar_wait(&in_full[stage], par);
+                tc_fence_after();
+                // score buffer bf was last read as P by P V of global step g - 2: issued earlier in program order, after its ew_done
+                if (elect_one()) {
+                    const uint64_t bk = umma_desc_sw128(smem_u32(s_inner + stage * 2 * FITILE));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_ss(tb + 64 * bf, a0 + 2 * kk, bk + 2 * kk, idesc_s, kk > 0);
+                    umma_commit(&s_full[bf]);
+                }
+                __syncwarp();
+                if (it >= 1) issue_pv(it - 1, g - 1);
+            }
+            issue_pv(n_it - 1, g - 1);
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps (thread = TMEM lane = query row)
+        const int tid = threadIdx.x;
+        const uint32_t tl = tb + (static_cast<uint32_t>(warp * 32) << 16);
+        int g = 0, k = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++k) {
+            int ot, h, b;
+            item(w, ot, h, b);
+            const long long bh = static_cast<long long>(b) * H + h;
+            const int row = ot * AT + tid;
+            const bool row_ok = row < S;
+            float mL = -INFINITY;          // (stale) running maximum, in log2 units
+            float l = 0.f;
+            for (int it = 0; it < n_it; ++it, ++g) {
+                const int bf = g & 1;
+                mbar_wait(&s_full[bf], (g >> 1) & 1);
+                tc_fence_after();
+                const int k0 = it * FTI;
+                uint32_t r0[32], r1[32];
+                tmem_ld32(tl + 64 * bf, r0);
+                tmem_ld32(tl + 64 * bf + 32, r1);
+                tmem_ld_wait();
+                const bool full = k0 + FTI <= S;
+                float mt = -INFINITY;
+                if (full) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mt = fmaxf(mt, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (k0 + i < S) mt = fmaxf(mt, __uint_as_float(r0[i]));
+                        if (k0 + 32 + i < S) mt = fmaxf(mt, __uint_as_float(r1[i]));
+                    }
+                }
+                const float mtL = mt * L2E;
+                const bool need = mtL > mL + RESCALE_LOG2;      // always true on the first tile (mL = -inf, key 0 is valid)
+                if (__any_sync(0xffffffffu, need)) {
+                    const float scale = need ? fast_exp2(mL - mtL) : 1.0f;      // exp2(-inf) = 0 on the first tile
+                    if (it > 0) {
+                        // the previous P V (global step g - 1) must have landed in O before it is rescaled; when s_full of step g has
+                        // completed, every P V up to step g - 2 has, so the parity wait cannot alias
+                        mbar_wait(o_done, (g - 1) & 1);
+                        tc_fence_after();
+                        uint32_t o0[32], o1[32];
+                        tmem_ld32(tl + C_O, o0);
+                        tmem_ld32(tl + C_O + 32, o1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * scale);
+                            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * scale);
+                        }
+                        tmem_st32(tl + C_O, o0);
+                        tmem_st32(tl + C_O + 32, o1);
+                    }
+                    l *= scale;
+                    if (need) mL = mtL;
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float p0 = fast_exp2(fmaf(__uint_as_float(c == 0 ? r0[i] : r1[i]), L2E, -mL));
+                        float p1 = fast_exp2(fmaf(__uint_as_float(c == 0 ? r0[i + 1] : r1[i + 1]), L2E, -mL));
+                        if (!full) {
+                            if (k0 + 32 * c + i >= S) p0 = 0.f;
+                            if (k0 + 32 * c + i + 1 >= S) p1 = 0.f;
+                        }
+                        l += p0 + p1;
+                        pk[i / 2] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st16(tl + 64 * bf + 16 * c, pk);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&ew_done[bf]);
+            }
+            mbar_wait(acc_full, k & 1);       // one phase per item (completes with the item's last P V)
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld32(tl + C_O, o0);
+            tmem_ld32(tl + C_O + 32, o1);
+            tmem_ld_wait();
+            tc_fence_before();                // orders the O read before the ew_done arrive of the next item's first step
+            if (row_ok) {
+                const float inv = l > 0.f ? 1.0f / l : 0.f;
+                const long long tok = static_cast<long long>(b) * S + row;
+                store_row_bf16_64(out + tok * E + h * AHD, o0, o1, inv, o_f16);
+                if (out32) {
+                    float* f = out32 + tok * E + h * AHD;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        uint32_t wv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int e = 8 * q + i;
+                            wv[i] = __float_as_uint(round_tf32_rn(__uint_as_float(e < 32 ? o0[e] : o1[e - 32]) * inv));     // feeds a tf32 GEMM
+                        }
+                        st_global_256(f + 8 * q, wv);
+                    }
+                }
+                lse_out[bh * S + row] = (mL == -INFINITY ? 0.f : mL * 0.6931471805599453f) + logf(fmaxf(l, 1e-30f));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tb, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1677,6 +1946,22 @@ int attn_tc_fwd(const void* qkv, int B, int S, int H, void* out, float* out32, f
         TVS_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
         TVS_CUDA(cudaFuncSetAttribute(attn_tc_fwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
         attr_set = true;
+    }
+    static const bool one_item = [] { const char* e = getenv("TVS_ATTN_FWD"); return e && e[0] == '3'; }();   // TVS_ATTN_FWD=3: one CTA per item (round 1 / early round 2)
+    if (!two_pass && !one_item) {      // default: persistent one-pass kernel
+        static bool attr_p = false;
+        if (!attr_p) {
+            TVS_CUDA(cudaFuncSetAttribute(attn_tc_fwd1p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdPSmem::TOTAL));
+            attr_p = true;
+        }
+        const int n_ot = (S + AT - 1) / AT;
+        const long long n_items = static_cast<long long>(n_ot) * H * B;
+        TVS_REQUIRE(n_items < (1LL << 31), "attention forward: too many (tile, head, sample) items");
+        const int resident = 2 * sm_count();
+        dim3 pgrid(static_cast<unsigned>(n_items < resident ? n_items : resident));
+        TVS_CUDA(launch_pdl(attn_tc_fwd1p_kernel, pgrid, dim3(ATC_THREADS), FwdPSmem::TOTAL, st, 1, mq, mqi, S, H, n_ot, static_cast<int>(n_items),
+                            static_cast<__nv_bfloat16*>(out), out32, lse, o_f16));
+        return check_launch("attn_tc_fwd1p_kernel");
     }
     dim3 grid((S + AT - 1) / AT, H, B);
     if (!two_pass) {
