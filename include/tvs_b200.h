@@ -62,7 +62,9 @@ int32_t tvs_gemm_last_variant(void);
  * "illegal instruction" for a mixed fp16 x bf16 kind::f16 MMA (measured, round 2).
  * The 16-bit pointers below are named *_bf16 for history; their format follows these flags. */
 enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1, TVS_AB_F16 = 2 /* A, W IEEE fp16 */ };
-enum { TVS_GEMM_ROUND_OUT_TF32 = 1, TVS_GEMM_OUT16_F16 = 2 };     /* tvs_gemm_args.reserved (flags) */
+enum { TVS_GEMM_ROUND_OUT_TF32 = 1, TVS_GEMM_OUT16_F16 = 2,
+       TVS_GEMM_STREAM_K = 4 /* opt-in: cut the (tile, k-block) space into one contiguous range per CTA pair (specialised pair
+                                kernels only; measured SLOWER than whole-tile round robin on the tower shapes) */ };     /* tvs_gemm_args.reserved (flags) */
 enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4, TVS_ACT_RES_RELU = 5 };
 
 typedef struct tvs_gemm_args {

@@ -63,7 +63,7 @@ def test_full_geometry_at_bench_batch(case, B, with_grads):
         abi.set_profiler(None)
     used = _variants(recs)
     M = B * (1 + (spec.image_size // spec.patch_size) ** 2 + st.num_context)
-    pair = {v for v in used if v.startswith(f"{M}x") and v.endswith("cta_group::2")}
+    pair = {v for v in used if v.startswith(f"{M}x") and "cta_group::2" in v}
     print(f"GEMM variants at M={M}: {sorted(v for v in used if v.startswith(f'{M}x'))}")
     # every compute-heavy tower shape (QKV, fc1, fc2 and their dgrads) must have run on the cta_group::2 pair kernel - the
     # instance bench.py's roofline names (256-wide tiles since the N = 768 / 2304 shapes moved to them; the 128-wide pair
@@ -164,11 +164,31 @@ def test_tower_gemm_shapes_at_bench_rows(name, N, K, epi, fmt, tile_n):
         scale = want.abs().max().item()
         err = (got.float() - want).abs().max().item()
         assert err <= rel * scale + 1e-3, f"{name} tile_n={tile_n} [{variant}]: max-abs err {err:.4e} (scale {scale:.3f})"
+    # a second launch must reproduce the first bit for bit (stream-K: fixed summation order, flags consumed and reset)
+    first = [got.clone() for got, _, _ in checks]
+    abi.gemm(A, W, tile_n=tile_n, **kw)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, got) for a, (got, _, _) in zip(first, checks)), f"{name} tile_n={tile_n} [{variant}]: second launch differs"
     heavy = N * K >= 768 * 1024
     bn = tile_n or int(variant.split("x")[0])
     if heavy and bn >= 128:      # launch_gemm: pairs when the problem fills the machine and is compute-heavy
-        assert variant.endswith("cta_group::2"), f"{name}: expected the pair kernel, got {variant}"
+        assert "cta_group::2" in variant, f"{name}: expected the pair kernel, got {variant}"
         assert variant.startswith(f"{bn}x"), variant
+        assert not variant.endswith("stream-k"), variant           # opt-in only (measured slower than whole-tile round robin)
+        # the opt-in stream-K schedule (cut tiles, parked fp32 accumulators, flags) must give the same numbers
+        tiles = -(-M // 256) * (N // bn)
+        pairs = torch.cuda.get_device_properties(0).multi_processor_count // 2
+        if tiles > pairs and tiles % pairs and "epi:generic" not in variant:
+            for rep in range(2):
+                for got, _, _ in checks:
+                    got.zero_()
+                abi.gemm(A, W, tile_n=tile_n, stream_k=True, **kw)
+                assert abi.gemm_last_variant().endswith("stream-k"), abi.gemm_last_variant()
+                torch.cuda.synchronize()
+                for got, want, rel in checks:
+                    scale = want.abs().max().item()
+                    err = (got.float() - want).abs().max().item()
+                    assert err <= rel * scale + 1e-3, f"{name} tile_n={tile_n} stream-K rep {rep}: max-abs err {err:.4e} (scale {scale:.3f})"
     print(f"GEMM {name} M={M} N={N} K={K} {fmt} tile_n={tile_n}: {variant}")
 
 

@@ -179,13 +179,14 @@ def _chk(t: torch.Tensor | None, dtype, name: str, dim2: bool = False) -> None:
 
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=ACT_NONE,
-         tile_n=0, round_out=False, conv_hw=None, overwrite=None):
+         tile_n=0, round_out=False, conv_hw=None, overwrite=None, stream_k=False):
     """C[M,N] = epilogue(A[M,K] @ W[N,K]^T); see tvs_gemm_bf16 in include/tvs_b200.h.  2-D views with a row stride
     are accepted (ld = stride(0)).  ``round_out``: out_f32 is rounded to nearest tf32 (it only feeds further tf32 GEMMs).
     ``conv_hw=(H, W)``: implicit-GEMM 3x3 convolution - A is the zero-bordered image [B*(H+2)*(W+2), C] from ``pad_nhwc``,
     W is [N, 9*C]; outputs / residual are unpadded [B*H*W, N].
     ``overwrite=(ctx, S, row0, n)``: deep-prompt overwrite fused into the epilogue - output rows at positions row0 .. row0+n-1 of
-    every S-row sample receive ctx ((n, N) shared or (B, n, N) per sample, f32) instead of the result (fc2 of a vision block)."""
+    every S-row sample receive ctx ((n, N) shared or (B, n, N) per sample, f32) instead of the result (fc2 of a vision block).
+    ``stream_k``: opt-in stream-K schedule of the specialised pair kernels (TVS_GEMM_STREAM_K; measured slower - off by default)."""
     require_device()
     ab = {(torch.bfloat16, torch.bfloat16): AB_BF16, (torch.float32, torch.float32): AB_TF32, (torch.float16, torch.float16): AB_F16}.get((A.dtype, W.dtype))
     if ab is None:      # a mixed fp16 x bf16 kind::f16 MMA is an illegal instruction on sm_100 (measured)
@@ -221,7 +222,7 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.aux_bf16, g.ldaux = _p(aux_bf16), (aux_bf16.stride(0) if aux_bf16 is not None else 0)
     g.act, g.tile_n = act, tile_n
     g.ab_dtype = ab
-    g.reserved = (1 if round_out else 0) | (2 if (out_bf16 is not None and out_bf16.dtype == torch.float16) else 0)
+    g.reserved = (1 if round_out else 0) | (2 if (out_bf16 is not None and out_bf16.dtype == torch.float16) else 0) | (4 if stream_k else 0)
     g.conv_h, g.conv_w = conv_hw if conv_hw is not None else (0, 0)
     if overwrite is not None:
         ctx, S_, row0, n_ = overwrite
@@ -237,7 +238,8 @@ def gemm_last_variant() -> str:
     """Template instance the calling thread's last ``gemm`` launched, e.g. ``"256x6 bf16 cta_group::2"``."""
     v = load().tvs_gemm_last_variant()
     epi = ("generic", "out_bf16", "res_f32", "fc1", "dqgelu")[(v >> 5) & 7]
-    return f"{v >> 16}x{(v >> 8) & 0xFF} {'tf32' if (v >> 4) & 1 else 'bf16'} epi:{epi} cta_group::{v & 0xF}"
+    sk = " stream-k" if (v >> 28) & 1 else ""          # the (tile, k-block) space cut into one contiguous range per CTA pair
+    return f"{(v >> 16) & 0xFFF}x{(v >> 8) & 0xFF} {'tf32' if (v >> 4) & 1 else 'bf16'} epi:{epi} cta_group::{v & 0xF}{sk}"
 
 
 def layernorm_fwd(x, gamma, beta, eps, *, y_f32=None, y_bf16=None, mean=None, rstd=None, round_tf32=False):

@@ -55,6 +55,12 @@ struct GemmEpilogue {
     // in the flattened image (the physical zero border makes every interior pixel's 9 taps correct); the epilogue maps
     // the padded row to the unpadded output row and skips border rows.
     int conv_wp, conv_hp, conv_kpt;
+    // stream-K (specialised pair kernels, static schedule): the (tile, k-block) iteration space is cut into one contiguous
+    // range per cluster; a tile cut in two is finished by the cluster that holds its FIRST k-blocks (it reaches the tile last),
+    // the other cluster computes the later k-blocks first and parks its raw fp32 accumulator in sk_ws (launch_gemm_inst)
+    float* sk_ws;
+    int* sk_flags;
+    int sk_q;        // iterations (k-blocks) per cluster; 0 = off (round-robin whole tiles)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -265,6 +271,12 @@ __device__ __forceinline__ void ld256(const void* p, uint32_t (&r)[8]) {
     asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
+}
+__device__ __forceinline__ void ld256_cg(const void* p, uint32_t (&r)[8]) {      // L2 only: data another SM has just written
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p)
+                 : "memory");
 }
 __device__ __forceinline__ void st256(void* p, const uint32_t (&r)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
@@ -587,7 +599,22 @@ struct TileIter {
     uint64_t* se;
     uint32_t slot, par, cta_rank;
 
+    // k-block range and role of the tile next() returned: role 0 = whole tile, 1 = owner of a cut tile (k-blocks [0, kb1); the
+    // cluster after this one parked [kb1, num_kb)), 2 = helper (k-blocks [kb0, num_kb): park the accumulator in slot `cluster`)
+    int kb0, kb1, role;
+    int sk_pos, sk_end, num_kb;      // stream-K: this cluster's range of the linearised (tile, k-block) space; sk_end < 0 = off
+
     __device__ __forceinline__ int next() {      // called by every lane of a converged warp
+        if (!dyn && sk_end >= 0) {
+            if (sk_pos >= sk_end) return -1;
+            const int t = sk_pos / num_kb;
+            kb0 = sk_pos - t * num_kb;
+            kb1 = min(num_kb, kb0 + (sk_end - sk_pos));
+            sk_pos += kb1 - kb0;
+            role = (kb0 == 0 && kb1 == num_kb) ? 0 : (kb0 == 0 ? 1 : 2);
+            return t;
+        }
+        kb0 = 0; kb1 = num_kb; role = 0;
         if (!dyn) {
             const int t = cur;
             cur += step;
@@ -679,6 +706,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tiles.cur = first_tile; tiles.step = tile_step; tiles.num = num_tiles;
     tiles.dyn = sched != nullptr; tiles.s_tile = sched_tile; tiles.sf = sched_full; tiles.se = sched_empty;
     tiles.slot = 0; tiles.par = 0; tiles.cta_rank = cta_rank;
+    tiles.num_kb = num_kb; tiles.kb0 = 0; tiles.kb1 = num_kb; tiles.role = 0; tiles.sk_pos = 0; tiles.sk_end = -1;
+    if (EPI != EPI_GENERIC && sched == nullptr && ep.sk_q > 0) {
+        const long long total = static_cast<long long>(num_tiles) * num_kb, lo = static_cast<long long>(first_tile) * ep.sk_q;
+        tiles.sk_pos = static_cast<int>(lo < total ? lo : total);
+        tiles.sk_end = static_cast<int>(lo + ep.sk_q < total ? lo + ep.sk_q : total);
+    }
 
     if (warp == 3) {
         if (sched != nullptr && cta_rank == 0) {
@@ -717,7 +750,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t stage = 0, phase = 0;
             for (int tile = tiles.next(); tile >= 0; tile = tiles.next()) {
                 const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = tiles.kb0; kb < tiles.kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     int a_col = kb * BK, a_row = m_blk * BM;
                     if (ep.conv_wp) {       // tap (ky, kx) = rows shifted by (ky - 1) * wp + (kx - 1); rows outside the matrix are zero-filled by TMA
@@ -751,7 +784,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_first = tiles.kb0, kb_last = tiles.kb1 - 1;
+                for (int kb = kb_first; kb <= kb_last; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * L::A_BYTES));
@@ -760,7 +794,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                     for (int k = 0; k < MMAS_PER_KB; ++k) {
                         // advance 32 bytes (16 bf16 / 8 tf32) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        const uint32_t accum = (kb != kb_first || k != 0) ? 1u : 0u;
                         if (CL == 2) {
                             if (TF32) umma_tf32_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
                             else umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
@@ -771,10 +805,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                     if (CL == 2) {
                         umma_commit_cg2(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit_cg2(&tmem_full[acc]);
+                        if (kb == kb_last) umma_commit_cg2(&tmem_full[acc]);
                     } else {
                         umma_commit(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                        if (kb == kb_last) umma_commit(&tmem_full[acc]);
                     }
                     }
                     __syncwarp();
@@ -808,7 +842,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const long long row0 = static_cast<long long>(m_blk) * BM + ew * 32;
                 const long long orow = row0 + lane;
                 const bool row_ok = orow < M;
-                const bool use_bias = EPI != EPI_DQGELU && ep.bias != nullptr;
+                const int role = tiles.role;          // stream-K: 0 whole tile, 1 owner of a cut tile, 2 helper (raw accumulator -> sk_ws)
+                const bool use_bias = EPI != EPI_DQGELU && ep.bias != nullptr && role != 2;
+                // the parked accumulator of a cut tile: slot = the HELPER's cluster id, [CL * 128 rows][BN] fp32; one flag per
+                // (slot, CTA of the pair, epilogue warp): the same warp of the same CTA rank reads exactly what it wrote
+                const int sk_slot = first_tile + (role == 1 ? 1 : 0);
+                float* sk_row = ep.sk_ws + (static_cast<long long>(sk_slot) * (CL * BM) + cta_rank * BM + ew * 32 + lane) * BN;
+                volatile int* sk_flag = ep.sk_flags + (sk_slot * 2 + static_cast<int>(cta_rank)) * 8 + (warp - 4);
                 float bias_r[NCH];
 #pragma unroll
                 for (int k = 0; k < NCH; ++k) {
@@ -822,9 +862,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (pr >= 0 && pr < ep.ovr_n) ovr_row = ep.ovr_ctx + smp * ep.ovr_bs + static_cast<long long>(pr) * N;
                 }
                 uint32_t ext[2][32];
-                if (row_ok && n_blk * BN + grp * 64 < N) spec_load_ext<EPI>(ep, orow, n_blk * BN + grp * 64, ext[0], ovr_row);
+                if (role != 2 && row_ok && n_blk * BN + grp * 64 < N) spec_load_ext<EPI>(ep, orow, n_blk * BN + grp * 64, ext[0], ovr_row);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
+                if (role == 1) {        // the helper parked its part at the very start of its range, this tile is our last: no real wait
+                    while (*sk_flag == 0) { }
+                    __threadfence();
+                }
                 if (use_bias) {
                     __syncwarp();                        // the previous tile's reads of the strip are done
 #pragma unroll
@@ -839,17 +883,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (row0 < M && col0 < N) {          // warp-uniform
                         uint32_t r[32];
                         tmem_ld_32x32(t_row + cc * 32, r);
-                        if (k + 1 < NCH) {
+                        if (role != 2 && k + 1 < NCH) {
                             const int coln = n_blk * BN + (grp * 2 + ((k + 1) & 1) + ((k + 1) >> 1) * 4) * 32;
                             if (row_ok && coln < N) spec_load_ext<EPI>(ep, orow, coln, ext[(k + 1) & 1], ovr_row);
                         }
+                        uint32_t pr[4][8];
+                        if (role == 1 && row_ok) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) ld256_cg(sk_row + cc * 32 + 8 * q, pr[q]);
+                        }
                         tmem_ld_wait();
-                        if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext[k & 1], use_bias ? smem_u32(s_bias + k * 32) : 0u, ovr_row != nullptr);
+                        if (role == 1 && row_ok) {      // + the k-blocks the helper computed (fixed order: deterministic)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(pr[i >> 3][i & 7]));
+                        }
+                        if (role == 2) {
+                            if (row_ok) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    uint32_t w8[8];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) w8[i] = r[8 * q + i];
+                                    st256(sk_row + cc * 32 + 8 * q, w8);
+                                }
+                            }
+                        } else if (row_ok) epilogue_spec<EPI>(ep, r, orow, col0, ext[k & 1], use_bias ? smem_u32(s_bias + k * 32) : 0u, ovr_row != nullptr);
                     }
                 }
                 tc_fence_before();
+                if (role == 2) __threadfence();       // every lane's parked values are visible before the flag is
                 __syncwarp();
                 if (lane == 0) {
+                    if (role == 2) *sk_flag = 1;
+                    if (role == 1) *sk_flag = 0;      // consumed: the slot is clean for the next launch (stream order)
                     if (CL == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
                     else mbar_arrive(&tmem_empty[acc]);
                 }
@@ -984,9 +1050,35 @@ static int* sched_slot() {
     return base[dev] + 2 * (seq++ % SCHED_SLOTS);
 }
 
+// stream-K work space: one parked accumulator tile (CL * 128 x 256 fp32) and 2 x 8 flags per cluster, per (device, stream) so that
+// GEMMs on different streams never share a slot.  Allocated on first use - never inside a stream capture (the call then runs
+// without stream-K; the warm-up steps that precede a capture have allocated it by then).
+struct SkWs { int dev; cudaStream_t stream; float* ws; int* flags; };
+static bool sk_workspace(cudaStream_t stream, int clusters, float** ws, int** flags) {
+    static SkWs table[16];
+    static int n = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    for (int i = 0; i < n; ++i)
+        if (table[i].dev == dev && table[i].stream == stream) { *ws = table[i].ws; *flags = table[i].flags; return true; }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone || n == 16) return false;
+    const int slots = sm_count() + 1;          // clusters + 1: the owner of the last cluster never reads, but keep the index in range
+    (void)clusters;
+    float* w = nullptr;
+    int* f = nullptr;
+    if (cudaMalloc(&w, static_cast<size_t>(slots) * 256 * 256 * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaMalloc(&f, static_cast<size_t>(slots) * 16 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); cudaFree(w); return false; }
+    cudaMemset(f, 0, static_cast<size_t>(slots) * 16 * sizeof(int));
+    table[n++] = SkWs{dev, stream, w, f};
+    *ws = w; *flags = f;
+    return true;
+}
+
 static thread_local int g_last_variant = 0;
 template <int BN, int STAGES, bool TF32, int CL, int EPI>
-static int launch_gemm_inst(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStream_t stream) {
+static int launch_gemm_inst(const tvs_gemm_args& a, const GemmEpilogue& ep_in, cudaStream_t stream) {
+    GemmEpilogue ep = ep_in;
     using L = GemmSmem<BN, STAGES, CL>;
     g_last_variant = (BN << 16) | (STAGES << 8) | (EPI << 5) | ((TF32 ? 1 : 0) << 4) | CL;
     CUtensorMap ta, tw;
@@ -1012,6 +1104,22 @@ static int launch_gemm_inst(const tvs_gemm_args& a, const GemmEpilogue& ep, cuda
     int* sched = (dyn_ok && (tiles > clusters || mode == 'f')) ? sched_slot() : nullptr;      // one tile per cluster needs no scheduler
     const int launch_clusters = mode == 'f' ? max_clusters : clusters;      // "force": every SM gets a CTA, most of them draw no tile at all (test switch)
     if (sched && mode == 'm') TVS_CUDA(cudaMemsetAsync(sched, 0, 2 * sizeof(int), stream));
+    // stream-K for the specialised pair kernels (the tower shapes at M = B * S): whole-tile round robin costs ceil(tiles / clusters)
+    // rounds - 3 instead of 2.51 for the N = 768 shapes, 11 instead of 10.05 for N = 3072 at M = 15 648.  OPT-IN (TVS_GEMM_STREAM_K /
+    // TVS_GEMM_STREAMK=1), because it measured SLOWER: N = 3072 plain 54.6 -> 62.1 us, fc2 65.7 -> 80.1, QKV 43.2 -> 51.4.  The kernels
+    // are bound by L2 -> SM ingress and epilogue traffic, not by the MMA count: a last round with fewer active pairs runs faster than
+    // a full one (so the quantisation costs less than the tile count suggests), while every pair pays two extra fp32 accumulator
+    // transfers (park + fetch, 128 KB per CTA each) for its two cut tiles.
+    ep.sk_q = 0; ep.sk_ws = nullptr; ep.sk_flags = nullptr;
+    static const bool sk_env = [] { const char* e = getenv("TVS_GEMM_STREAMK"); return e && e[0] == '1'; }();
+    if (EPI != EPI_GENERIC && CL == 2 && (sk_env || (a.reserved & TVS_GEMM_STREAM_K)) && sched == nullptr && launch_clusters == max_clusters && tiles > max_clusters && tiles % max_clusters != 0) {
+        constexpr int BKE = TF32 ? BK_BYTES / 4 : BK_BYTES / 2;
+        const long long num_kb = (a.K + BKE - 1) / BKE;
+        const long long total = static_cast<long long>(tiles) * num_kb;
+        const long long q = (total + max_clusters - 1) / max_clusters;
+        if (q >= num_kb && total < (1LL << 31) && sk_workspace(stream, max_clusters, &ep.sk_ws, &ep.sk_flags)) ep.sk_q = static_cast<int>(q);
+    }
+    if (ep.sk_q > 0) g_last_variant |= 1 << 28;      // reported as " stream-k" (tvs_gemm_last_variant)
     TVS_CUDA(launch_pdl(kern, dim3(launch_clusters * CL), dim3(GEMM_THREADS), L::TOTAL, stream, CL, ta, tw, a.M, a.N, a.K, ep, sched));
     return check_launch("gemm_bf16_tcgen05_kernel");
 }
