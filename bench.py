@@ -463,7 +463,12 @@ def rooflines(agg_runs, timing):
     flops_total = sum(v[1] for v in inst.values())
     heavy = {k: v for k, v in inst.items() if v[1] >= 0.10 * flops_total} or inst
     t_k = max(heavy.items(), key=lambda kv: kv[1][0]) if inst else None
-    h_k = next((kv for kv in top if kv[1][2] > 0 and kv[1][1] == 0), None)
+    # ... and the same rule for the HBM-bound pick: among the kernels that move a real share (>= 10 %) of the step's algorithmic
+    # bytes, the one with the largest time (the launch-bound [B*L, 512] text-tower LayerNorms on the second stream wait for SMs:
+    # a lot of overlapped time, < 1 % of the bytes)
+    hbm = [kv for kv in top if kv[1][2] > 0 and kv[1][1] == 0]
+    bytes_total = sum(kv[1][2] for kv in hbm)
+    h_k = next((kv for kv in hbm if kv[1][2] >= 0.10 * bytes_total), hbm[0] if hbm else None)
     out["tensor"] = None
     if t_k:
         e = entry(t_k[0], t_k[1][:4], True)

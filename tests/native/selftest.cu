@@ -403,8 +403,9 @@ static void attn_timing(int B, int S, int H, int hd) {
     cudaFree(dQKV); cudaFree(dDO); cudaFree(dOut); cudaFree(dDQKV); cudaFree(dLse); cudaFree(dDelta);
 }
 
-static void test_attn() {
+static void test_attn(bool timing = true) {
     attn_case(1, 128, 1, 64, 0, false);
+    attn_case(10, 300, 12, 64, 0, false);      // 360 (tile, head, sample) items > 2 x 148 resident CTAs: the persistent kernels' multi-item path
     attn_case(1, 64, 1, 64, 0, false);
     attn_case(2, 493, 12, 64, 0, false);
     attn_case(2, 100, 2, 64, 0, false);
@@ -413,6 +414,7 @@ static void test_attn() {
     attn_case(2, 12, 8, 64, 1, true);
     attn_case(2, 130, 4, 16, 0, false);
     attn_case(1, 493, 4, 16, 0, false);
+    if (!timing) return;
     attn_timing(32, 489, 12, 64);
     attn_timing(32, 489, 4, 16);
 }
@@ -675,6 +677,7 @@ int main(int argc, char** argv) {
     if (what == "loss" || what == "all") test_loss();
     if (what == "ln" || what == "all") test_ln();
     if (what == "attn" || what == "all") test_attn();
+    if (what == "attncheck") test_attn(false);      // correctness cases only (compute-sanitizer runs)
     if (what == "gemm" || what == "all") test_gemm();
     if (what == "ffn" || what == "all") test_ffn(what == "ffn");
     if (what == "gemmstep" || what == "all") test_gemm_step_shapes();

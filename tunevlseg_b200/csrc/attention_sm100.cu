@@ -1617,6 +1617,9 @@ attn_tc_fwd1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // walking the (query tile, head, sample) items - see attn_tc_bwdp_kernel for what a per-CTA timeline showed (a quarter of a
 // one-item CTA's life is set-up and the first TMA round trip).  Q is double-buffered and requested one item ahead, the K / V
 // ring and the two score buffers never drain between items, and the O read-out of item k overlaps Q K^T of item k + 1.
+// Measured: 57.9 -> 49.8 us per layer (B = 32, S = 489, H = 12).  A variant with EIGHT softmax warps (two per TMEM lane quarter,
+// 32 score columns each, tile maximum and row sum exchanged through shared memory behind a 64-thread named barrier per step)
+// was slower, 53.6 us: the extra barrier and exchange per step cost more than the shorter per-thread chain saves.
 // ------------------------------------------------------------------------------------------------
 struct FwdPSmem {
     static constexpr int Q = 0;                                   // [2] x ATILE
