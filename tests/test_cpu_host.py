@@ -587,3 +587,60 @@ def test_load_checkpoint_rejects_pickles_that_name_foreign_globals(tmp_path, mon
     with pytest.raises(pickle.UnpicklingError):
         load_checkpoint(bad)
     assert load_checkpoint(bad, allow_unsafe_pickle=True)["w"] is None      # explicit opt-in: print(...) ran and returned None
+
+
+@pytest.mark.parametrize("case", ["maple", "coop"])
+def test_no_freeze_last_layer_composition_over_cpu_abi_emulation(case, monkeypatch):
+    """``no_freeze_last_layer=True`` without the additive layer (base_clipseg.py:73-80): only the transposed convolution of the
+    frozen model trains; its weight / bias gradients (one TN GEMM over the patches in DecoderFn.backward) and the learner
+    gradients against autograd through the oracle - over the CPU emulation of the C ABI."""
+    import contextlib
+    from functools import partial
+
+    import tunevlseg_b200.models.core_models.coop as nets
+    import tunevlseg_b200.models.core_models.coop.context_learner as learners
+    from oracle import clipseg as OC
+    from tests import fake_abi
+    from tests.helpers import LEARNER_CASES, SMALL, hf_model, make_batch, oracle_state
+
+    fake_abi.install(monkeypatch)
+
+    class _NoStream:
+        def wait_stream(self, other): ...
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    monkeypatch.setenv("TVS_TEXT_STREAM", "0")
+
+    weights = OC.init_weights(SMALL, seed=7)
+    c = LEARNER_CASES[case]
+    torch.manual_seed(3)
+    net = getattr(nets, c["cls"])(
+        model_cfg=dict(pretrained_model_name_or_path=hf_model(SMALL, weights), freeze_encoder=False, freeze_decoder=False),
+        context_learner=partial(getattr(learners, c["learner"]), **dict(c["kw"])), freeze_all=True, no_freeze_last_layer=True,
+        use_new_last_layer=False, new_last_layer_kernel_size=5, residual_ratio=0.5)
+    net.context_learner.eval()
+    trainable = {k for k, p in net.named_parameters() if p.requires_grad}
+    assert {"model.decoder.transposed_convolution.weight", "model.decoder.transposed_convolution.bias"} <= trainable
+    assert not any(k.startswith("model.") and "transposed_convolution" not in k for k in trainable)
+    st = oracle_state(case, net, SMALL)
+    w = dict(weights)
+    for k in ("decoder.transposed_convolution.weight", "decoder.transposed_convolution.bias"):
+        w[k] = weights[k].detach().clone().requires_grad_(True)
+    img, ids, am, _ = make_batch(SMALL, 2, 8, 9)
+    logits = net(text_input={"input_ids": ids, "attention_mask": am}, image_input=img)
+    ref = OC.net_forward(w, SMALL, st, None, ids, am, img)
+    assert (logits - ref).abs().max().item() < 2e-2
+    gw = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    (logits * gw).sum().backward()
+    (ref * gw).sum().backward()
+    tc = net.model.decoder.transposed_convolution
+    for g, g_ref in ((tc.weight.grad, w["decoder.transposed_convolution.weight"].grad), (tc.bias.grad, w["decoder.transposed_convolution.bias"].grad)):
+        assert g is not None and g.shape == g_ref.shape
+        assert ((g - g_ref).norm() / g_ref.norm()).item() < 5e-2, ((g - g_ref).norm() / g_ref.norm()).item()
+    named = dict(net.named_parameters())
+    for k, p_ref in st.params.items():
+        pk = f"context_learner.{k}"
+        if pk in named and p_ref.grad is not None and p_ref.grad.abs().max() > 0:
+            assert ((named[pk].grad - p_ref.grad).norm() / p_ref.grad.norm()).item() < 5e-2, pk

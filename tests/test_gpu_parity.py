@@ -146,3 +146,63 @@ def test_bottom_block_pruning_matches_full_backward(case, monkeypatch):
         worst = max(worst, diff / max(scale, 1e-30))
         assert diff <= 2e-3 * scale + 1e-12, f"{case}: {k} differs between pruned and full bottom-block backward ({diff:.3e} of {scale:.3e})"
     print(f"PARITY pruning {case}: worst relative difference {worst:.2e}")
+
+
+@pytest.mark.parametrize("case", ["maple", "coop", "vpt"])
+def test_no_freeze_last_layer_trains_the_transposed_convolution(case):
+    """base_clipseg.py:73-80 (``no_freeze_last_layer=True`` without the additive layer): the decoder's transposed convolution
+    trains with the prompts.  Logits against the oracle, and the weight / bias gradients of the transposed convolution (one
+    small GEMM in DecoderFn.backward) plus the learner gradients against autograd through the oracle."""
+    import tunevlseg_b200.models.core_models.coop as nets
+    import tunevlseg_b200.models.core_models.coop.context_learner as learners
+    from functools import partial
+
+    from tests.helpers import hf_model
+    from tunevlseg_b200.losses import DiceCELoss
+
+    spec, B, L, seed = SMALL, 3, 9, 21
+    weights = OC.init_weights(spec, seed=7)
+    c = LEARNER_CASES[case]
+    torch.manual_seed(seed)
+    net = getattr(nets, c["cls"])(
+        model_cfg=dict(pretrained_model_name_or_path=hf_model(spec, weights), freeze_encoder=False, freeze_decoder=False),
+        context_learner=partial(getattr(learners, c["learner"]), **dict(c["kw"])), freeze_all=True, no_freeze_last_layer=True,
+        use_new_last_layer=False, new_last_layer_kernel_size=5, residual_ratio=0.5)
+    net.context_learner.eval()
+    with torch.no_grad():
+        for p in net.context_learner.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    trainable = {k for k, p in net.named_parameters() if p.requires_grad}
+    assert {"model.decoder.transposed_convolution.weight", "model.decoder.transposed_convolution.bias"} <= trainable
+    assert not any(k.startswith("model.") and "transposed_convolution" not in k for k in trainable)
+    st = oracle_state(case, net, spec)
+    w = dict(weights)
+    for k in ("decoder.transposed_convolution.weight", "decoder.transposed_convolution.bias"):
+        w[k] = weights[k].detach().clone().requires_grad_(True)
+    img, ids, am, mask = make_batch(spec, B, L, seed + 1)
+
+    net = net.cuda()
+    logits = net(text_input={"input_ids": ids.cuda(), "attention_mask": am.cuda()}, image_input=img.cuda())
+    conf = torch.zeros(4, dtype=torch.int64, device="cuda")
+    loss, _ = DiceCELoss(sigmoid=True, lambda_dice=1, lambda_ce=0.2).forward_with_metrics(logits, mask.cuda(), 0.5, conf)
+    loss.backward()
+    torch.cuda.synchronize()
+    ref = OC.net_forward(w, spec, st, None, ids, am, img)
+    OLM.dice_ce_loss(ref, mask).backward()
+    err = (logits.detach().cpu() - ref.detach()).abs().max().item()
+    assert err <= LOGIT_TOL, f"{case}: logits max-abs err {err:.4f}"
+    tc = net.model.decoder.transposed_convolution
+    for name, g, g_ref in (("weight", tc.weight.grad, w["decoder.transposed_convolution.weight"].grad),
+                           ("bias", tc.bias.grad, w["decoder.transposed_convolution.bias"].grad)):
+        assert g is not None and g.shape == g_ref.shape, name
+        rel = (g.detach().cpu() - g_ref).abs().max().item() / g_ref.abs().max().item()
+        l2 = ((g.detach().cpu() - g_ref).norm() / g_ref.norm()).item()
+        print(f"PARITY no_freeze_last_layer {case}: transposed_convolution.{name} grad rel err {rel:.4f} (L2 {l2:.4f})")
+        assert rel <= GRAD_TOL and l2 <= GRAD_L2_TOL, f"{case}: transposed_convolution.{name} grad rel err {rel:.4f} / L2 {l2:.4f}"
+    named = dict(net.named_parameters())
+    for k, p_ref in st.params.items():
+        pk = f"context_learner.{k}"
+        if pk not in named or p_ref.grad is None or p_ref.grad.abs().max() == 0:
+            continue
+        l2 = ((named[pk].grad.detach().cpu() - p_ref.grad).norm() / p_ref.grad.norm()).item()
+        assert l2 <= GRAD_L2_TOL, f"{case}: grad {pk} L2 rel err {l2:.4f}"

@@ -638,7 +638,7 @@ class DecoderFn(torch.autograd.Function):
 
     @staticmethod
     @_phase("decoder.fwd")
-    def forward(ctx, tap0, tap1, tap2, cond, add_w, add_b, ratio, pk: PackedClipSeg, blend: int, n_strip: int):
+    def forward(ctx, tap0, tap1, tap2, cond, add_w, add_b, ratio, pk: PackedClipSeg, blend: int, n_strip: int, tconv_w=None, tconv_b=None):
         taps = (tap0, tap1, tap2)
         B, S, Dv = tap0.shape
         Dr, G, P = pk.Dr, pk.grid, pk.patch
@@ -667,7 +667,13 @@ class DecoderFn(torch.autograd.Function):
         abi.slice_rows(out.view(B, S, Dr), 1, G2, y_f32=feat32)
         tconv = _e((B * G2, P * P), F32, out)
         feat_rn = rn_act(feat32.view(B * G2, Dr))
-        abi.gemm(feat_rn, pk.w_tconv, out_f32=tconv)
+        # no_freeze_last_layer (base_clipseg.py:73-80): the transposed convolution trains - read the live weight / bias
+        w_tconv, b_tconv, w_tconv_t = pk.w_tconv, pk.b_tconv, pk.w_tconv_t
+        if tconv_w is not None:
+            tw = tconv_w.detach().to(F32).reshape(Dr, -1)                              # [Dr, P*P]
+            w_tconv, w_tconv_t = tf32_rn(tw.t()), _bf(tw)
+            b_tconv = tconv_b.detach().to(F32).contiguous()
+        abi.gemm(feat_rn, w_tconv, out_f32=tconv)
         H = G * P
         logits = _e((B, 1, H, H), F32, out)
         addmap = add_out = wa16 = ratio_d = add_b_d = None
@@ -684,11 +690,12 @@ class DecoderFn(torch.autograd.Function):
             add_out = _e((B, H, H), F32, out) if blend == abi.BLEND_RATIO else None
             ratio_d = None if ratio is None else ratio.detach().to(F32).reshape(1).contiguous()
             add_b_d = add_b.detach().to(F32).contiguous()
-            abi.head_fwd(tconv, addmap[:, :KK], pk.b_tconv, add_b_d, ratio_d, blend, B, G, P, ks, logits, add_out)
+            abi.head_fwd(tconv, addmap[:, :KK], b_tconv, add_b_d, ratio_d, blend, B, G, P, ks, logits, add_out)
         else:
-            abi.head_fwd(tconv, None, pk.b_tconv, None, None, blend, B, G, P, 1, logits, None)
+            abi.head_fwd(tconv, None, b_tconv, None, None, blend, B, G, P, 1, logits, None)
         ctx.pk, ctx.saved_layers, ctx.film_saved = pk, saved_layers, film_saved
         ctx.head = (tconv, add_out, ratio_d, wa16, feat32, ks)
+        ctx.tconv = (b_tconv, w_tconv_t, None if tconv_w is None else tuple(tconv_w.shape), None if tconv_b is None else tuple(tconv_b.shape))
         ctx.dims = (B, S, Dv, blend, n_strip)
         ctx.has = (add_w is not None, add_b is not None, ratio is not None)
         ctx.shapes = (None if add_w is None else add_w.shape, None if add_b is None else add_b.shape,
@@ -703,6 +710,7 @@ class DecoderFn(torch.autograd.Function):
         Dr, G, P = pk.Dr, pk.grid, pk.patch
         G2, M = G * G, B * S
         tconv, add_out, ratio_d, wa16, feat32, ks = ctx.head
+        b_tconv, w_tconv_t, tw_shape, tb_shape = ctx.tconv
         dl = dlogits.contiguous().to(F32)
         dev = dl.device
         dtconv16 = _e((B * G2, P * P), BF16, dl)
@@ -717,7 +725,7 @@ class DecoderFn(torch.autograd.Function):
             if HEAD_BWD_GEMM and Wimg % 4 == 0:
                 # daddmap[b, yi, xi, ky, kx] = wb * sum_{Y, X} dl[b, Y, X] wy(Y; ky, yi) wx(X; kx, xi): contract X, then Y, on the
                 # tensor cores (kind::tf32; the operands are gradients: the MMA's truncation is far inside their tolerance)
-                abi.head_bwd(dl, tconv, add_out, pk.b_tconv, ratio_d, blend, B, G, P, ks, dtconv16, None, dba, dr_)
+                abi.head_bwd(dl, tconv, add_out, b_tconv, ratio_d, blend, B, G, P, ks, dtconv16, None, dba, dr_)
                 wm = pk.tap_matrix(ks)                                   # [R, W], R = G * ks padded to 8
                 R = wm.shape[0]
                 t1 = _e((R, B * Wimg), F32, dl)
@@ -728,8 +736,8 @@ class DecoderFn(torch.autograd.Function):
                 dam = c2.view(B, R, R)[:, :G * ks, :G * ks].reshape(B, G, ks, G, ks).permute(0, 3, 1, 4, 2).reshape(B * G2, KK)
                 daddmap[:, :KK] = dam * ratio_d if blend == abi.BLEND_RATIO else dam
             else:
-                abi.head_bwd(dl, tconv, add_out, pk.b_tconv, ratio_d, blend, B, G, P, ks, dtconv16, daddmap[:, :KK], dba, dr_)
-            abi.gemm(dtconv16, pk.w_tconv_t, out_f32=dfeat)
+                abi.head_bwd(dl, tconv, add_out, b_tconv, ratio_d, blend, B, G, P, ks, dtconv16, daddmap[:, :KK], dba, dr_)
+            abi.gemm(dtconv16, w_tconv_t, out_f32=dfeat)
             da16 = _e(tuple(daddmap.shape), BF16, dl)
             abi.cast_bf16(daddmap, da16)
             abi.gemm(da16, wa16.t().contiguous(), residual=dfeat, out_f32=dfeat)
@@ -739,8 +747,25 @@ class DecoderFn(torch.autograd.Function):
             d_add_b = dba.reshape(ctx.shapes[1]) if ctx.has[1] else None
             d_ratio = dr_.reshape(ctx.shapes[2]) if (ctx.has[2] and blend == abi.BLEND_RATIO) else None
         else:
-            abi.head_bwd(dl, None, None, pk.b_tconv, None, blend, B, G, P, 1, dtconv16, None, None, None)
-            abi.gemm(dtconv16, pk.w_tconv_t, out_f32=dfeat)
+            abi.head_bwd(dl, None, None, b_tconv, None, blend, B, G, P, 1, dtconv16, None, None, None)
+            abi.gemm(dtconv16, w_tconv_t, out_f32=dfeat)
+        d_tconv_w = d_tconv_b = None
+        if tw_shape is not None:
+            # weight gradient of the transposed convolution: dW[c, p] = sum_m feat[m, c] * dtconv[m, p] - one TN GEMM on the
+            # transposed copies (contraction over the B*G*G patches), bf16 operands like every other gradient GEMM; the bias is
+            # added to every pixel, so its gradient is the sum of dlogits (the blend scales both inside head_bwd's dtconv, and
+            # d(logits)/d(bias) = (1 - ratio) under the ratio blend, 1 otherwise)
+            Mp = B * G2
+            Kp = (Mp + 7) // 8 * 8                                   # K of the GEMM: rows padded with zeros to a multiple of 8
+            ft = torch.zeros((Dr, Kp), dtype=BF16, device=dev)
+            ft[:, :Mp] = feat32.view(Mp, Dr).t()
+            dt_t = torch.zeros((P * P, Kp), dtype=BF16, device=dev)
+            dt_t[:, :Mp] = dtconv16.t()
+            dwt = _e((Dr, P * P), F32, dl)
+            abi.gemm(ft, dt_t, out_f32=dwt)
+            d_tconv_w = dwt.reshape(tw_shape)
+            scale = (1.0 - ratio_d) if (blend == abi.BLEND_RATIO and ratio_d is not None) else 1.0
+            d_tconv_b = (dl.sum() * scale).reshape(tb_shape)
         g = _e((M, Dr), F32, dl)
         abi.unslice_rows(dfeat.view(B, G2, Dr), S, 1, g.view(B, S, Dr))
         need_taps = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
@@ -766,7 +791,7 @@ class DecoderFn(torch.autograd.Function):
                 abi.gemm(g16, pk.w_red_t[i], out_f32=dt)
                 dtaps[len(dtaps) - 1 - i] = dt.view(B, S, Dv)
         ctx.saved_layers = None
-        return dtaps[0], dtaps[1], dtaps[2], dcond, d_add_w, d_add_b, d_ratio, None, None, None
+        return dtaps[0], dtaps[1], dtaps[2], dcond, d_add_w, d_add_b, d_ratio, None, None, None, d_tconv_w, d_tconv_b
 
 
 # ------------------------------------------------------------------------------------------------------------------

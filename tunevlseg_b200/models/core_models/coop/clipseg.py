@@ -51,8 +51,12 @@ class BaseCLIPSeg(HFCLIPSegWrapper, ABC):
             )
             self.residual_ratio = nn.Parameter(torch.tensor(residual_ratio))
         elif no_freeze_last_layer:
-            raise NotImplementedError("no_freeze_last_layer=True needs the transposed-convolution weight gradient: "
-                                      "outside the dgrad-only path (SURVEY.md section 8f, rank 4)")
+            # base_clipseg.py:73-80: the decoder's last layer (the transposed convolution) trains with the prompts.  Its weight
+            # gradient is one small GEMM, featT [Dr, B*G*G] x dlogits-per-patchT [P*P, B*G*G] (engine.DecoderFn.backward).
+            trans_conv = self.model.decoder.transposed_convolution
+            if isinstance(trans_conv, nn.Sequential):
+                raise NotImplementedError("use_complex_transposed_convolution=True (refined decoder) is outside the supported path")
+            trans_conv.requires_grad_(True)
 
     # ---- shared pieces ------------------------------------------------------------------------------------------
     @property
@@ -116,6 +120,14 @@ class BaseCLIPSeg(HFCLIPSegWrapper, ABC):
         conv = self.additive_decoder_layer[1]
         return conv.weight, conv.bias, self.residual_ratio
 
+    def _tconv_params(self):
+        """(weight, bias) of the transposed convolution when it trains (no_freeze_last_layer), else (None, None): the
+        decoder then reads the live parameters instead of the copies packed once per device."""
+        tc = self.model.decoder.transposed_convolution
+        if isinstance(tc, nn.Sequential) or not tc.weight.requires_grad:
+            return None, None
+        return tc.weight, tc.bias
+
     @abstractmethod
     def model_forward(self, input_ids=None, pixel_values=None, attention_mask=None, **kwargs) -> torch.Tensor: ...
 
@@ -145,7 +157,7 @@ class COOPCLIPSeg(BaseCLIPSeg):
         pk = self.packed
         taps, feats = engine.vision_tower_stock(pk, pixel_values)
         cond = self._text_condition(input_ids, attention_mask, self.context_learner, image_features=feats)
-        return engine.DecoderFn.apply(*taps, cond, None, None, None, pk, abi.BLEND_NONE, 0)
+        return engine.DecoderFn.apply(*taps, cond, None, None, None, pk, abi.BLEND_NONE, 0, *self._tconv_params())
 
 
 class VPTCLIPSeg(BaseCLIPSeg):
@@ -170,7 +182,7 @@ class VPTCLIPSeg(BaseCLIPSeg):
         taps = engine.VisionTowerFn.apply(lr.visual_stack(n_run), pixel_values, pk, lr.prompt_depth)
         w, b, _ = self._head_params()
         blend = abi.BLEND_NONE if w is None else abi.BLEND_ADD
-        return engine.DecoderFn.apply(*taps, cond, w, b, None, pk, blend, lr.num_context)
+        return engine.DecoderFn.apply(*taps, cond, w, b, None, pk, blend, lr.num_context, *self._tconv_params())
 
 
 class BaseMultimodalCLIPSeg(BaseCLIPSeg):
@@ -201,7 +213,7 @@ class BaseMultimodalCLIPSeg(BaseCLIPSeg):
         w, b, r = self._head_params()
         blend = abi.BLEND_NONE if w is None else abi.BLEND_RATIO
         n_strip = lr.num_context if isinstance(lr, BaseVisualLearner) else 0
-        return engine.DecoderFn.apply(*taps, cond, w, b, r, pk, blend, n_strip)
+        return engine.DecoderFn.apply(*taps, cond, w, b, r, pk, blend, n_strip, *self._tconv_params())
 
 
 class MapleCLIPSeg(BaseMultimodalCLIPSeg):
