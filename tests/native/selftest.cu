@@ -579,6 +579,7 @@ static void test_ln() {
     ln_case(9, 1024);
     ln_case(2051, 768);       // two rows per warp (M >= 2048), odd row count
     ln_case(15648, 64);       // half-warp-per-row kernels at the decoder shape
+    ln_case(9001, 768);       // M >= 8192: the persistent pipelined forward when TVS_LN_FWD=4 selects it
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -681,7 +682,7 @@ int main(int argc, char** argv) {
     if (what == "gemm" || what == "all") test_gemm();
     if (what == "ffn" || what == "all") test_ffn(what == "ffn");
     if (what == "gemmstep" || what == "all") test_gemm_step_shapes();
-    if (what == "lnprof") { ln_case(37, 768); ln_case(5, 512); ln_case(33, 256); ln_case(1003, 64); ln_case(9, 1024); ln_case(7, 2048); ln_timing(15648, 768); }
+    if (what == "lnprof") { ln_case(9001, 768); ln_case(37, 768); ln_case(5, 512); ln_case(33, 256); ln_case(1003, 64); ln_case(9, 1024); ln_case(7, 2048); ln_timing(15648, 768); }
     if (what == "gemmprof") {   // epilogue cost isolation on the fc1 shape (for timing / ncu)
         const int bn = argc > 3 ? atoi(argv[3]) : 256;
         printf("-- N=3072: bf16 out only\n");

@@ -153,6 +153,85 @@ layernorm_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ gam
     }
 }
 
+// Persistent, software-pipelined forward (TVS_LN_FWD=4): a fixed grid of warps walks the rows with a stride; the row a warp
+// will normalise NEXT is already in flight (registers) while it reduces and stores the current one, so in steady state only
+// bandwidth matters - the one-shot kernels above expose a DRAM round trip, the reductions and the store back to back per row
+// and leave the tail of every wave of CTAs half empty.
+template <int MAXC>
+__global__ void __launch_bounds__(LN2_WARPS * 32, 3)
+layernorm_fwd_pipe_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M,
+                          int D, float* __restrict__ y32, __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                          int round_out) {
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31;
+    const int nch = D >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * LN2_WARPS;
+    long long row = static_cast<long long>(blockIdx.x) * LN2_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    float4 cur[MAXC], nxt[MAXC];
+    {
+        const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+            if (lane + 32 * i < nch) cur[i] = __ldcs(xr + lane + 32 * i);
+    }
+    const float inv_d = 1.0f / static_cast<float>(D);
+    for (; row < M; row += stride) {
+        const long long rn = row + stride;
+        if (rn < M) {
+            const float4* xr = reinterpret_cast<const float4*>(x + rn * D);
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i)
+                if (lane + 32 * i < nch) nxt[i] = __ldcs(xr + lane + 32 * i);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+            if (lane + 32 * i < nch) s += (cur[i].x + cur[i].y) + (cur[i].z + cur[i].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float m = s / static_cast<float>(D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+            if (lane + 32 * i < nch) {
+                const float a = cur[i].x - m, b = cur[i].y - m, c = cur[i].z - m, d = cur[i].w - m;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float r = 1.0f / sqrtf(q / static_cast<float>(D) + eps);
+        (void)inv_d;
+        if (lane == 0) {
+            if (mean_out) mean_out[row] = m;
+            if (rstd_out) rstd_out[row] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nch) {
+                const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+                float4 o;
+                o.x = (cur[i].x - m) * r * g.x + b.x;
+                o.y = (cur[i].y - m) * r * g.y + b.y;
+                o.z = (cur[i].z - m) * r * g.z + b.z;
+                o.w = (cur[i].w - m) * r * g.w + b.w;
+                if (y32)
+                    reinterpret_cast<float4*>(y32 + row * D)[c] =
+                        (round_out & 1) ? make_float4(round_tf32_rn(o.x), round_tf32_rn(o.y), round_tf32_rn(o.z), round_tf32_rn(o.w)) : o;
+                if (y16)
+                    reinterpret_cast<uint2*>(y16 + row * D)[c] = (round_out & 2) ? make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w))
+                                                                                : make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) cur[i] = nxt[i];
+    }
+}
+
 // VAR 0: dx_add is fetched after the reductions (two dependent DRAM round trips per row); VAR 1: every load of the row is
 // issued before the first reduction (one round trip, 24 more registers); VAR 2: VAR 1 + streaming (evict-first) hints on
 // the operands nobody re-reads (saved x, the incoming fp32 gradient stream and its fp32 successor).
@@ -486,7 +565,14 @@ extern "C" __attribute__((visibility("default"))) int tvs_layernorm_fwd(const fl
         else
             TVS_CUDA(launch_pdl(layernorm_fwd_wide_kernel<2, 3>, dim3(gridw), dim3(LNW_ROWS * 96), 0, static_cast<cudaStream_t>(stream), 1, x, gamma, beta,
                                 eps, static_cast<long long>(M), D, y_f32, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
-    } else if (D <= 768 && M >= 2048 && variant == 1) {      // large row counts: two rows per warp
+    } else if (D <= 768 && M >= 8192 && variant == 4) {      // persistent, software-pipelined (one row in flight per warp)
+        static const int ctas_per_sm = [] { const char* e = getenv("TVS_LN_PIPE_CTAS"); return e ? atoi(e) : 4; }();
+        const long long want = (static_cast<long long>(M) + LN2_WARPS - 1) / LN2_WARPS;
+        const long long cap = static_cast<long long>(sm_count()) * ctas_per_sm;
+        TVS_CUDA(launch_pdl(layernorm_fwd_pipe_kernel<6>, dim3(static_cast<unsigned>(want < cap ? want : cap)), dim3(LN2_WARPS * 32), 0,
+                            static_cast<cudaStream_t>(stream), 1, x, gamma, beta, eps, static_cast<long long>(M), D, y_f32,
+                            static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
+    } else if (D <= 768 && M >= 2048 && (variant == 1 || variant == 4)) {      // large row counts: two rows per warp
         const unsigned grid2 = static_cast<unsigned>((M + 2 * LN2_WARPS - 1) / (2 * LN2_WARPS));
         TVS_CUDA(launch_pdl(layernorm_fwd2_kernel<6>, dim3(grid2), dim3(LN2_WARPS * 32), 0, static_cast<cudaStream_t>(stream), 1, x, gamma, beta, eps,
                             static_cast<long long>(M), D, y_f32, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, round_tf32));
