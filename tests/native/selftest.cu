@@ -298,7 +298,7 @@ static void attn_case(int B, int S, int H, int hd, int causal, bool use_mask, bo
     auto lse = host(dLse, (size_t)B * H * S);
 
     // CPU reference in double from the bf16-rounded inputs
-    double err_o = 0, err_l = 0, err_dq = 0, err_dk = 0, err_dv = 0, sc_dq = 1e-9, sc_dk = 1e-9, sc_dv = 1e-9;
+    double err_o = 0, err_l = 0, err_dq = 0, err_dk = 0, err_dv = 0, sc_dq = 1e-9, sc_dk = 1e-9, sc_dv = 1e-9, sc_o = 0;
     std::vector<double> P((size_t)S * S), dP((size_t)S * S);
     for (int b = 0; b < B; ++b)
         for (int h = 0; h < H; ++h) {
@@ -329,6 +329,7 @@ static void attn_case(int B, int S, int H, int hd, int causal, bool use_mask, bo
                     for (int j = 0; j < S; ++j) o += P[(size_t)i * S + j] * v(j, d);
                     O[(size_t)i * hd + d] = o;
                     err_o = std::max(err_o, fabs(o - (double)bf(out[((size_t)b * S + i) * E + h * hd + d])));
+                    sc_o = std::max(sc_o, fabs(o));
                 }
             }
             // backward
@@ -362,7 +363,9 @@ static void attn_case(int B, int S, int H, int hd, int causal, bool use_mask, bo
         }
     char name[160];
     snprintf(name, sizeof name, "attn B=%d S=%d H=%d hd=%d causal=%d mask=%d  out", B, S, H, hd, causal, use_mask);
-    report(name, err_o, 2e-2);
+    // bf16 output: half an ulp is 2^-9 of the value; probabilities are bf16 too.  2e-2 absolute covers |out| <= ~3, beyond that
+    // the bound scales with the largest reference output (the inputs are random: their range moves with the random stream)
+    report(name, err_o, std::max(2e-2, 6e-3 * sc_o));
     snprintf(name, sizeof name, "attn B=%d S=%d H=%d hd=%d causal=%d mask=%d  lse", B, S, H, hd, causal, use_mask);
     report(name, err_l, 1e-3);
     snprintf(name, sizeof name, "attn B=%d S=%d H=%d hd=%d causal=%d mask=%d  dq (rel)", B, S, H, hd, causal, use_mask);
@@ -405,7 +408,6 @@ static void attn_timing(int B, int S, int H, int hd) {
 
 static void test_attn(bool timing = true) {
     attn_case(1, 128, 1, 64, 0, false);
-    attn_case(10, 300, 12, 64, 0, false);      // 360 (tile, head, sample) items > 2 x 148 resident CTAs: the persistent kernels' multi-item path
     attn_case(1, 64, 1, 64, 0, false);
     attn_case(2, 493, 12, 64, 0, false);
     attn_case(2, 100, 2, 64, 0, false);
@@ -414,6 +416,9 @@ static void test_attn(bool timing = true) {
     attn_case(2, 12, 8, 64, 1, true);
     attn_case(2, 130, 4, 16, 0, false);
     attn_case(1, 493, 4, 16, 0, false);
+    // (appended after the older cases so that those keep their random streams)
+    attn_case(10, 300, 12, 64, 0, false);      // 360 (tile, head, sample) items > 2 x 148 resident CTAs: the persistent kernels' multi-item path
+    attn_case(40, 100, 8, 64, 0, false);       // 320 items of TWO inner steps each (<= ring depth): the next item's outer tiles are requested after the loop
     if (!timing) return;
     attn_timing(32, 489, 12, 64);
     attn_timing(32, 489, 4, 16);
@@ -675,13 +680,14 @@ int main(int argc, char** argv) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("device: %s, %d SMs, abi %d\n", prop.name, prop.multiProcessorCount, tvs_version());
-    if (what == "loss" || what == "all") test_loss();
-    if (what == "ln" || what == "all") test_ln();
-    if (what == "attn" || what == "all") test_attn();
-    if (what == "attncheck") test_attn(false);      // correctness cases only (compute-sanitizer runs)
-    if (what == "gemm" || what == "all") test_gemm();
-    if (what == "ffn" || what == "all") test_ffn(what == "ffn");
-    if (what == "gemmstep" || what == "all") test_gemm_step_shapes();
+    // every group starts from its own seed: its data do not depend on which groups ran before it ("all" vs a single group)
+    if (what == "loss" || what == "all") { rng.seed(1234); test_loss(); }
+    if (what == "ln" || what == "all") { rng.seed(2345); test_ln(); }
+    if (what == "attn" || what == "all") { rng.seed(3456); test_attn(); }
+    if (what == "attncheck") { rng.seed(3456); test_attn(false); }      // correctness cases only (compute-sanitizer runs)
+    if (what == "gemm" || what == "all") { rng.seed(4567); test_gemm(); }
+    if (what == "ffn" || what == "all") { rng.seed(5678); test_ffn(what == "ffn"); }
+    if (what == "gemmstep" || what == "all") { rng.seed(6789); test_gemm_step_shapes(); }
     if (what == "lnprof") { ln_case(9001, 768); ln_case(37, 768); ln_case(5, 512); ln_case(33, 256); ln_case(1003, 64); ln_case(9, 1024); ln_case(7, 2048); ln_timing(15648, 768); }
     if (what == "gemmprof") {   // epilogue cost isolation on the fc1 shape (for timing / ncu)
         const int bn = argc > 3 ? atoi(argv[3]) : 256;
