@@ -23,6 +23,9 @@ def reference_path() -> str | None:
     built = os.path.join(HERE, "_ref")
     if os.path.exists(os.path.join(built, "src", "models", "core_models", "coop", "__init__.pyc")):
         return built
+    archive = os.path.join(built, "reference_src.zip")          # the same byte-compiled modules as one archive (zipimport)
+    if os.path.exists(archive):
+        return archive
     return None
 
 

@@ -102,3 +102,24 @@ def test_cris_known_quirks():
     assert bool(d["learner_hasgrad/context_vectors"]) and d["learner_grad/context_vectors"].abs().max() > 0
     for k in ("additive_decoder_layer.0.weight", "additive_decoder_layer.2.weight", "additive_decoder_layer.2.bias", "residual_ratio"):
         assert bool(d[f"head_hasgrad/{k}"])
+
+
+def test_built_reference_archive_imports_without_sources():
+    """bench.py's reference arm on the GPU box: /root/reference is absent there and file-sync tools may drop *.pyc, so
+    oracle/build_ref.py also packs the byte-compiled reference into oracle/_ref/reference_src.zip; the reference's own
+    MapleCLIPSeg must import from that archive alone (zipimport, sourceless members, packages without __init__)."""
+    import os
+    import subprocess
+    import sys
+
+    import pytest
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    archive = os.path.join(root, "oracle", "_ref", "reference_src.zip")
+    if not os.path.exists(archive):
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); from oracle import ref_shim; ref_shim.install_shim(); "
+            "import src.models.core_models.coop as m; print(m.MapleCLIPSeg.__name__, m.__spec__.origin)") % (root, archive)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "MapleCLIPSeg" in res.stdout and "reference_src.zip" in res.stdout, res.stdout
