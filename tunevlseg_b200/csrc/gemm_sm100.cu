@@ -1157,7 +1157,10 @@ static int launch_gemm(const tvs_gemm_args& a, const GemmEpilogue& ep, cudaStrea
     const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
     constexpr int STAGES2 = BN == 256 ? 6 : 8;     // 32 KB / 24 KB per stage per CTA in pair mode
     // pairs win on the compute-heavy shapes; the memory-bound N = K = 768 residual GEMM is slightly better with single CTAs
-    const bool heavy = static_cast<long long>(a.N) * a.K >= 768LL * 1024;
+    // (measured at M = 15 648, N = K = 768: with the fp32 residual in / out 38.7 us single vs 39.6 us pairs; with a plain 16-bit output
+    // - the out-proj dgrad - 23.0 us single vs 21.0 us pairs, so that case takes the pairs too)
+    const bool heavy = static_cast<long long>(a.N) * a.K >= 768LL * 1024 ||
+                       (static_cast<long long>(a.N) * a.K >= 512LL * 1024 && a.out_f32 == nullptr && a.residual == nullptr && a.pre_bf16 == nullptr);
     const bool use2 = BN >= 128 && (mode == 2 || (mode == -1 && tiles >= 2LL * sm_count() && heavy));
     if (use2) return launch_gemm_cl<(BN >= 128 ? BN : 128), STAGES2, TF32, 2>(a, ep, stream);
     return launch_gemm_cl<BN, STAGES, TF32, 1>(a, ep, stream);
