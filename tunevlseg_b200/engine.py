@@ -574,28 +574,42 @@ class TextTowerFn(torch.autograd.Function):
 
     @staticmethod
     @_phase("text_tower.fwd")
-    def forward(ctx, emb, ctx_deep, key_mask, pool_pos, pk: PackedClipSeg, n_ctx: int):
+    def forward(ctx, emb, ctx_deep, key_mask, pool_pos, pk: PackedClipSeg, n_ctx: int, defer=None):
+        """``defer`` (a list): the tower's kernels are NOT enqueued now - a closure that enqueues them (writing into the returned
+        tensor) is appended instead, to be called later on the same stream, before anything reads the result.  This separates
+        WHEN the autograd node is created (its sequence number decides which tower's backward autograd enqueues first) from
+        WHEN the forward kernels enter the stream / the captured graph (clipseg.BaseMultimodalCLIPSeg.model_forward)."""
         B, S, D = emb.shape
         need_grad = emb.requires_grad or (ctx_deep is not None and ctx_deep.requires_grad)
-        x = emb.detach().to(F32).contiguous().view(B * S, D).clone()
+        emb_d = emb.detach()
         cd = None if ctx_deep is None else ctx_deep.detach().to(F32).contiguous()
         depth = 1 if cd is None else cd.shape[0] + 1
         km = None if key_mask is None else key_mask.to(torch.uint8).contiguous()
-        saved = []
-        for idx in range(1, len(pk.t_layers) + 1):
-            x, sv = encoder_layer_fwd(pk.t_layers[idx - 1], x, B, S, True, km, pk.eps, need_grad,
-                                      overwrite=(cd[idx - 1], 1, n_ctx) if idx < depth else None)
-            saved.append(sv)
-        xf = _e((B * S, D), F32, x)
-        mean_f, rstd_f = _e((B * S,), F32, x), _e((B * S,), F32, x)
-        abi.layernorm_fwd(x, pk.fin_g, pk.fin_b, pk.eps, y_f32=xf, mean=mean_f, rstd=rstd_f)
-        rows = torch.arange(B, device=x.device) * S + pool_pos.to(x.device)
-        pooled = xf.index_select(0, rows)
-        cond = _e((B, pk.w_tproj.shape[0]), F32, x)
-        abi.gemm(rn_act(pooled), pk.w_tproj, out_f32=cond)
-        ctx.pk, ctx.saved, ctx.km = pk, saved, km
-        ctx.fin = (x, mean_f, rstd_f, rows)
+        cond = _e((B, pk.w_tproj.shape[0]), F32, emb_d)
+        ctx.pk, ctx.km = pk, km
         ctx.dims = (B, S, D, depth, n_ctx, None if cd is None else tuple(cd.shape))
+
+        def run():
+            with torch.no_grad():
+                x = emb_d.to(F32).contiguous().view(B * S, D).clone()
+                saved = []
+                for idx in range(1, len(pk.t_layers) + 1):
+                    x, sv = encoder_layer_fwd(pk.t_layers[idx - 1], x, B, S, True, km, pk.eps, need_grad,
+                                              overwrite=(cd[idx - 1], 1, n_ctx) if idx < depth else None)
+                    saved.append(sv)
+                xf = _e((B * S, D), F32, x)
+                mean_f, rstd_f = _e((B * S,), F32, x), _e((B * S,), F32, x)
+                abi.layernorm_fwd(x, pk.fin_g, pk.fin_b, pk.eps, y_f32=xf, mean=mean_f, rstd=rstd_f)
+                rows = torch.arange(B, device=x.device) * S + pool_pos.to(x.device)
+                pooled = xf.index_select(0, rows)
+                abi.gemm(rn_act(pooled), pk.w_tproj, out_f32=cond)
+                ctx.saved = saved
+                ctx.fin = (x, mean_f, rstd_f, rows)
+
+        if defer is None:
+            run()
+        else:
+            defer.append(run)
         return cond
 
     @staticmethod
@@ -616,7 +630,7 @@ class TextTowerFn(torch.autograd.Function):
                 abi.prompt_grad(g.view(B, S, D), 1, n, dctx[idx - 1], zero_rows=True)
             g, _ = encoder_layer_bwd(pk.t_layers[idx - 1], ctx.saved[idx - 1], g, None, B, S, True, ctx.km)
         ctx.saved = None
-        return g.view(B, S, D), dctx, None, None, None, None
+        return g.view(B, S, D), dctx, None, None, None, None, None
 
 
 @torch.no_grad()

@@ -78,8 +78,9 @@ class BaseCLIPSeg(HFCLIPSegWrapper, ABC):
             raise ValueError("Make sure to pass as many prompt texts as there are query images")
         abi.check_cuda_input(pixel_values)      # TvsError for host tensors: there is no CPU path
 
-    def _text_condition(self, input_ids, attention_mask, learner, image_features=None):
-        """Conditional embedding (B, projection_dim).  ``learner`` None = stock HF text path (no prompts)."""
+    def _text_condition(self, input_ids, attention_mask, learner, image_features=None, defer=None):
+        """Conditional embedding (B, projection_dim).  ``learner`` None = stock HF text path (no prompts).
+        ``defer``: see engine.TextTowerFn.forward (the tower's kernels are enqueued later by the closure appended to it)."""
         pk = self.packed
         tm = self.model.clip.text_model
         max_len = self.model.config.text_config.max_position_embeddings
@@ -101,7 +102,7 @@ class BaseCLIPSeg(HFCLIPSegWrapper, ABC):
         if learner is not None:
             pool = torch.clamp(pool, max=max_len - 1)
         key_mask = None if attention_mask is None else (attention_mask != 0).to(torch.uint8)
-        return engine.TextTowerFn.apply(emb, deep, key_mask, pool, pk, n)
+        return engine.TextTowerFn.apply(emb, deep, key_mask, pool, pk, n, defer)
 
     def _text_stream(self) -> torch.cuda.Stream:
         if os.environ.get("TVS_TEXT_STREAM", "1") == "0":      # A/B switch: text tower in line with the vision tower
@@ -205,9 +206,27 @@ class BaseMultimodalCLIPSeg(BaseCLIPSeg):
         main = torch.cuda.current_stream()
         side = self._text_stream()
         side.wait_stream(main)            # after the visual branch of a shared learner has filled its cache
-        with torch.cuda.stream(side):
-            cond = self._text_condition(input_ids, attention_mask, lr)
-        taps = engine.VisionTowerFn.apply(vis_ctx, pixel_values, pk, lr.prompt_depth)
+        # Which branch is enqueued / captured first matters (same box, ms per step): text first (default) 9.18-9.19; vision forward
+        # first with the text node still created first ("2", deferred text kernels) 9.24-9.26; vision first in forward AND hence the
+        # text backward first ("1") 9.90-10.02 - the branch captured first is served first, and the text branch is the one whose
+        # ~190 launch latencies must start early to stay hidden.  The switches stay for A/B only.
+        mode = os.environ.get("TVS_VISION_FIRST", "0")
+        if mode == "1":      # experiment: enqueue / capture the critical branch first (the text node then has the higher sequence
+            taps = engine.VisionTowerFn.apply(vis_ctx, pixel_values, pk, lr.prompt_depth)      # number: ITS backward is enqueued first)
+            with torch.cuda.stream(side):
+                cond = self._text_condition(input_ids, attention_mask, lr)
+        elif mode == "2":    # text node created first (so the vision backward is still enqueued first), its kernels enqueued after
+            deferred: list = []                                                                    # the vision tower's
+            with torch.cuda.stream(side):
+                cond = self._text_condition(input_ids, attention_mask, lr, defer=deferred)
+            taps = engine.VisionTowerFn.apply(vis_ctx, pixel_values, pk, lr.prompt_depth)
+            with torch.cuda.stream(side):
+                for run in deferred:
+                    run()
+        else:
+            with torch.cuda.stream(side):
+                cond = self._text_condition(input_ids, attention_mask, lr)
+            taps = engine.VisionTowerFn.apply(vis_ctx, pixel_values, pk, lr.prompt_depth)
         main.wait_stream(side)
         cond.record_stream(main)
         w, b, r = self._head_params()
