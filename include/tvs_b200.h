@@ -63,9 +63,12 @@ int32_t tvs_gemm_last_variant(void);
  * The 16-bit pointers below are named *_bf16 for history; their format follows these flags. */
 enum { TVS_AB_BF16 = 0, TVS_AB_TF32 = 1, TVS_AB_F16 = 2 /* A, W IEEE fp16 */ };
 enum { TVS_GEMM_ROUND_OUT_TF32 = 1, TVS_GEMM_OUT16_F16 = 2,
+       TVS_GEMM_PRE_DGELU = 8 /* with TVS_ACT_QGELU and pre_bf16: store QuickGELU'(pre-activation) instead of the pre-activation
+                                 (the forward has the sigmoid in registers anyway; the dgrad then only multiplies, TVS_ACT_MULAUX) */,
        TVS_GEMM_STREAM_K = 4 /* opt-in: cut the (tile, k-block) space into one contiguous range per CTA pair (specialised pair
                                 kernels only; measured SLOWER than whole-tile round robin on the tower shapes) */ };     /* tvs_gemm_args.reserved (flags) */
-enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4, TVS_ACT_RES_RELU = 5 };
+enum { TVS_ACT_NONE = 0, TVS_ACT_QGELU = 1, TVS_ACT_RELU = 2, TVS_ACT_DQGELU = 3, TVS_ACT_DRELU = 4, TVS_ACT_RES_RELU = 5,
+       TVS_ACT_MULAUX = 6 /* v *= aux_bf16[m,n]: the dgrad through an activation whose DERIVATIVE the forward saved (TVS_GEMM_PRE_DGELU) */ };
 
 typedef struct tvs_gemm_args {
     const void* A;  int64_t lda;           /* bf16 [M,K] */

@@ -39,7 +39,7 @@ def round_tf32(x, y):
 
 
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=abi.ACT_NONE, tile_n=0, round_out=False, conv_hw=None,
-         overwrite=None):
+         overwrite=None, stream_k=False, pre_is_grad=False):
     H16 = (BF16, torch.float16)          # kind::f16 takes two bf16 or two fp16 operands (mixing is illegal on sm_100); kind::tf32 two fp32
     assert A.dtype == W.dtype and A.dtype in (BF16, torch.float16, F32), (A.dtype, W.dtype)
     assert A.dim() == 2 and W.dim() == 2, (A.shape, W.shape)
@@ -61,7 +61,11 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
         assert bias.numel() == W.shape[0]
         v = v + bias
     if pre_bf16 is not None:
-        pre_bf16.copy_(v)
+        if pre_is_grad:          # TVS_GEMM_PRE_DGELU: the derivative of the activation is saved instead of the pre-activation
+            assert act == abi.ACT_QGELU
+            pre_bf16.copy_(_qg_grad(v))
+        else:
+            pre_bf16.copy_(v)
     if act == abi.ACT_QGELU:
         v = _qg(v)
     elif act == abi.ACT_RELU:
@@ -70,6 +74,8 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
         v = v * _qg_grad(aux_bf16.float())
     elif act == abi.ACT_DRELU:
         v = v * (aux_bf16.float() > 0)
+    elif act == abi.ACT_MULAUX:
+        v = v * aux_bf16.float()
     if residual is not None:
         assert residual.shape == v.shape
         v = v + residual

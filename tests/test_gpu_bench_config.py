@@ -111,6 +111,7 @@ def test_full_geometry_at_bench_batch(case, B, with_grads):
 TOWER_GEMMS = [
     ("qkv", 2304, 768, "bias", "f16"), ("out_proj", 768, 768, "residual", "f16"), ("fc1", 3072, 768, "qgelu_pre", "f16"),
     ("fc2", 768, 3072, "residual", "f16"),
+    ("fc1_dgelu", 3072, 768, "qgelu_pre_grad", "f16"), ("d_fc2_mul", 3072, 768, "mulaux", "bf16"),
     ("d_fc2", 3072, 768, "dqgelu", "bf16"), ("d_fc1", 768, 3072, "plain", "bf16"), ("d_out_proj", 768, 768, "plain", "bf16"),
     ("d_qkv", 768, 2304, "plain", "bf16"),
 ]
@@ -147,6 +148,17 @@ def test_tower_gemm_shapes_at_bench_rows(name, N, K, epi, fmt, tile_n):
         kw = dict(bias=bias, pre_bf16=pre, out_bf16=out, act=abi.ACT_QGELU)
         u = ref + bias
         checks = [(pre, u, 2 ** -7), (out, u * torch.sigmoid(1.702 * u), max(ulp, 2 ** -9))]      # tanh.approx sigmoid: ~2^-11
+    elif epi == "qgelu_pre_grad":           # fc1 as the engine runs it: the saved tensor is QuickGELU'(u) (TVS_GEMM_PRE_DGELU)
+        pre, out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda"), torch.empty(M, N, dtype=dt, device="cuda")
+        kw = dict(bias=bias, pre_bf16=pre, out_bf16=out, act=abi.ACT_QGELU, pre_is_grad=True)
+        u = ref + bias
+        sg = torch.sigmoid(1.702 * u)
+        checks = [(pre, sg * (1 + 1.702 * u * (1 - sg)), 2 ** -7), (out, u * sg, max(ulp, 2 ** -9))]
+    elif epi == "mulaux":                   # dgrad through the activation with the saved derivative: one multiply
+        aux = (torch.rand(M, N, device="cuda", generator=g) * 1.2 - 0.1).to(torch.bfloat16)
+        out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        kw = dict(aux_bf16=aux, out_bf16=out, act=abi.ACT_MULAUX)
+        checks = [(out, ref * aux.float(), 2 ** -7)]
     elif epi == "dqgelu":
         aux = (torch.randn(M, N, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
         out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")

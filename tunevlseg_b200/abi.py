@@ -15,7 +15,7 @@ import torch
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtvs_b200.so")
 
-ACT_NONE, ACT_QGELU, ACT_RELU, ACT_DQGELU, ACT_DRELU, ACT_RES_RELU = range(6)
+ACT_NONE, ACT_QGELU, ACT_RELU, ACT_DQGELU, ACT_DRELU, ACT_RES_RELU, ACT_MULAUX = range(7)
 AB_BF16, AB_TF32, AB_F16 = range(3)
 H16 = (torch.bfloat16, torch.float16)       # 16-bit activation formats of the kind::f16 MMA (per operand)
 BLEND_NONE, BLEND_RATIO, BLEND_ADD = range(3)
@@ -179,14 +179,16 @@ def _chk(t: torch.Tensor | None, dtype, name: str, dim2: bool = False) -> None:
 
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf16=None, aux_bf16=None, act=ACT_NONE,
-         tile_n=0, round_out=False, conv_hw=None, overwrite=None, stream_k=False):
+         tile_n=0, round_out=False, conv_hw=None, overwrite=None, stream_k=False, pre_is_grad=False):
     """C[M,N] = epilogue(A[M,K] @ W[N,K]^T); see tvs_gemm_bf16 in include/tvs_b200.h.  2-D views with a row stride
     are accepted (ld = stride(0)).  ``round_out``: out_f32 is rounded to nearest tf32 (it only feeds further tf32 GEMMs).
     ``conv_hw=(H, W)``: implicit-GEMM 3x3 convolution - A is the zero-bordered image [B*(H+2)*(W+2), C] from ``pad_nhwc``,
     W is [N, 9*C]; outputs / residual are unpadded [B*H*W, N].
     ``overwrite=(ctx, S, row0, n)``: deep-prompt overwrite fused into the epilogue - output rows at positions row0 .. row0+n-1 of
     every S-row sample receive ctx ((n, N) shared or (B, n, N) per sample, f32) instead of the result (fc2 of a vision block).
-    ``stream_k``: opt-in stream-K schedule of the specialised pair kernels (TVS_GEMM_STREAM_K; measured slower - off by default)."""
+    ``stream_k``: opt-in stream-K schedule of the specialised pair kernels (TVS_GEMM_STREAM_K; measured slower - off by default).
+    ``pre_is_grad`` (with ACT_QGELU and pre_bf16): pre_bf16 receives QuickGELU'(pre-activation) instead of the pre-activation
+    (TVS_GEMM_PRE_DGELU); the dgrad through the activation is then ``act=ACT_MULAUX`` with that tensor as ``aux_bf16``."""
     require_device()
     ab = {(torch.bfloat16, torch.bfloat16): AB_BF16, (torch.float32, torch.float32): AB_TF32, (torch.float16, torch.float16): AB_F16}.get((A.dtype, W.dtype))
     if ab is None:      # a mixed fp16 x bf16 kind::f16 MMA is an illegal instruction on sm_100 (measured)
@@ -222,7 +224,7 @@ def gemm(A, W, *, bias=None, residual=None, out_f32=None, out_bf16=None, pre_bf1
     g.aux_bf16, g.ldaux = _p(aux_bf16), (aux_bf16.stride(0) if aux_bf16 is not None else 0)
     g.act, g.tile_n = act, tile_n
     g.ab_dtype = ab
-    g.reserved = (1 if round_out else 0) | (2 if (out_bf16 is not None and out_bf16.dtype == torch.float16) else 0) | (4 if stream_k else 0)
+    g.reserved = (1 if round_out else 0) | (2 if (out_bf16 is not None and out_bf16.dtype == torch.float16) else 0) | (4 if stream_k else 0) | (8 if pre_is_grad else 0)
     g.conv_h, g.conv_w = conv_hw if conv_hw is not None else (0, 0)
     if overwrite is not None:
         ctx, S_, row0, n_ = overwrite

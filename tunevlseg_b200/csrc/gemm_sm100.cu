@@ -58,6 +58,7 @@ struct GemmEpilogue {
     // stream-K (specialised pair kernels, static schedule): the (tile, k-block) iteration space is cut into one contiguous
     // range per cluster; a tile cut in two is finished by the cluster that holds its FIRST k-blocks (it reaches the tile last),
     // the other cluster computes the later k-blocks first and parks its raw fp32 accumulator in sk_ws (launch_gemm_inst)
+    int pre_dgelu;   // TVS_GEMM_PRE_DGELU: pre_bf16 receives QuickGELU'(v) instead of v
     float* sk_ws;
     int* sk_flags;
     int sk_q;        // iterations (k-blocks) per cluster; 0 = off (round-robin whole tiles)
@@ -213,20 +214,24 @@ __device__ __forceinline__ float rn_tf32f(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ bool is_dact(int act) { return act == TVS_ACT_DQGELU || act == TVS_ACT_DRELU; }
+__device__ __forceinline__ bool is_dact(int act) { return act == TVS_ACT_DQGELU || act == TVS_ACT_DRELU || act == TVS_ACT_MULAUX; }
 
 __device__ __forceinline__ float epi_act(const GemmEpilogue& ep, float v, float aux) {
     if (ep.act == TVS_ACT_QGELU) return quick_gelu(v);
     if (ep.act == TVS_ACT_RELU) return fmaxf(v, 0.0f);
     if (ep.act == TVS_ACT_DQGELU) return v * quick_gelu_grad(aux);
     if (ep.act == TVS_ACT_DRELU) return aux > 0.0f ? v : 0.0f;
+    if (ep.act == TVS_ACT_MULAUX) return v * aux;
     return v;
 }
 
 // 4 consecutive columns [col, col+4) of one row, all vector accesses 16-byte (f32) / 8-byte (bf16) aligned
 __device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, float4 bias, long long row, int col) {
     v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-    if (ep.pre_bf16) *reinterpret_cast<uint2*>(ep.pre_bf16 + row * ep.ldpre + col) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    if (ep.pre_bf16) {
+        const float4 s4 = ep.pre_dgelu ? make_float4(quick_gelu_grad(v.x), quick_gelu_grad(v.y), quick_gelu_grad(v.z), quick_gelu_grad(v.w)) : v;
+        *reinterpret_cast<uint2*>(ep.pre_bf16 + row * ep.ldpre + col) = make_uint2(pack_bf16x2(s4.x, s4.y), pack_bf16x2(s4.z, s4.w));
+    }
     if (ep.act != TVS_ACT_NONE) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (is_dact(ep.act)) {
@@ -252,7 +257,7 @@ __device__ __forceinline__ void epilogue_vec4(const GemmEpilogue& ep, float4 v, 
 // scalar, fully predicated (ragged N such as the 25-tap additive map, or unaligned leading dimensions)
 __device__ __forceinline__ void epilogue_scalar(const GemmEpilogue& ep, float x, long long row, int c) {
     if (ep.bias) x += __ldg(ep.bias + c);
-    if (ep.pre_bf16) ep.pre_bf16[row * ep.ldpre + c] = __float2bfloat16(x);
+    if (ep.pre_bf16) ep.pre_bf16[row * ep.ldpre + c] = __float2bfloat16(ep.pre_dgelu ? quick_gelu_grad(x) : x);
     if (ep.act != TVS_ACT_NONE) x = epi_act(ep, x, is_dact(ep.act) ? __bfloat162float(ep.aux_bf16[row * ep.ldaux + c]) : 0.f);
     if (ep.residual) x += ep.residual[row * ep.ldr + c];
     if (ep.act == TVS_ACT_RES_RELU) x = fmaxf(x, 0.f);
@@ -343,7 +348,16 @@ __device__ __forceinline__ void epilogue_direct(const GemmEpilogue& ep, const ui
             for (int i = 0; i < 8; ++i) v[8 * q + i] += __uint_as_float(b[i]);
         }
     }
-    if (ep.pre_bf16) st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, v);
+    if (ep.pre_bf16) {
+        if (ep.pre_dgelu) {
+            float gd[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gd[i] = quick_gelu_grad(v[i]);
+            st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, gd);
+        } else {
+            st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, v);
+        }
+    }
     if (ep.act == TVS_ACT_QGELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
@@ -416,16 +430,37 @@ __device__ __forceinline__ void epilogue_spec(const GemmEpilogue& ep, const uint
             st256(ep.out_f32 + row * ep.ldo32 + col0 + 8 * q, o);
         }
     } else if (EPI == EPI_FC1) {
-        st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, v);
+        if (ep.pre_dgelu) {      // kernel-uniform: save QuickGELU'(u) instead of u - the sigmoid is in registers here, and the dgrad
+            float gd[32];        // through the activation becomes one multiply per element (TVS_ACT_MULAUX) instead of a MUFU + 8 ops
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+            for (int i = 0; i < 32; ++i) {
+                const float t = 1.702f * v[i];
+                const float sg = sigmoid_tanh(t);
+                gd[i] = sg * fmaf(t, 1.0f - sg, 1.0f);
+                v[i] *= sg;
+            }
+            st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, gd);
+        } else {
+            st_bf16_row32(ep.pre_bf16 + row * ep.ldpre + col0, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+        }
         st_f16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
     } else if (EPI == EPI_DQGELU) {
+        if (ep.act == TVS_ACT_MULAUX) {      // kernel-uniform: aux already holds the derivative
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float2 u = unpack_bf16x2(ext[i]);
-            v[2 * i] *= quick_gelu_grad(u.x);
-            v[2 * i + 1] *= quick_gelu_grad(u.y);
+            for (int i = 0; i < 16; ++i) {
+                const float2 u = unpack_bf16x2(ext[i]);
+                v[2 * i] *= u.x;
+                v[2 * i + 1] *= u.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float2 u = unpack_bf16x2(ext[i]);
+                v[2 * i] *= quick_gelu_grad(u.x);
+                v[2 * i + 1] *= quick_gelu_grad(u.y);
+            }
         }
         st_bf16_row32(ep.out_bf16 + row * ep.ldo16 + col0, v);
     }
@@ -1132,7 +1167,7 @@ static int pick_epi(const tvs_gemm_args& a, const GemmEpilogue& ep, bool tf32) {
     if (ep.act == TVS_ACT_NONE && o16 && !ep.out16_f16 && !o32 && !res && !pre) return EPI_OUT_BF16;
     if (ep.act == TVS_ACT_NONE && o32 && res && !o16 && !pre) return EPI_RES_F32;
     if (ep.act == TVS_ACT_QGELU && o16 && ep.out16_f16 && pre && !o32 && !res) return EPI_FC1;
-    if (ep.act == TVS_ACT_DQGELU && o16 && !ep.out16_f16 && !o32 && !res && !pre && !ep.bias) return EPI_DQGELU;
+    if ((ep.act == TVS_ACT_DQGELU || ep.act == TVS_ACT_MULAUX) && o16 && !ep.out16_f16 && !o32 && !res && !pre && !ep.bias) return EPI_DQGELU;
     return EPI_GENERIC;
 }
 
@@ -1208,7 +1243,8 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     TVS_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
                 "tvs_gemm_bf16: A and W must be 16-byte aligned");
     TVS_REQUIRE(a.out_f32 || a.out_bf16 || a.pre_bf16, "tvs_gemm_bf16: no output");
-    TVS_REQUIRE(!(a.act == TVS_ACT_DQGELU || a.act == TVS_ACT_DRELU) || a.aux_bf16, "tvs_gemm_bf16: aux_bf16 required for derivative epilogues");
+    TVS_REQUIRE(!(a.act == TVS_ACT_DQGELU || a.act == TVS_ACT_DRELU || a.act == TVS_ACT_MULAUX) || a.aux_bf16, "tvs_gemm_bf16: aux_bf16 required for derivative epilogues");
+    TVS_REQUIRE(!(a.reserved & TVS_GEMM_PRE_DGELU) || (a.act == TVS_ACT_QGELU && a.pre_bf16), "tvs_gemm_bf16: TVS_GEMM_PRE_DGELU needs TVS_ACT_QGELU and pre_bf16");
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec_ok = (!a.out_f32 || (a.ldo32 % 4 == 0 && al16(a.out_f32))) && (!a.out_bf16 || (a.ldo16 % 4 == 0 && al16(a.out_bf16))) &&
                         (!a.pre_bf16 || (a.ldpre % 4 == 0 && al16(a.pre_bf16))) && (!a.aux_bf16 || (a.ldaux % 4 == 0 && al16(a.aux_bf16))) &&
@@ -1228,6 +1264,7 @@ extern "C" __attribute__((visibility("default"))) int tvs_gemm_bf16(const tvs_ge
     ep.act = a.act;
     ep.round_out = a.reserved & TVS_GEMM_ROUND_OUT_TF32;
     ep.out16_f16 = (a.reserved & TVS_GEMM_OUT16_F16) ? 1 : 0;
+    ep.pre_dgelu = (a.reserved & TVS_GEMM_PRE_DGELU) ? 1 : 0;
     ep.fmt_a = ep.fmt_b = a.ab_dtype == TVS_AB_F16 ? 0 : 1;
     ep.ovr_ctx = a.ovr_ctx;
     ep.ovr_bs = a.ovr_batch_stride;

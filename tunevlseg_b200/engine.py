@@ -95,6 +95,11 @@ FUSE_OVERWRITE = os.environ.get("TVS_FUSE_OVERWRITE", "1") != "0"
 
 # TVS_TAIL=0: run the bottom block's backward on every row (A/B measurements); default: prompt rows only
 TAIL_PRUNE = os.environ.get("TVS_TAIL", "1") != "0"
+# TVS_PRE_DGELU=1 (experiment, off): the fc1 epilogue of a 16-bit (vision) block saves QuickGELU'(u) instead of u and the fc2-dgrad
+# epilogue only multiplies by it (TVS_GEMM_PRE_DGELU / TVS_ACT_MULAUX).  Measured at M = 15 648: the dgrad GEMM 79.6 -> 77.2 us,
+# the fc1 GEMM 80.4 -> 84.9 us, step 9.37 vs 9.37 ms: what separates the dGELU epilogue from the plain one (56.3 us) is the 96 MB
+# read of the saved tensor through the LSU (64-byte segments per thread), not the MUFU + 8 operations per element.
+PRE_DGELU = os.environ.get("TVS_PRE_DGELU", "0") == "1"
 
 
 def split_bf16(w: torch.Tensor, head_only: bool = False):
@@ -304,8 +309,9 @@ def encoder_layer_fwd(pk: PackedLayer, x, B, S, causal, key_mask, eps, save: boo
     abi.layernorm_fwd(x1, pk.g2, pk.be2, eps, y_f32=ln if hi else None, y_bf16=None if hi else ln, mean=mean2, rstd=rstd2, round_tf32=hi)
     u = _e((M, F), BF16, x)
     a = _e((M, F), adt, x)
+    # (TVS_PRE_DGELU=1: `u` receives QuickGELU'(pre-activation) and the fc2-dgrad epilogue multiplies by it - see PRE_DGELU)
     abi.gemm(ln, pk.w1_32 if hi else pk.w1, bias=pk.b1, pre_bf16=u if save else None, out_f32=a if hi else None,
-             out_bf16=None if hi else a, act=abi.ACT_QGELU, round_out=hi)
+             out_bf16=None if hi else a, act=abi.ACT_QGELU, round_out=hi, pre_is_grad=(save and not hi and PRE_DGELU))
     x2 = _e((M, D), F32, x)
     fuse = overwrite is not None and not hi and D % 32 == 0 and FUSE_OVERWRITE
     abi.gemm(a, pk.w2_32 if hi else pk.w2, bias=pk.b2, residual=x1, out_f32=x2,
@@ -340,7 +346,7 @@ def encoder_layer_bwd(pk: PackedLayer, sv: Saved, g, g16, B, S, causal, key_mask
         abi.gemm(g1, pk.wo_t32, out_f32=datt if pk.attn32 else None, out_bf16=None if pk.attn32 else datt)
     else:
         du = _e((M, F), BF16, g)
-        abi.gemm(g16, pk.w2_t, aux_bf16=sv.u, out_bf16=du, act=abi.ACT_DQGELU)
+        abi.gemm(g16, pk.w2_t, aux_bf16=sv.u, out_bf16=du, act=abi.ACT_MULAUX if PRE_DGELU else abi.ACT_DQGELU)
         dln = _e((M, D), BF16, g)
         abi.gemm(du, pk.w1_t, out_bf16=dln)
         g1, g1_16 = _e((M, D), F32, g), _e((M, D), BF16, g)
