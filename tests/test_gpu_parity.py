@@ -83,9 +83,9 @@ def test_small_long_prompt_truncation():
     _run_case("coop_deep", SMALL, B=2, L=76, seed=5)
 
 
-@pytest.mark.parametrize("case", ["maple", "vpt", "coop"])
+@pytest.mark.parametrize("case", ["maple", "vpt", "coop", "shared_separate", "shared_attn", "cocoop", "coop_deep"])
 def test_full_geometry(case):
-    """ViT-B/16 @ 352^2 (the BASELINE.json geometry), B=2 - the oracle still finishes in seconds."""
+    """ViT-B/16 @ 352^2 (the BASELINE.json geometry), B=2 - the oracle still finishes in seconds.  All learner families."""
     _run_case(case, FULL, B=2, L=8, seed=3)
 
 
