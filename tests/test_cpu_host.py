@@ -644,3 +644,34 @@ def test_no_freeze_last_layer_composition_over_cpu_abi_emulation(case, monkeypat
         pk = f"context_learner.{k}"
         if pk in named and p_ref.grad is not None and p_ref.grad.abs().max() > 0:
             assert ((named[pk].grad - p_ref.grad).norm() / p_ref.grad.norm()).item() < 5e-2, pk
+
+
+def test_nvtx_ranges_bracket_library_calls_and_phases():
+    """TVS_NVTX=1: every library call and every step phase is bracketed by an NVTX range (pushed and popped even when the call
+    raises - here it does, there is no GPU).  Read once at import: exercised in a fresh interpreter."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+log = []
+torch.cuda.nvtx.range_push = lambda name: log.append(("push", name))
+torch.cuda.nvtx.range_pop = lambda: log.append(("pop", None))
+from tunevlseg_b200 import abi, engine
+assert abi.NVTX
+try:
+    abi.cast_bf16(torch.zeros(4, 4), torch.zeros(4, 4, dtype=torch.bfloat16))
+except abi.TvsError:
+    pass
+with abi.nvtx_range("vision_tower.fwd"):
+    pass
+assert log == [("push", "tvs.cast_bf16"), ("pop", None), ("push", "vision_tower.fwd"), ("pop", None)], log
+assert engine.VisionTowerFn.forward.__name__ == "forward"
+print("ok")
+""" % root
+    env = dict(os.environ, TVS_NVTX="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
