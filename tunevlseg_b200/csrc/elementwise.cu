@@ -239,13 +239,30 @@ film_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
         float sm = 0.f, sa = 0.f;
         if (d < D && grp < ngrp) {
             const float m = mul[static_cast<long long>(b) * D + d];
-            for (int s = grp; s < S; s += ngrp) {
+            // four rows per trip, all eight loads issued before the first use: with one row per trip the ~30 dependent DRAM round
+            // trips of a thread were the kernel (24.6 us for 12 MB at B = 32); same summation order per accumulator pair as before
+            // is NOT kept - the partial sums are combined at the end (fp32, fixed order: deterministic)
+            float sm1 = 0.f, sa1 = 0.f, sm2 = 0.f, sa2 = 0.f, sm3 = 0.f, sa3 = 0.f;
+            int s = grp;
+            for (; s + 3 * ngrp < S; s += 4 * ngrp) {
+                const long long o0 = (static_cast<long long>(b) * S + s) * D + d, st = static_cast<long long>(ngrp) * D;
+                const float g0 = __ldcs(dy + o0), g1 = __ldcs(dy + o0 + st), g2 = __ldcs(dy + o0 + 2 * st), g3 = __ldcs(dy + o0 + 3 * st);
+                const float x0 = __ldcs(x + o0), x1 = __ldcs(x + o0 + st), x2 = __ldcs(x + o0 + 2 * st), x3 = __ldcs(x + o0 + 3 * st);
+                sm = fmaf(g0, x0, sm); sa += g0;
+                sm1 = fmaf(g1, x1, sm1); sa1 += g1;
+                sm2 = fmaf(g2, x2, sm2); sa2 += g2;
+                sm3 = fmaf(g3, x3, sm3); sa3 += g3;
+                dx[o0] = m * g0; dx[o0 + st] = m * g1; dx[o0 + 2 * st] = m * g2; dx[o0 + 3 * st] = m * g3;
+            }
+            for (; s < S; s += ngrp) {
                 const long long off = (static_cast<long long>(b) * S + s) * D + d;
                 const float g = dy[off];
-                sm += g * x[off];
+                sm = fmaf(g, x[off], sm);
                 sa += g;
                 dx[off] = m * g;
             }
+            sm = (sm + sm1) + (sm2 + sm3);
+            sa = (sa + sa1) + (sa2 + sa3);
         }
         sm_m[threadIdx.x] = sm;
         sm_a[threadIdx.x] = sa;
