@@ -46,8 +46,15 @@ int sm_count() {
 // graph of ~640 kernel nodes) it changes nothing - 11.41 / 11.29 ms with, 11.35 / 11.32 ms without - so the inter-kernel
 // gap is not what the step is waiting for; the plumbing stays for kernels with longer prologues.
 bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("TVS_PDL"); return e && e[0] == '1'; }();
+    static const bool on = [] { const char* e = getenv("TVS_PDL"); return e && (e[0] == '1' || e[0] == '2'); }();
     return on;
+}
+// (round 2, persistent attention kernels in place: TVS_PDL=1 9.63 vs 9.35 ms, TVS_PDL=2 9.44-9.56 vs 9.43 ms - still no gain.)
+// TVS_PDL=2: only launches of at most this many CTAs (the text tower's and the decoder's small kernels - a persistent GEMM has one
+// CTA per SM) are launched programmatically; 0 = no limit (TVS_PDL=1)
+int pdl_max_ctas() {
+    static const int n = [] { const char* e = getenv("TVS_PDL"); return (e && e[0] == '2') ? 128 : 0; }();
+    return n;
 }
 
 }  // namespace tvs

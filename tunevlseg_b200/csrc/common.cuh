@@ -39,6 +39,7 @@ int sm_count();
 // pdl_wait() until the predecessor has completed and its writes are visible.  Only kernels that call pdl_wait() before
 // their first global-memory access may be launched this way.
 bool pdl_enabled();
+int pdl_max_ctas();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -59,7 +60,7 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
         attr[n].val.clusterDim.z = 1;
         ++n;
     }
-    if (pdl_enabled()) {
+    if (pdl_enabled() && (pdl_max_ctas() == 0 || static_cast<long long>(grid.x) * grid.y * grid.z <= pdl_max_ctas())) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;
